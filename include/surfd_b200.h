@@ -1,0 +1,124 @@
+/* surfd_b200.h -- C ABI of the B200-native Surf-D generation hot path.
+ *
+ * The reference (Yzmblog/SurfD) has no FFI registry; its hot path sits behind three Python call
+ * boundaries.  Each entry point below names the reference interface it replaces.
+ * Conventions: every pointer marked "dev" is CUDA device memory owned by the caller (torch tensors
+ * in the shipped host code); the library never frees caller memory, never throws, and returns an
+ * int status: 0 ok, >0 domain status (see SURFD_* below), <0 = -(cudaError_t).  `stream` is a
+ * cudaStream_t passed as void*.  Work is stream-ordered; calls that must report a count to the host
+ * (documented per function) synchronise that stream once.  One host thread per GPU.
+ */
+#ifndef SURFD_B200_H
+#define SURFD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SURFD_OK 0
+#define SURFD_EMPTY_SURFACE 1   /* reference: RuntimeError("No surface found ...") _marching_cubes_lewiner.py:130-131 */
+#define SURFD_CAPACITY 2        /* output buffers too small; *n_v / *n_f hold the required sizes */
+#define SURFD_QUEUE_OVERFLOW 3  /* internal BFS queue bound exceeded (pathological field) */
+#define SURFD_BAD_ARGUMENT 4    /* reference: ValueError on bad shapes _marching_cubes_lewiner.py:102-105 */
+
+int surfd_version(void);
+/* last CUDA / argument error text of the calling thread (static buffer) */
+const char* surfd_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Decoder: CoordsEncoder + CbnDecoder + udf_func closure
+ *   AutoEncoder/models/coordsenc.py:34-51, AutoEncoder/models/cbndec.py:16-134,
+ *   sample/generate_uncond.py:96-101 (udf = (1 - sigmoid(logit)) * 0.1)
+ * `packed` (host or device pointer, see `packed_on_device`) is the float32 blob produced by
+ * surfd_b200.decoder.pack_decoder(): fc_p W[512][64] (63 padded), b[512]; 5x{fc_0 W[512][512], b,
+ * fc_1 W, b}; fc_out w[512], b[4]; 11x CBN {Wg[512][L], bg[512], Wb[512][L], bb[512], mean[512], var[512]}.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct surfd_decoder surfd_decoder;
+
+int surfd_dec_create(const float* packed, size_t n_floats, int latent_dim, int packed_on_device,
+                     int max_chunk_points, surfd_decoder** out);
+void surfd_dec_destroy(surfd_decoder* d);
+/* size of the packed blob in floats for a latent dimension */
+size_t surfd_dec_packed_floats(int latent_dim);
+
+/* Fold the conditional batch-norm of one shape: s = gamma(z)/sqrt(var+1e-5), t = beta(z) - s*mean
+ * (cbndec.py:68-82).  lat_dev: [L] float32 dev.  Must precede queries for that shape. */
+int surfd_dec_set_latent(surfd_decoder* d, const float* lat_dev, void* stream);
+
+/* precision: 0 = fp32 FFMA (parity mode), 1 = TF32 tcgen05 tensor cores (fast mode) */
+int surfd_dec_set_precision(surfd_decoder* d, int mode);
+
+/* udf (and optionally -normalize(d udf/dx), meshudf.py:231-251) at explicit points.
+ * pts_dev [M][3]; udf_dev [M]; grad_dev [M][3] or NULL.  Replaces udf_func / sample_udf /
+ * sample_grads (meshudf.py:209-251) for the (CbnDecoder, latent) closure. */
+int surfd_udf_query(surfd_decoder* d, const float* pts_dev, int64_t M, float* udf_dev, float* grad_dev,
+                    void* stream);
+
+/* Whole lattice of one shape.  mode 0: dense get_udf_and_grads (meshudf.py:254-304);
+ * mode 1: coarse-to-fine GridFiller.fill_grid (meshudf.py:36-206).  udf_dev [N^3], grad_dev [N^3][3]
+ * (zero where not evaluated), both also clamped like meshudf.py:342.  counts (host, may be NULL):
+ * [0] udf evaluations, [1] gradient evaluations.  Synchronises `stream` (level sizes are read back). */
+int surfd_udf_lattice(surfd_decoder* d, int N, int mode, double max_dist, float* udf_dev, float* grad_dev,
+                      int64_t* counts_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Marching cubes: meshudf/_marching_cubes_lewiner_cy.pyx marching_cubes_udf (:1115-1773) behind
+ * udf_mc_lewiner (_marching_cubes_lewiner.py:87-154).  Output numbering is the reference's own
+ * (traversal order).  Vertices are float32 pyx-level vertices (x,y,z)=(axis2,axis1,axis0) in index
+ * units (the wrapper's fliplr/spacing is applied by the host shell exactly as numpy does); faces
+ * int32 in raw pyx order.  surfd_mc_udf synchronises `stream` to read the counts.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct surfd_mc surfd_mc;
+int surfd_mc_create(surfd_mc** out);
+void surfd_mc_destroy(surfd_mc* m);
+/* Runs classification + ordered replay into buffers owned by the handle (sized from the candidate
+ * count) and reports the vertex / face counts; surfd_mc_fetch() then copies them to caller memory. */
+int surfd_mc_udf(surfd_mc* m, const float* udf_dev, const float* grad_dev, int N, int64_t* n_v, int64_t* n_f,
+                 int64_t* stats_host /* [8] or NULL: n_cand, n_seed, n_accept, n_unsure, n_nontrivial */, void* stream);
+int surfd_mc_fetch(surfd_mc* m, float* verts_dev /* [n_v][3] */, int32_t* faces_dev /* [n_f][3] */, void* stream);
+/* classification pass alone (HBM-bound scan, pyx:1157-1158,1215-1218): candidate bitmask words
+ * [ceil(N^3/32)] and count; used by the benchmarks / tests. */
+int surfd_mc_classify(surfd_mc* m, const float* udf_dev, int N, uint32_t* bits_dev_or_null,
+                      int64_t* n_cand_host, void* stream);
+
+/* UDF face filter of get_mesh_from_udf (meshudf.py:356-379): evaluates the decoder at both end
+ * points and the midpoint of every face edge (9 points per face, float64 positions rounded to
+ * float32 like `torch.from_numpy(points).float()`), keep[f] = 0 if any udf > 1/N.
+ * verts64_dev [V][3] float64 final vertex positions, faces_dev [F][3] int32. */
+int surfd_face_filter(surfd_decoder* d, const double* verts64_dev, const int32_t* faces_dev, int64_t n_f,
+                      int N, uint8_t* keep_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sampler: GaussianDiffusion.p_sample_loop over MDM/UNetModel
+ *   diffusion/gaussian_diffusion.py:570-708 (loop), :471-520 (p_sample), :258-363 (p_mean_variance)
+ *   diffusion/respace.py:63-132, models/mdm.py:91-110, models/openaimodel.py:710-749
+ * ------------------------------------------------------------------------------------------- */
+typedef struct surfd_unet surfd_unet;
+/* packed: float32 blob from surfd_b200.unet.pack_unet() (layout in DESIGN.md); L = 32 or 64 */
+int surfd_unet_create(const float* packed, size_t n_floats, int packed_on_device, int L, int max_batch,
+                      surfd_unet** out);
+void surfd_unet_destroy(surfd_unet* u);
+size_t surfd_unet_packed_floats(void);
+/* one model evaluation x0_hat = model(x_t, t, context/labels): teacher-forced parity entry.
+ * x_dev [B][L]; t_dev [B] int64 (already mapped through timestep_map); context_dev [B][512] or NULL;
+ * labels_dev [B] int64 or NULL; out_dev [B][L]. */
+int surfd_unet_forward(surfd_unet* u, int B, const float* x_dev, const int64_t* t_dev,
+                       const float* context_dev, const int64_t* labels_dev, float* out_dev, void* stream);
+/* full reverse process.  coef_dev [3][n_steps] float32: posterior_mean_coef1, posterior_mean_coef2,
+ * exp(0.5*posterior_log_variance_clipped) (index = spaced step); tmap_dev [n_steps] int64;
+ * noise_dev [n_steps+1][B][L]: row 0 = x_T, row 1+k = the randn_like draw of loop iteration k
+ * (iteration k handles step index n_steps-1-k); guidance: 1 = single forward, otherwise the
+ * reference's two-forward CFG combination (models/cfg_sampler.py:19-26) is replayed. */
+int surfd_sample(surfd_unet* u, int B, int n_steps, const int64_t* tmap_dev, const float* coef_dev,
+                 const float* noise_dev, const float* context_dev, const int64_t* labels_dev,
+                 float guidance, float* out_dev, void* stream);
+
+/* kernel-launch counter (all kernels launched by this library since load / last reset) */
+int64_t surfd_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,722 @@
+// decoder.cu -- fused-epilogue point-MLP (CoordsEncoder + CbnDecoder + udf_func) and its input gradient,
+// plus the lattice drivers (dense and GridFiller-equivalent) and the UDF face filter.
+//
+// Reference being replaced (read-only, /root/reference):
+//   AutoEncoder/models/coordsenc.py:34-51      positional encoding 3 -> 63
+//   AutoEncoder/models/cbndec.py:16-47,68-103  fc_p, 5 x ConditionalResnetBlock1d, CBN, fc_out
+//   sample/generate_uncond.py:96-101           udf = (1 - sigmoid(logit)) * 0.1
+//   meshudf/meshudf.py:209-251                 sample_udf / sample_grads (-normalize(autograd grad))
+//   meshudf/meshudf.py:36-206                  GridFiller (coarse-to-fine query schedule)
+//   meshudf/meshudf.py:254-304                 get_udf_and_grads (dense schedule)
+//   meshudf/meshudf.py:356-379                 UDF face filter
+//
+// Layout in HBM: activations are [points][512] fp32 row-major (K contiguous), weights [out][in]
+// row-major exactly as the checkpoint's Conv1d(k=1) tensors, plus a transposed copy for the
+// input-gradient pass.  The conditional batch-norm is folded once per shape into (s,t) so a layer is
+//   C = A * W^T + b (+R);   A_next = relu(s (.) C + t)
+// with the activation written by the producing GEMM's epilogue (no separate elementwise passes).
+#include <math.h>
+#include <vector>
+
+#include "common.cuh"
+
+namespace surfd {
+
+constexpr int HID = 512;
+constexpr int ENC = 64;  // 63 padded to 64
+constexpr int NBLK = 5;
+constexpr int NCBN = 11;
+
+// ------------------------------------------------------------------------------------------------
+// SGEMM (NT): C[m][n] = sum_k A[m][k] * W[n][k], fp32 FFMA, 128x128x16 tiles, 8x8 per thread.
+// ------------------------------------------------------------------------------------------------
+struct Epilogue {
+  const float* bias;    // [N] or null
+  const float* mask;    // [M][ld] activation buffer: v = mask>0 ? v*mscale[n] : 0   (relu/CBN backward)
+  const float* mscale;  // [N]
+  const float* R;       // residual [M][ld] or null (may alias C)
+  float* C;             // [M][ld] or null
+  float* act;           // [M][ld] or null : relu(s2[n]*v + t2[n])
+  const float* s2;
+  const float* t2;
+  int ld;
+};
+
+constexpr int BM = 128, BN = 128, BK = 16;
+
+__global__ void __launch_bounds__(256, 2)
+sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw, int M, int N, int K,
+                Epilogue e) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int m0 = (blockIdx.x / n_tiles) * BM;
+  const int n0 = (blockIdx.x % n_tiles) * BN;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  // global -> register staging: 2 float4 of A and 2 of W per thread per k-tile
+  float4 ra[2], rb[2];
+  const int lrow0 = tid >> 2, lkq = (tid & 3) * 4;  // rows lrow0 and lrow0+64
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = lrow0 + h * 64;
+      const int gm = m0 + row;
+      ra[h] = gm < M ? *reinterpret_cast<const float4*>(A + (size_t)gm * lda + k0 + lkq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int gn = n0 + row;
+      rb[h] = gn < N ? *reinterpret_cast<const float4*>(W + (size_t)gn * ldw + k0 + lkq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = lrow0 + h * 64;
+      As[buf][lkq + 0][row] = ra[h].x; As[buf][lkq + 1][row] = ra[h].y;
+      As[buf][lkq + 2][row] = ra[h].z; As[buf][lkq + 3][row] = ra[h].w;
+      Bs[buf][lkq + 0][row] = rb[h].x; Bs[buf][lkq + 1][row] = rb[h].y;
+      Bs[buf][lkq + 2][row] = rb[h].z; Bs[buf][lkq + 3][row] = rb[h].w;
+    }
+  };
+
+  const int KT = K / BK;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  int cur = 0;
+  for (int kt = 0; kt < KT; ++kt) {
+    if (kt + 1 < KT) load_tile((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < KT) store_tile(cur ^ 1);
+    __syncthreads();
+    cur ^= 1;
+  }
+
+  // epilogue
+#pragma unroll
+  for (int jh = 0; jh < 2; ++jh) {
+    const int n = n0 + jh * 64 + tx * 4;
+    if (n >= N) continue;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), ms = bias, s2 = bias, t2 = bias;
+    if (e.bias) bias = *reinterpret_cast<const float4*>(e.bias + n);
+    if (e.mask) ms = *reinterpret_cast<const float4*>(e.mscale + n);
+    if (e.act) { s2 = *reinterpret_cast<const float4*>(e.s2 + n); t2 = *reinterpret_cast<const float4*>(e.t2 + n); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      if (m >= M) continue;
+      const size_t off = (size_t)m * e.ld + n;
+      float4 v = make_float4(acc[i][jh * 4 + 0] + bias.x, acc[i][jh * 4 + 1] + bias.y, acc[i][jh * 4 + 2] + bias.z,
+                             acc[i][jh * 4 + 3] + bias.w);
+      if (e.mask) {
+        const float4 mk = *reinterpret_cast<const float4*>(e.mask + off);
+        v.x = mk.x > 0.f ? v.x * ms.x : 0.f; v.y = mk.y > 0.f ? v.y * ms.y : 0.f;
+        v.z = mk.z > 0.f ? v.z * ms.z : 0.f; v.w = mk.w > 0.f ? v.w * ms.w : 0.f;
+      }
+      if (e.R) {
+        const float4 r = *reinterpret_cast<const float4*>(e.R + off);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      if (e.C) *reinterpret_cast<float4*>(e.C + off) = v;
+      if (e.act) {
+        float4 a;
+        a.x = fmaxf(fmaf(s2.x, v.x, t2.x), 0.f); a.y = fmaxf(fmaf(s2.y, v.y, t2.y), 0.f);
+        a.z = fmaxf(fmaf(s2.z, v.z, t2.z), 0.f); a.w = fmaxf(fmaf(s2.w, v.w, t2.w), 0.f);
+        *reinterpret_cast<float4*>(e.act + off) = a;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+
+// CBN fold for one shape: s = gamma(z)/sqrt(var+eps), t = beta(z) - s*mean  (cbndec.py:68-82; BatchNorm1d eval)
+__global__ void fold_cbn_kernel(const float* __restrict__ cbn, int L, const float* __restrict__ lat,
+                                float* __restrict__ s_out, float* __restrict__ t_out) {
+  const int layer = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= HID) return;
+  const size_t per = (size_t)HID * L * 2 + 4 * HID;
+  const float* base = cbn + per * layer;
+  const float* Wg = base;
+  const float* bg = Wg + (size_t)HID * L;
+  const float* Wb = bg + HID;
+  const float* bb = Wb + (size_t)HID * L;
+  const float* mean = bb + HID;
+  const float* var = mean + HID;
+  float g = 0.f, b = 0.f;
+  for (int k = 0; k < L; ++k) {
+    const float z = lat[k];
+    g = fmaf(Wg[(size_t)c * L + k], z, g);
+    b = fmaf(Wb[(size_t)c * L + k], z, b);
+  }
+  g += bg[c];
+  b += bb[c];
+  const float inv = 1.0f / sqrtf(var[c] + 1e-5f);
+  const float s = g * inv;
+  s_out[layer * HID + c] = s;
+  t_out[layer * HID + c] = b - s * mean[c];
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
+  for (int j = 0; j < 32; j += 8)
+    if (x < cols && y + j < rows) tile[threadIdx.y + j][threadIdx.x] = in[(size_t)(y + j) * cols + x];
+  __syncthreads();
+  x = blockIdx.y * 32 + threadIdx.x; y = blockIdx.x * 32 + threadIdx.y;
+  for (int j = 0; j < 32; j += 8)
+    if (x < rows && y + j < cols) out[(size_t)(y + j) * rows + x] = tile[threadIdx.x][threadIdx.y + j];
+}
+
+// Lattice coordinates exactly as the reference builds them: fp32(idx) * fp32(voxel) rounded, then + (-1)
+// rounded -- no FMA (meshudf.py:73-75, 285-286).
+// src: level-linear indices (q in [0,NL^3)) or null for the dense run [base, base+M).
+__global__ void lattice_points_kernel(const int32_t* __restrict__ src, int64_t base, int M, int NL, int stride, int N,
+                                      float voxel, float origin, float* __restrict__ pts, int32_t* __restrict__ dst) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int64_t q = src ? (int64_t)src[m] : base + m;
+  const int i2 = (int)(q % NL), i1 = (int)((q / NL) % NL), i0 = (int)(q / ((int64_t)NL * NL));
+  const int a0 = i0 * stride, a1 = i1 * stride, a2 = i2 * stride;
+  pts[3 * m + 0] = __fadd_rn(__fmul_rn((float)a0, voxel), origin);
+  pts[3 * m + 1] = __fadd_rn(__fmul_rn((float)a1, voxel), origin);
+  pts[3 * m + 2] = __fadd_rn(__fmul_rn((float)a2, voxel), origin);
+  dst[m] = (int32_t)(((int64_t)a0 * N + a1) * N + a2);
+}
+
+// CoordsEncoder.encode: [x, sin(x*2^j), cos(x*2^j)]_{j=0..9}; blocks of 3 (xyz); column 63 is zero padding.
+__global__ void encode_kernel(const float* __restrict__ pts, int M, float* __restrict__ E) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float p[3] = {pts[3 * m], pts[3 * m + 1], pts[3 * m + 2]};
+  float* e = E + (size_t)m * ENC;
+  float v[ENC];
+  v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+  float f = 1.0f;
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float arg = p[a] * f;
+      v[3 + 6 * j + a] = sinf(arg);
+      v[3 + 6 * j + 3 + a] = cosf(arg);
+    }
+    f *= 2.0f;
+  }
+  v[63] = 0.f;
+#pragma unroll
+  for (int k = 0; k < ENC; k += 4) *reinterpret_cast<float4*>(e + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+}
+
+// fc_out + sigmoid + udf scaling; one warp per point.
+// udf = (1 - sigmoid(logit)) * 0.1 ; dudf = (-0.1 * (1-p)) * p  (sigmoid backward order of torch autograd)
+__global__ void out_kernel(const float* __restrict__ act, int M, const float* __restrict__ wout, const float* __restrict__ bout,
+                           float* __restrict__ udf, const int32_t* __restrict__ dst, float* __restrict__ dudf) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float* a = act + (size_t)warp * HID;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < HID / 128; ++k) {
+    const float4 x = *reinterpret_cast<const float4*>(a + k * 128 + lane * 4);
+    const float4 w = *reinterpret_cast<const float4*>(wout + k * 128 + lane * 4);
+    s = fmaf(x.x, w.x, s); s = fmaf(x.y, w.y, s); s = fmaf(x.z, w.z, s); s = fmaf(x.w, w.w, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const float logit = s + bout[0];
+    const float p = 1.0f / (1.0f + expf(-logit));
+    const float u = (1.0f - p) * 0.1f;
+    udf[dst ? dst[warp] : warp] = u;
+    if (dudf) dudf[warp] = (-0.1f * (1.0f - p)) * p;
+  }
+}
+
+// d logit / d net_final = wout (.) relu'(.) (.) s_final
+__global__ void bwd_init_kernel(const float* __restrict__ act, int64_t total, const float* __restrict__ wout,
+                                const float* __restrict__ s, float* __restrict__ dnet) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= total) return;
+  const int n = (int)(i % HID);
+  const float4 a = *reinterpret_cast<const float4*>(act + i);
+  const float4 w = *reinterpret_cast<const float4*>(wout + n);
+  const float4 sc = *reinterpret_cast<const float4*>(s + n);
+  float4 r;
+  r.x = a.x > 0.f ? w.x * sc.x : 0.f; r.y = a.y > 0.f ? w.y * sc.y : 0.f;
+  r.z = a.z > 0.f ? w.z * sc.z : 0.f; r.w = a.w > 0.f ? w.w * sc.w : 0.f;
+  *reinterpret_cast<float4*>(dnet + i) = r;
+}
+
+// chain rule through the positional encoding, the sigmoid/udf scaling and -F.normalize(., eps=1e-12)
+__global__ void grad_finish_kernel(const float* __restrict__ de, const float* __restrict__ pts, const float* __restrict__ dudf,
+                                   int M, float* __restrict__ grad, const int32_t* __restrict__ dst) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* d = de + (size_t)m * ENC;
+  float g[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float x = pts[3 * m + a];
+    float acc = d[a];
+    float f = 1.0f;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const float arg = x * f;
+      acc += d[3 + 6 * j + a] * (cosf(arg) * f);
+      acc += d[3 + 6 * j + 3 + a] * (-sinf(arg) * f);
+      f *= 2.0f;
+    }
+    g[a] = acc * dudf[m];
+  }
+  const float nrm = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+  const float den = fmaxf(nrm, 1e-12f);
+  const size_t o = (size_t)(dst ? dst[m] : m) * 3;
+  grad[o + 0] = -(g[0] / den);
+  grad[o + 1] = -(g[1] / den);
+  grad[o + 2] = -(g[2] / den);
+}
+
+// bit mask of lattice points with udf < thr (word = 32 consecutive points)
+__global__ void below_bits_kernel(const float* __restrict__ udf, int64_t n, float thr, uint32_t* __restrict__ bits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool p = i < n && udf[i] < thr;
+  const uint32_t w = __ballot_sync(0xffffffffu, p);
+  if ((threadIdx.x & 31) == 0 && i < n) bits[i >> 5] = w;
+}
+
+// ---- GridFiller-equivalent schedule (meshudf.py:123-206) -----------------------------------------
+// level l has NL^3 coarse points (stride S = N/NL).  active_l(q) = (l==0) or (active_{l-1} & close_{l-1})(parent);
+// a point needs a query when it is active and was not already a coarser-level point.
+__global__ void gf_mark_kernel(int level, int NL, const uint8_t* __restrict__ active_prev, const uint8_t* __restrict__ close_prev,
+                               uint8_t* __restrict__ active, uint32_t* __restrict__ need_bits) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = (int64_t)NL * NL * NL;
+  bool need = false;
+  if (q < n) {
+    bool act = true;
+    bool fresh = true;
+    if (level > 0) {
+      const int i2 = (int)(q % NL), i1 = (int)((q / NL) % NL), i0 = (int)(q / ((int64_t)NL * NL));
+      const int NP = NL >> 1;
+      const int64_t par = ((int64_t)(i0 >> 1) * NP + (i1 >> 1)) * NP + (i2 >> 1);
+      act = active_prev[par] && close_prev[par];
+      fresh = ((i0 | i1 | i2) & 1) != 0;
+    }
+    if (active) active[q] = act ? 1 : 0;
+    need = act && fresh;
+  }
+  const uint32_t w = __ballot_sync(0xffffffffu, need);
+  if ((threadIdx.x & 31) == 0 && q < n) need_bits[q >> 5] = w;
+}
+
+__global__ void gf_close_kernel(int NL, int stride, int N, const float* __restrict__ udf, const uint8_t* __restrict__ active,
+                                float thr, uint8_t* __restrict__ close) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (int64_t)NL * NL * NL) return;
+  uint8_t c = 0;
+  if (active[q]) {
+    const int i2 = (int)(q % NL), i1 = (int)((q / NL) % NL), i0 = (int)(q / ((int64_t)NL * NL));
+    const float u = udf[((int64_t)i0 * stride * N + (int64_t)i1 * stride) * N + (int64_t)i2 * stride];
+    c = fabsf(u) < thr ? 1 : 0;
+  }
+  close[q] = c;
+}
+
+struct GfLevels {
+  int n_levels;            // number of non-final levels
+  int NL[8];
+  const uint8_t* active[8];
+  const uint8_t* close[8];
+};
+
+// far blocks copy their anchor's value (meshudf.py:192-194); every lattice point walks the levels coarse->fine.
+__global__ void gf_resolve_kernel(GfLevels lv, int N, float* __restrict__ udf) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (int64_t)N * N * N) return;
+  const int i2 = (int)(p % N), i1 = (int)((p / N) % N), i0 = (int)(p / ((int64_t)N * N));
+  for (int l = 0; l < lv.n_levels; ++l) {
+    const int NL = lv.NL[l];
+    const int S = N / NL;
+    const int q0 = i0 / S, q1 = i1 / S, q2 = i2 / S;
+    const int64_t q = ((int64_t)q0 * NL + q1) * NL + q2;
+    if (!lv.active[l][q]) return;  // unreachable: an inactive anchor implies a coarser far block (already returned)
+    if (!lv.close[l][q]) {
+      const int64_t a = ((int64_t)q0 * S * N + (int64_t)q1 * S) * N + (int64_t)q2 * S;
+      if (a != p) udf[p] = udf[a];
+      return;
+    }
+  }
+}
+
+// face filter points (meshudf.py:358-367): for face f and k in [0,9): edge e = k%3 -> (v[e], v[(e+1)%3]);
+// k/3: 0 first endpoint, 1 second endpoint, 2 midpoint (float64 math, then float32 like .float()).
+__global__ void face_points_kernel(const double* __restrict__ verts, const int32_t* __restrict__ faces, int64_t f0, int M,
+                                   float* __restrict__ pts) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int64_t f = f0 + m / 9;
+  const int k = m % 9;
+  const int e = k % 3, kind = k / 3;
+  const int32_t va = faces[3 * f + e], vb = faces[3 * f + (e + 1) % 3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double xa = verts[3 * (int64_t)va + a], xb = verts[3 * (int64_t)vb + a];
+    const double x = kind == 0 ? xa : (kind == 1 ? xb : (xa + xb) / 2);
+    pts[3 * m + a] = (float)x;
+  }
+}
+
+__global__ void face_keep_kernel(const float* __restrict__ udf, int n_faces, float thr, uint8_t* __restrict__ keep) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_faces) return;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) ok = ok && !(udf[(size_t)f * 9 + k] > thr);
+  keep[f] = ok ? 1 : 0;
+}
+
+}  // namespace surfd
+
+using namespace surfd;
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct surfd_decoder {
+  int L = 0;
+  int chunk = 0;
+  int precision = 0;
+  DevBuf weights;    // packed blob
+  DevBuf wT;         // transposes: WpT [64][512], then 5x{W0T, W1T}
+  DevBuf fold;       // s[11][512], t[11][512]
+  DevBuf acts;       // 11 x [chunk][512]
+  DevBuf net, dnet, dh, enc, de, pts, dudf, udf_tmp;
+  DevBuf dst;        // int32 [chunk]
+  DevBuf bits, list; // lattice masks / lists
+  DevBuf gf_state;   // per-level active/close bytes
+  Compactor comp;
+  bool latent_set = false;
+
+  const float* Wp() const { return weights.as<float>(); }
+  const float* bp() const { return Wp() + HID * ENC; }
+  const float* W0(int i) const { return bp() + HID + (size_t)i * 2 * (HID * HID + HID); }
+  const float* b0(int i) const { return W0(i) + HID * HID; }
+  const float* W1(int i) const { return b0(i) + HID; }
+  const float* b1(int i) const { return W1(i) + HID * HID; }
+  const float* wout() const { return bp() + HID + (size_t)NBLK * 2 * (HID * HID + HID); }
+  const float* bout() const { return wout() + HID; }
+  const float* cbn() const { return bout() + 4; }
+  const float* WpT() const { return wT.as<float>(); }
+  const float* W0T(int i) const { return WpT() + ENC * HID + (size_t)i * 2 * HID * HID; }
+  const float* W1T(int i) const { return W0T(i) + HID * HID; }
+  const float* s(int layer) const { return fold.as<float>() + layer * HID; }
+  const float* t(int layer) const { return fold.as<float>() + (NCBN + layer) * HID; }
+  float* act(int i) const { return acts.as<float>() + (size_t)i * chunk * HID; }
+};
+
+extern "C" size_t surfd_dec_packed_floats(int L) {
+  return (size_t)HID * ENC + HID + (size_t)NBLK * 2 * (HID * HID + HID) + HID + 4 +
+         (size_t)NCBN * ((size_t)HID * L * 2 + 4 * HID);
+}
+
+static int launch_gemm(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const Epilogue& e,
+                       cudaStream_t st) {
+  const int tiles = (int)(cdiv(M, BM) * cdiv(N, BN));
+  sgemm_nt_kernel<<<tiles, 256, 0, st>>>(A, lda, W, ldw, M, N, K, e);
+  SURFD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int surfd_dec_create(const float* packed, size_t n_floats, int L, int packed_on_device, int max_chunk,
+                                surfd_decoder** out) {
+  SURFD_REQUIRE(out != nullptr && packed != nullptr, "null argument");
+  SURFD_REQUIRE(L > 0 && L <= 4096, "latent_dim out of range");
+  SURFD_REQUIRE(n_floats == surfd_dec_packed_floats(L), "packed decoder blob has the wrong size");
+  if (max_chunk <= 0) max_chunk = 148 * 2 * 128;  // 4 full waves of 128x128 tiles at 2 CTAs/SM
+  max_chunk = (int)(cdiv(max_chunk, 128) * 128);
+  surfd_decoder* d = new surfd_decoder();
+  d->L = L;
+  d->chunk = max_chunk;
+  int st = 0;
+  auto fail = [&](int code) { surfd_dec_destroy(d); return code; };
+  if ((st = d->weights.reserve(n_floats * sizeof(float)))) return fail(st);
+  cudaError_t ce = cudaMemcpy(d->weights.p, packed, n_floats * sizeof(float),
+                              packed_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
+  const size_t c = (size_t)max_chunk;
+  if ((st = d->wT.reserve(((size_t)ENC * HID + (size_t)NBLK * 2 * HID * HID) * sizeof(float)))) return fail(st);
+  if ((st = d->fold.reserve((size_t)2 * NCBN * HID * sizeof(float)))) return fail(st);
+  if ((st = d->acts.reserve((size_t)NCBN * c * HID * sizeof(float)))) return fail(st);
+  if ((st = d->net.reserve(c * HID * sizeof(float)))) return fail(st);
+  if ((st = d->dnet.reserve(c * HID * sizeof(float)))) return fail(st);
+  if ((st = d->dh.reserve(c * HID * sizeof(float)))) return fail(st);
+  if ((st = d->enc.reserve(c * ENC * sizeof(float)))) return fail(st);
+  if ((st = d->de.reserve(c * ENC * sizeof(float)))) return fail(st);
+  if ((st = d->pts.reserve(c * 3 * sizeof(float)))) return fail(st);
+  if ((st = d->dudf.reserve(c * sizeof(float)))) return fail(st);
+  if ((st = d->udf_tmp.reserve(c * sizeof(float)))) return fail(st);
+  if ((st = d->dst.reserve(c * sizeof(int32_t)))) return fail(st);
+  if ((st = d->comp.init())) return fail(st);
+  // transposed weight copies for the input-gradient pass
+  {
+    dim3 blk(32, 8);
+    transpose_kernel<<<dim3(ENC / 32, HID / 32), blk>>>(d->Wp(), HID, ENC, const_cast<float*>(d->WpT()));
+    ++g_launch_count;
+    for (int i = 0; i < NBLK; ++i) {
+      transpose_kernel<<<dim3(HID / 32, HID / 32), blk>>>(d->W0(i), HID, HID, const_cast<float*>(d->W0T(i)));
+      transpose_kernel<<<dim3(HID / 32, HID / 32), blk>>>(d->W1(i), HID, HID, const_cast<float*>(d->W1T(i)));
+      g_launch_count += 2;
+    }
+    ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
+  }
+  *out = d;
+  return 0;
+}
+
+extern "C" void surfd_dec_destroy(surfd_decoder* d) {
+  if (!d) return;
+  d->weights.release(); d->wT.release(); d->fold.release(); d->acts.release(); d->net.release(); d->dnet.release();
+  d->dh.release(); d->enc.release(); d->de.release(); d->pts.release(); d->dudf.release(); d->udf_tmp.release();
+  d->dst.release(); d->bits.release(); d->list.release(); d->gf_state.release();
+  d->comp.destroy();
+  delete d;
+}
+
+extern "C" int surfd_dec_set_precision(surfd_decoder* d, int mode) {
+  SURFD_REQUIRE(d != nullptr, "null decoder");
+  SURFD_REQUIRE(mode == 0, "only precision mode 0 (fp32) is built in this version");
+  d->precision = mode;
+  return 0;
+}
+
+extern "C" int surfd_dec_set_latent(surfd_decoder* d, const float* lat_dev, void* stream) {
+  SURFD_REQUIRE(d != nullptr && lat_dev != nullptr, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* s = d->fold.as<float>();
+  fold_cbn_kernel<<<dim3(HID / 128, NCBN), 128, 0, st>>>(d->cbn(), d->L, lat_dev, s, s + NCBN * HID);
+  SURFD_CHECK_LAUNCH();
+  d->latent_set = true;
+  return 0;
+}
+
+// Forward over M (<= chunk) points already in d->pts.  keep_acts: store every layer's activation (for the
+// gradient pass); otherwise ping-pong two buffers.  Writes udf through `dst` (or densely when dst==null).
+static int dec_forward(surfd_decoder* d, int M, bool keep_acts, float* udf_out, const int32_t* dst, cudaStream_t st) {
+  float* E = d->enc.as<float>();
+  float* net = d->net.as<float>();
+  encode_kernel<<<(unsigned)cdiv(M, 128), 128, 0, st>>>(d->pts.as<float>(), M, E);
+  SURFD_CHECK_LAUNCH();
+  auto A = [&](int layer) { return keep_acts ? d->act(layer) : d->act(layer & 1); };
+  Epilogue e{};
+  e.ld = HID;
+  // net = fc_p(E);  act0 = relu(cbn_0(net))
+  e.bias = d->bp(); e.C = net; e.act = A(0); e.s2 = d->s(0); e.t2 = d->t(0);
+  SURFD_TRY(launch_gemm(E, ENC, d->Wp(), ENC, M, HID, ENC, e, st));
+  for (int i = 0; i < NBLK; ++i) {
+    // h = fc_0(act);  act' = relu(cbn_1(h))
+    Epilogue e0{};
+    e0.ld = HID; e0.bias = d->b0(i); e0.act = A(2 * i + 1); e0.s2 = d->s(2 * i + 1); e0.t2 = d->t(2 * i + 1);
+    SURFD_TRY(launch_gemm(A(2 * i), HID, d->W0(i), HID, M, HID, HID, e0, st));
+    // net += fc_1(act');  act'' = relu(cbn_next(net))
+    Epilogue e1{};
+    e1.ld = HID; e1.bias = d->b1(i); e1.R = net; e1.C = net; e1.act = A(2 * i + 2); e1.s2 = d->s(2 * i + 2); e1.t2 = d->t(2 * i + 2);
+    SURFD_TRY(launch_gemm(A(2 * i + 1), HID, d->W1(i), HID, M, HID, HID, e1, st));
+  }
+  out_kernel<<<(unsigned)cdiv((int64_t)M * 32, 256), 256, 0, st>>>(A(10), M, d->wout(), d->bout(), udf_out, dst,
+                                                                  keep_acts ? d->dudf.as<float>() : nullptr);
+  SURFD_CHECK_LAUNCH();
+  return 0;
+}
+
+// Input gradient for the M points of the last dec_forward(keep_acts=true).
+static int dec_backward(surfd_decoder* d, int M, float* grad_out, const int32_t* dst, cudaStream_t st) {
+  float* dnet = d->dnet.as<float>();
+  float* dh = d->dh.as<float>();
+  const int64_t total = (int64_t)M * HID;
+  bwd_init_kernel<<<(unsigned)cdiv(total / 4, 256), 256, 0, st>>>(d->act(10), total, d->wout(), d->s(10), dnet);
+  SURFD_CHECK_LAUNCH();
+  for (int i = NBLK - 1; i >= 0; --i) {
+    // dh = (dnet * W1) (.) relu'(act_{2i+1}) (.) s_{2i+1}
+    Epilogue e1{};
+    e1.ld = HID; e1.mask = d->act(2 * i + 1); e1.mscale = d->s(2 * i + 1); e1.C = dh;
+    SURFD_TRY(launch_gemm(dnet, HID, d->W1T(i), HID, M, HID, HID, e1, st));
+    // dnet += (dh * W0) (.) relu'(act_{2i}) (.) s_{2i}
+    Epilogue e0{};
+    e0.ld = HID; e0.mask = d->act(2 * i); e0.mscale = d->s(2 * i); e0.R = dnet; e0.C = dnet;
+    SURFD_TRY(launch_gemm(dh, HID, d->W0T(i), HID, M, HID, HID, e0, st));
+  }
+  Epilogue ee{};
+  ee.ld = ENC; ee.C = d->de.as<float>();
+  SURFD_TRY(launch_gemm(dnet, HID, d->WpT(), HID, M, ENC, HID, ee, st));
+  grad_finish_kernel<<<(unsigned)cdiv(M, 128), 128, 0, st>>>(d->de.as<float>(), d->pts.as<float>(), d->dudf.as<float>(), M,
+                                                            grad_out, dst);
+  SURFD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int surfd_udf_query(surfd_decoder* d, const float* pts_dev, int64_t M, float* udf_dev, float* grad_dev,
+                               void* stream) {
+  SURFD_REQUIRE(d && d->latent_set, "decoder latent not set");
+  SURFD_REQUIRE(M >= 0 && (M == 0 || (pts_dev && udf_dev)), "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t base = 0; base < M; base += d->chunk) {
+    const int m = (int)((M - base) < d->chunk ? (M - base) : d->chunk);
+    SURFD_CUDA(cudaMemcpyAsync(d->pts.p, pts_dev + 3 * base, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SURFD_TRY(dec_forward(d, m, grad_dev != nullptr, udf_dev + base, nullptr, st));
+    if (grad_dev) SURFD_TRY(dec_backward(d, m, grad_dev + 3 * base, nullptr, st));
+  }
+  return 0;
+}
+
+// evaluate udf (and optionally gradients) at lattice points given by a list of level-linear indices
+static int lattice_eval(surfd_decoder* d, const int32_t* list, int64_t base, int64_t count, int NL, int stride, int N,
+                        bool want_grad, float* udf_lat, float* grad_lat, cudaStream_t st) {
+  const float voxel = (float)(2.0 / (N - 1));
+  for (int64_t off = 0; off < count; off += d->chunk) {
+    const int m = (int)((count - off) < d->chunk ? (count - off) : d->chunk);
+    lattice_points_kernel<<<(unsigned)cdiv(m, 256), 256, 0, st>>>(list ? list + off : nullptr, base + off, m, NL, stride, N, voxel,
+                                                                 -1.0f, d->pts.as<float>(), d->dst.as<int32_t>());
+    SURFD_CHECK_LAUNCH();
+    if (!want_grad) {
+      SURFD_TRY(dec_forward(d, m, false, udf_lat, d->dst.as<int32_t>(), st));
+    } else {
+      // the forward is recomputed with stored activations (the reference's sample_grads also re-runs it);
+      // its udf output goes to a scratch buffer so the lattice values stay those of the first pass.
+      SURFD_TRY(dec_forward(d, m, true, d->udf_tmp.as<float>(), nullptr, st));
+      SURFD_TRY(dec_backward(d, m, grad_lat, d->dst.as<int32_t>(), st));
+    }
+  }
+  return 0;
+}
+
+static int lattice_grads(surfd_decoder* d, int N, float thr, float* udf_dev, float* grad_dev, int64_t* n_grad,
+                         cudaStream_t st) {
+  const int64_t n3 = (int64_t)N * N * N;
+  const int64_t words = cdiv(n3, 32);
+  SURFD_TRY(d->bits.reserve((size_t)words * sizeof(uint32_t)));
+  below_bits_kernel<<<(unsigned)cdiv(n3, 256), 256, 0, st>>>(udf_dev, n3, thr, d->bits.as<uint32_t>());
+  SURFD_CHECK_LAUNCH();
+  SURFD_TRY(d->comp.count(d->bits.as<uint32_t>(), words, st));
+  int64_t cnt = 0;
+  SURFD_TRY(d->comp.read_total(&cnt, st));
+  *n_grad = cnt;
+  if (cnt == 0) return 0;
+  SURFD_TRY(d->list.reserve((size_t)cnt * sizeof(int32_t)));
+  SURFD_TRY(d->comp.scatter(d->bits.as<uint32_t>(), words, d->list.as<int32_t>(), st));
+  return lattice_eval(d, d->list.as<int32_t>(), 0, cnt, N, 1, N, true, udf_dev, grad_dev, st);
+}
+
+extern "C" int surfd_udf_lattice(surfd_decoder* d, int N, int mode, double max_dist, float* udf_dev, float* grad_dev,
+                                 int64_t* counts_host, void* stream) {
+  SURFD_REQUIRE(d && d->latent_set, "decoder latent not set");
+  SURFD_REQUIRE(udf_dev && grad_dev, "null argument");
+  SURFD_REQUIRE(N >= 2 && N <= 1024, "N out of range");
+  SURFD_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (dense) or 1 (GridFiller)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n3 = (int64_t)N * N * N;
+  int64_t n_udf = 0, n_grad = 0;
+  SURFD_CUDA(cudaMemsetAsync(grad_dev, 0, (size_t)n3 * 3 * sizeof(float), st));
+  if (mode == 0) {
+    SURFD_TRY(lattice_eval(d, nullptr, 0, n3, N, 1, N, false, udf_dev, grad_dev, st));
+    n_udf = n3;
+    const float thr = (float)(max_dist - 1e-3);  // meshudf.py:295, compared in fp32
+    SURFD_TRY(lattice_grads(d, N, thr, udf_dev, grad_dev, &n_grad, st));
+  } else {
+    // levels 32, 64, ..., N   (meshudf.py:44: [32 * 2**i for i in range(int(log2(N) - 4))])
+    int n_lv = 0, NLs[8];
+    {
+      const int cnt = (int)(log2((double)N) - 4);
+      SURFD_REQUIRE(cnt >= 1 && cnt <= 8, "GridFiller needs N >= 32");
+      for (int i = 0; i < cnt; ++i) NLs[n_lv++] = 32 << i;
+      SURFD_REQUIRE(NLs[n_lv - 1] == N, "GridFiller mode needs N = 32 * 2^k");
+    }
+    SURFD_CUDA(cudaMemsetAsync(udf_dev, 0, (size_t)n3 * sizeof(float), st));
+    // per-level state bytes: active, close
+    size_t state_bytes = 0, offs_a[8], offs_c[8];
+    for (int l = 0; l < n_lv; ++l) {
+      const size_t nl3 = (size_t)NLs[l] * NLs[l] * NLs[l];
+      offs_a[l] = state_bytes; state_bytes += nl3;
+      offs_c[l] = state_bytes; state_bytes += nl3;
+    }
+    SURFD_TRY(d->gf_state.reserve(state_bytes));
+    uint8_t* sb = d->gf_state.as<uint8_t>();
+    SURFD_TRY(d->bits.reserve((size_t)cdiv(n3, 32) * sizeof(uint32_t)));
+    for (int l = 0; l < n_lv; ++l) {
+      const int NL = NLs[l];
+      const int stride = N / NL;
+      const int64_t nl3 = (int64_t)NL * NL * NL;
+      const int64_t words = cdiv(nl3, 32);
+      gf_mark_kernel<<<(unsigned)cdiv(nl3, 256), 256, 0, st>>>(l, NL, l ? sb + offs_a[l - 1] : nullptr, l ? sb + offs_c[l - 1] : nullptr,
+                                                              sb + offs_a[l], d->bits.as<uint32_t>());
+      SURFD_CHECK_LAUNCH();
+      SURFD_TRY(d->comp.count(d->bits.as<uint32_t>(), words, st));
+      int64_t cnt = 0;
+      SURFD_TRY(d->comp.read_total(&cnt, st));
+      n_udf += cnt;
+      if (cnt > 0) {
+        SURFD_TRY(d->list.reserve((size_t)cnt * sizeof(int32_t)));
+        SURFD_TRY(d->comp.scatter(d->bits.as<uint32_t>(), words, d->list.as<int32_t>(), st));
+        SURFD_TRY(lattice_eval(d, d->list.as<int32_t>(), 0, cnt, NL, stride, N, false, udf_dev, grad_dev, st));
+      }
+      if (NL < N) {
+        const float thr = (float)(1.5 * 1.7 * (2.0 / NL));  // meshudf.py:185-188
+        gf_close_kernel<<<(unsigned)cdiv(nl3, 256), 256, 0, st>>>(NL, stride, N, udf_dev, sb + offs_a[l], thr, sb + offs_c[l]);
+        SURFD_CHECK_LAUNCH();
+      }
+    }
+    if (n_lv > 1) {
+      GfLevels lv{};
+      lv.n_levels = n_lv - 1;
+      for (int l = 0; l < n_lv - 1; ++l) { lv.NL[l] = NLs[l]; lv.active[l] = sb + offs_a[l]; lv.close[l] = sb + offs_c[l]; }
+      gf_resolve_kernel<<<(unsigned)cdiv(n3, 256), 256, 0, st>>>(lv, N, udf_dev);
+      SURFD_CHECK_LAUNCH();
+    }
+    const float thr = (float)(2.5 * 2.0 / N);  // meshudf.py:199
+    SURFD_TRY(lattice_grads(d, N, thr, udf_dev, grad_dev, &n_grad, st));
+  }
+  if (counts_host) { counts_host[0] = n_udf; counts_host[1] = n_grad; }
+  return 0;
+}
+
+extern "C" int surfd_face_filter(surfd_decoder* d, const double* verts64_dev, const int32_t* faces_dev, int64_t n_f, int N,
+                                 uint8_t* keep_dev, void* stream) {
+  SURFD_REQUIRE(d && d->latent_set, "decoder latent not set");
+  SURFD_REQUIRE(n_f >= 0 && (n_f == 0 || (verts64_dev && faces_dev && keep_dev)), "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int faces_per_chunk = d->chunk / 9;
+  const float thr = (float)(1.0 / N);  // meshudf.py:372
+  for (int64_t f0 = 0; f0 < n_f; f0 += faces_per_chunk) {
+    const int nf = (int)((n_f - f0) < faces_per_chunk ? (n_f - f0) : faces_per_chunk);
+    const int m = nf * 9;
+    face_points_kernel<<<(unsigned)cdiv(m, 256), 256, 0, st>>>(verts64_dev, faces_dev, f0, m, d->pts.as<float>());
+    SURFD_CHECK_LAUNCH();
+    SURFD_TRY(dec_forward(d, m, false, d->udf_tmp.as<float>(), nullptr, st));
+    face_keep_kernel<<<(unsigned)cdiv(nf, 256), 256, 0, st>>>(d->udf_tmp.as<float>(), nf, thr, keep_dev + f0);
+    SURFD_CHECK_LAUNCH();
+  }
+  return 0;
+}

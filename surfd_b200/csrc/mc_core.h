@@ -30,7 +30,7 @@
 #define MC_LUT_STORAGE static
 #endif
 
-namespace surfd_mc {
+namespace surfd_mccore {
 
 #include "mc_luts.inc"
 
@@ -402,20 +402,22 @@ MC_HD void add_face_from_edge(Grid& g, Cell& c, int vi) {
       py = (double)c.y + 1.0 * fy / ff;
       pz = (double)c.z + 1.0 * fz / ff;
     }
-    if (g.n_v >= g.cap_v) { g.status = MC_CAPACITY; ++g.n_v; idx = 0; }
-    else {
-      idx = (int)g.n_v;
+    idx = (int)g.n_v;
+    if (g.n_v < g.cap_v) {
       g.verts[3 * g.n_v + 0] = (float)px;
       g.verts[3 * g.n_v + 1] = (float)py;
       g.verts[3 * g.n_v + 2] = (float)pz;
-      ++g.n_v;
-      g.face_layer[slot] = idx;
+    } else {
+      g.status = MC_CAPACITY;  // keep counting so the caller learns the required size
     }
+    ++g.n_v;
+    g.face_layer[slot] = idx;
   } else if (vi == 12 && !c.v12_done) {
     center_vertex(c);
   }
-  if (g.n_f3 >= g.cap_f3) { g.status = MC_CAPACITY; ++g.n_f3; }
-  else g.faces[g.n_f3++] = idx;
+  if (g.n_f3 < g.cap_f3) g.faces[g.n_f3] = idx;
+  else g.status = MC_CAPACITY;
+  ++g.n_f3;
 }
 
 MC_HD void add_tiling(Grid& g, Cell& c, const Tiling& t, int config) {
@@ -457,7 +459,6 @@ MC_HD_NOINLINE bool visit_cube(Grid& g, int z, int y, int x, int mode) {
   }
   int visited_vs[8];
   float sign_vs[8];
-  const bool q_nonempty_at_entry_dummy = false; (void)q_nonempty_at_entry_dummy;
   for (int vtx = 0; vtx < 8; ++vtx) {
     visited_vs[vtx] = 0;
     sign_vs[vtx] = 0.0f;
@@ -629,4 +630,4 @@ MC_HD_NOINLINE void replay(Grid& g) {
   if (g.status == MC_OK && g.n_v == 0) g.status = MC_EMPTY;
 }
 
-}  // namespace surfd_mc
+}  // namespace surfd_mccore

@@ -1,0 +1,146 @@
+"""Device implementation of the reference's meshudf package boundary.
+
+  udf_mc_lewiner(volume, grads, spacing, ...)   <- meshudf/_marching_cubes_lewiner.py:87-154
+  get_mesh_from_udf(udf_func, ...)               <- meshudf/meshudf.py:307-437 (differentiable=False part)
+
+`udf_func` closures cannot cross the C ABI; the drop-in recognises the decoder-backed closure
+(`DecoderUdf`, which carries the UdfDecoder and the latent) and refuses foreign callables loudly --
+there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .decoder import UdfDecoder
+
+
+class MarchingCubes:
+    """Handle owning the marching-cubes workspaces (reused across shapes)."""
+
+    def __init__(self, device="cuda"):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.surfd_mc_create(ctypes.byref(h)))
+        self._h = h
+        self.last_stats = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.surfd_mc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_raw(self, volume, grads):
+        """pyx-level output: vertices float32 [V,3] (x,y,z)=(axis2,axis1,axis0) index units, faces int32 [F,3]."""
+        if volume.dim() != 3:
+            raise ValueError("Input volume should be a 3D numpy array.")
+        if min(volume.shape) < 2:
+            raise ValueError("Input array must be at least 2x2x2.")
+        N = volume.shape[0]
+        if volume.shape[1] != N or volume.shape[2] != N:
+            raise ValueError("surfd_b200 marching cubes needs a cubic lattice")
+        volume = volume.to(self.device, torch.float32).contiguous()
+        grads = grads.to(self.device, torch.float32).contiguous()
+        nv, nf = ctypes.c_int64(), ctypes.c_int64()
+        stats = (ctypes.c_int64 * 8)()
+        _lib.check(self.lib.surfd_mc_udf(self._h, _lib.ptr(volume), _lib.ptr(grads), N, ctypes.byref(nv), ctypes.byref(nf),
+                                         stats, _lib.stream_ptr()))
+        self.last_stats = dict(n_cand=stats[0], n_seed=stats[1], n_accept=stats[2], n_unsure=stats[3], n_nontrivial=stats[4])
+        verts = torch.empty(nv.value, 3, device=self.device, dtype=torch.float32)
+        faces = torch.empty(nf.value, 3, device=self.device, dtype=torch.int32)
+        _lib.check(self.lib.surfd_mc_fetch(self._h, _lib.ptr(verts), _lib.ptr(faces), _lib.stream_ptr()))
+        return verts, faces
+
+    def classify(self, volume):
+        """candidate-cube count and bit mask (one bit per lattice index)."""
+        N = volume.shape[0]
+        volume = volume.to(self.device, torch.float32).contiguous()
+        words = (N * N * N + 31) // 32
+        bits = torch.empty(words, device=self.device, dtype=torch.int32)
+        n = ctypes.c_int64()
+        _lib.check(self.lib.surfd_mc_classify(self._h, _lib.ptr(volume), N, _lib.ptr(bits), ctypes.byref(n), _lib.stream_ptr()))
+        return int(n.value), bits
+
+
+_default_mc = {}
+
+
+def _mc_for(device):
+    key = str(torch.device(device))
+    if key not in _default_mc:
+        _default_mc[key] = MarchingCubes(device)
+    return _default_mc[key]
+
+
+def udf_mc_lewiner(volume, grads, spacing=(1.0, 1.0, 1.0), gradient_direction="descent", step_size=1,
+                   allow_degenerate=True, use_classic=False, mask=None, mc=None):
+    """Same contract as the reference wrapper, on device tensors: returns (vertices float64 [V,3] in
+    (axis0,axis1,axis2) order scaled by `spacing`, faces int32 [F,3], None, None)."""
+    if len(spacing) != 3:
+        raise ValueError("`spacing` must consist of three floats.")
+    if int(step_size) != 1 or use_classic or mask is not None or not allow_degenerate:
+        raise NotImplementedError("surfd_b200 implements the configuration the Surf-D scripts use: "
+                                  "step_size=1, use_classic=False, mask=None, allow_degenerate=True")
+    mc = mc or _mc_for(volume.device if volume.is_cuda else "cuda")
+    verts, faces = mc.run_raw(volume, grads)
+    vertices = torch.flip(verts, dims=[1])                       # np.fliplr(vertices)
+    if gradient_direction == "descent":
+        faces = torch.flip(faces, dims=[1])                      # np.fliplr(faces)
+    elif gradient_direction != "ascent":
+        raise ValueError("Incorrect input %s in `gradient_direction`, see docstring." % (gradient_direction))
+    if not (float(spacing[0]) == 1 and float(spacing[1]) == 1 and float(spacing[2]) == 1):
+        sp = torch.tensor([float(s) for s in spacing], dtype=torch.float64, device=vertices.device)
+        vertices = vertices.to(torch.float64) * sp               # float32 * float64 -> float64 like numpy
+    return vertices, faces.contiguous(), None, None
+
+
+class DecoderUdf:
+    """The `udf_func` closure of sample/generate_*.py as an object the C ABI can see."""
+
+    def __init__(self, decoder: UdfDecoder, lat):
+        self.decoder = decoder
+        self.lat = lat
+
+    def bind(self):
+        self.decoder.set_latent(self.lat)
+
+    def __call__(self, c):
+        self.bind()
+        return self.decoder.query(c)
+
+
+def get_mesh_from_udf(udf_func, coords_range=(-1, 1), max_dist=0.1, N=128, smooth_borders=True, differentiable=True,
+                      max_batch=2 ** 12, use_fast_grid_filler=True, mc=None, return_stats=False):
+    """Lattice query + marching cubes + UDF face filter (meshudf.py:307-379).
+
+    Returns (verts float32 cuda [V,3], faces int64 cuda [F,3]) exactly at the meshudf.py:379 boundary:
+    all marching-cubes vertices, faces with the `udf > 1/N` ones removed.  The trimesh clean-up and border
+    smoothing that follow in the reference (meshudf.py:379-434) are outside this path."""
+    if not isinstance(udf_func, DecoderUdf):
+        raise TypeError("surfd_b200.get_mesh_from_udf needs a DecoderUdf (decoder + latent); arbitrary Python "
+                        "closures cannot run in the CUDA library and there is no CPU fallback")
+    if tuple(float(c) for c in coords_range) != (-1.0, 1.0):
+        raise NotImplementedError("the reference's marching cubes hard-codes the [-1,1] range (pyx:1131)")
+    if differentiable:
+        raise NotImplementedError("differentiable=True (meshudf.py:439-512) is outside the generation path")
+    dec = udf_func.decoder
+    udf_func.bind()
+    udf, grads, counts = dec.lattice(N, use_fast_grid_filler=use_fast_grid_filler, max_dist=max_dist)
+    udf.clamp_(min=0)                                            # udf[udf < 0] = 0
+    spacing = (coords_range[1] - coords_range[0]) / (N - 1)
+    vertices, faces, _, _ = udf_mc_lewiner(udf, grads, spacing=[spacing] * 3, mc=mc)
+    vertices = vertices + coords_range[0]                        # float64, meshudf.py:352
+    keep = dec.face_filter(vertices, faces, N)
+    faces_kept = faces[keep.bool()]
+    out = (vertices.to(torch.float32), faces_kept.to(torch.int64))
+    if return_stats:
+        return out + (dict(n_udf=counts[0], n_grad=counts[1], n_faces_mc=int(faces.shape[0]), n_faces_kept=int(faces_kept.shape[0])),)
+    return out

@@ -1,0 +1,176 @@
+"""Synthetic checkpoints in the reference's on-disk layouts.
+
+The reference ships no weights and literal random init is degenerate (zero_module sites make the UNet output 0,
+zero-init CBN/fc_1 make the decoder latent-independent: SURVEY F5), so benchmarks and parity tests use:
+  synth_ae_rand(L, seed)   every decoder tensor randomised           -> {"decoder": state_dict}
+  synth_mdm(cond_mode, seed) every UNet tensor randomised           -> flat state_dict with "Unet." keys
+Both are plain torch CPU code with fixed generators, so the GPU box, this container and the oracle all see
+bit-identical tensors.
+"""
+import math
+
+import torch
+
+from .decoder import expected_keys
+
+
+def _fill(shape, gen, kind):
+    if kind == "weight":
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        return torch.randn(shape, generator=gen) / math.sqrt(max(fan_in, 1))
+    if kind == "bias":
+        return 0.02 * torch.randn(shape, generator=gen)
+    raise ValueError(kind)
+
+
+def synth_ae_rand(latent_dim=32, seed=4321):
+    """'rand' AE checkpoint: tensors with dim>=2 ~ N(0,1)/sqrt(fan_in) (fan_in = numel of one output row),
+    biases ~ 0.02 N(0,1), BN running_mean ~ 0.1 N(0,1), running_var ~ U(0.5,1.5)."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in expected_keys(latent_dim).items():
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.tensor(0, dtype=torch.long)
+        elif k.endswith("running_mean"):
+            sd[k] = 0.1 * torch.randn(shp, generator=gen)
+        elif k.endswith("running_var"):
+            sd[k] = 0.5 + torch.rand(shp, generator=gen)
+        elif k.endswith("conv_gamma.bias"):
+            sd[k] = 1.0 + 0.02 * torch.randn(shp, generator=gen)
+        elif len(shp) >= 2:
+            sd[k] = _fill(shp, gen, "weight")
+        else:
+            sd[k] = _fill(shp, gen, "bias")
+    return {"epoch": 0, "encoder": {}, "decoder": sd, "optimizer": {}}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 'poly' AE checkpoint: an exactly-constructed decoder whose field is the UDF of a 32-face convex polytope.
+#
+# SURVEY.md 8(d) asks for a decoder *fitted* to an analytic UDF family so that a zero-level set exists for
+# any latent.  Training is not possible offline (no GPU here, ~17 h on 8 cores), so the fit is done in closed
+# form.  The ReLU residual MLP computes m(x) = max_i (n_i.x - r_i(z)) by a pairwise-max tournament
+# (max(a,b) = a + relu(b-a); one ConditionalResnetBlock1d per level for 32 -> 2, signed values carried as
+# (+v,-v) channel pairs so nothing needs a large offset), the last block forms d = |max(A,B)| and copies it into
+# K+1 channels, and the final CBN+ReLU+fc_out realises the convex piecewise-linear
+#     logit(d) = 2 - 40 d + sum_j v_j relu(k_j - d)   ~=  log((0.1-d)/d)   on (0, 0.05]
+# (all hinge terms positive: no cancellation in fp32/TF32), so udf(x) = 0.1*(1-sigmoid(logit)) ~= |m(x)| near the
+# surface -- the unsigned distance to the polytope (exact inside and next to faces) -- and saturates smoothly
+# towards 0.1 far away.  The latent moves every face: r_i(z) = r0 - tau_i(z), tau linear in z through bn_0's
+# conv_beta of block 0.  Same key set / shapes as a trained checkpoint.
+# ---------------------------------------------------------------------------------------------------------
+POLY_K = 96
+
+
+def poly_planes(n_planes=32):
+    """unit normals (Fibonacci sphere), deterministic"""
+    i = torch.arange(n_planes, dtype=torch.float64) + 0.5
+    phi = torch.acos(1 - 2 * i / n_planes)
+    theta = math.pi * (1 + 5 ** 0.5) * i
+    n = torch.stack([torch.cos(theta) * torch.sin(phi), torch.sin(theta) * torch.sin(phi), torch.cos(phi)], -1)
+    return n.to(torch.float32)
+
+
+def _poly_u(latent_dim, seed, amp):
+    gen = torch.Generator().manual_seed(seed)
+    return torch.randn(32, latent_dim, generator=gen) * (amp / math.sqrt(latent_dim))
+
+
+def poly_offsets(latent, seed=4321, r0=0.5, amp=0.05):
+    """r_i(z) for a latent [L] (same arithmetic the checkpoint encodes; used by tests for the exact field)."""
+    U = _poly_u(latent.numel(), seed, amp)
+    return r0 - U @ latent.reshape(-1).to(torch.float32)
+
+
+def _poly_pl():
+    """knots k_0=0 < k_1 < ... < k_K = 0.05 and the hinge weights v_j of g(d) = log((0.1-d)/d) - (2 - 40 d)"""
+    k = torch.logspace(math.log10(2e-5), math.log10(0.05), POLY_K, dtype=torch.float64)
+    g = torch.log((0.1 - k) / k) - (2 - 40 * k)
+    g[-1] = 0.0
+    xs = torch.cat([torch.zeros(1, dtype=torch.float64), k])
+    ys = torch.cat([torch.tensor([14.0], dtype=torch.float64), g])
+    slopes = (ys[1:] - ys[:-1]) / (xs[1:] - xs[:-1])            # slope on (x_{j-1}, x_j), j = 1..K   (all < 0)
+    nxt = torch.cat([slopes[1:], torch.zeros(1, dtype=torch.float64)])
+    v = nxt - slopes                                             # v_j = slope_{j+1} - slope_j  (> 0 by convexity)
+    return k, v
+
+
+def poly_logit(d):
+    """the piecewise-linear logit(d) the checkpoint encodes (float64)"""
+    k, v = _poly_pl()
+    d = d.to(torch.float64)
+    return 2 - 40 * d + (v[None, :] * torch.relu(k[None, :] - d.reshape(-1, 1))).sum(-1).reshape(d.shape)
+
+
+def synth_ae_poly(latent_dim=32, seed=4321, r0=0.5, amp=0.05):
+    H = 512
+    sd = {}
+    for key, shp in expected_keys(latent_dim).items():
+        if key.endswith("num_batches_tracked"):
+            sd[key] = torch.tensor(0, dtype=torch.long)
+        elif key.endswith("running_var"):
+            sd[key] = torch.full(shp, 1.0 - 1e-5)
+        elif key.endswith("conv_gamma.bias"):
+            sd[key] = torch.ones(shp)
+        else:
+            sd[key] = torch.zeros(shp)
+    n = poly_planes(32)
+    U = _poly_u(latent_dim, seed, amp)
+    # level-0 channels: plane i -> (2i: +a_i, 2i+1: -a_i),  a_i = n_i.x - r0 ; tau enters through bn_0 beta of block 0
+    Wp, bp = sd["decoder.fc_p.weight"], sd["decoder.fc_p.bias"]
+    for i in range(32):
+        Wp[2 * i, 0:3, 0] = n[i]
+        Wp[2 * i + 1, 0:3, 0] = -n[i]
+        bp[2 * i] = -r0
+        bp[2 * i + 1] = r0
+        sd["decoder.blocks.0.bn_0.conv_beta.weight"][2 * i, :, 0] = U[i]
+        sd["decoder.blocks.0.bn_0.conv_beta.weight"][2 * i + 1, :, 0] = -U[i]
+    k, v = _poly_pl()
+    K = k.numel()
+    base = [0, 64, 96, 112, 120]      # first channel of level l's (+,-) pairs; level 4 = A+,A-,B+,B- at 120..123
+    CH_D = 124                        # D = B - A
+    CH_ABS = 125                      # K+1 copies of d = |max(A,B)| from here
+    assert CH_ABS + K + 1 <= H
+    for lvl in range(4):              # blocks 0..3: 32 -> 16 -> 8 -> 4 -> 2
+        n_in = 32 >> lvl
+        W0 = sd[f"decoder.blocks.{lvl}.fc_0.weight"]
+        W1 = sd[f"decoder.blocks.{lvl}.fc_1.weight"]
+        for p in range(n_in // 2):
+            a_p, a_m = base[lvl] + 4 * p, base[lvl] + 4 * p + 1
+            b_p, b_m = base[lvl] + 4 * p + 2, base[lvl] + 4 * p + 3
+            h = 3 * p                 # hidden channels: relu(a), relu(-a), relu(b-a)
+            W0[h, a_p, 0] = 1; W0[h, a_m, 0] = -1
+            W0[h + 1, a_p, 0] = -1; W0[h + 1, a_m, 0] = 1
+            W0[h + 2, b_p, 0] = 1; W0[h + 2, b_m, 0] = -1; W0[h + 2, a_p, 0] = -1; W0[h + 2, a_m, 0] = 1
+            for c, sgn in ((base[lvl + 1] + 2 * p, 1.0), (base[lvl + 1] + 2 * p + 1, -1.0)):
+                W1[c, h, 0] = sgn; W1[c, h + 1, 0] = -sgn; W1[c, h + 2, 0] = sgn
+            if lvl == 3:
+                # D = B - A = M(pair 1) - M(pair 0), written while the two level-4 values are produced
+                sgn = -1.0 if p == 0 else 1.0
+                W1[CH_D, h, 0] = sgn; W1[CH_D, h + 1, 0] = -sgn; W1[CH_D, h + 2, 0] = sgn
+    # block 4: relu(A), relu(-A), relu(D) -> h+ = relu(M), h- = relu(-M), M = A + relu(D);  d = h+ + h-
+    W0, W1 = sd["decoder.blocks.4.fc_0.weight"], sd["decoder.blocks.4.fc_1.weight"]
+    W0[0, 120, 0] = 1; W0[0, 121, 0] = -1; W0[0, CH_D, 0] = 1
+    W0[1, 120, 0] = -1; W0[1, 121, 0] = 1; W0[1, CH_D, 0] = -1
+    for j in range(K + 1):
+        W1[CH_ABS + j, 0, 0] = 1; W1[CH_ABS + j, 1, 0] = 1
+    # final CBN: channel CH_ABS: relu(d) (gamma=1, beta=0) with fc_out -40; channels CH_ABS+1+j: relu(k_j - d), fc_out v_j
+    gam, bet, wout = sd["decoder.bn.conv_gamma.bias"], sd["decoder.bn.conv_beta.bias"], sd["decoder.fc_out.weight"]
+    wout[0, CH_ABS, 0] = -40.0
+    for j in range(K):
+        gam[CH_ABS + 1 + j] = -1.0
+        bet[CH_ABS + 1 + j] = float(k[j])
+        wout[0, CH_ABS + 1 + j, 0] = float(v[j])
+    sd["decoder.fc_out.bias"][0] = 2.0
+    return {"epoch": 0, "encoder": {}, "decoder": sd, "optimizer": {}}
+
+
+def poly_udf(pts, latent, seed=4321, r0=0.5, amp=0.05):
+    """the field the 'poly' checkpoint encodes, evaluated directly in float64:
+    0.1*(1 - sigmoid(logit_PL(|m|))), m = max_i(n_i.x - r_i(z));  ~= |m| for |m| <= 0.05"""
+    n = poly_planes(32).to(torch.float64)
+    r = poly_offsets(latent, seed, r0, amp).to(torch.float64)
+    m = (pts.to(torch.float64) @ n.T - r).max(-1).values
+    return 0.1 * (1 - torch.sigmoid(poly_logit(m.abs()))), m

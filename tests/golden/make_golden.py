@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""Generate the committed golden vectors by running the REFERENCE itself (imported from /root/reference,
+CPU fp32) on seeded inputs.  Run in the build container only:  python tests/golden/make_golden.py [what...]
+
+Fixtures (tests/golden/*.npz) are small on purpose; the synthetic checkpoints are regenerated from seeds
+by surfd_b200.synth, so only inputs that are not seed-derivable and the reference outputs are stored.
+"""
+import os, sys
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+sys.path[:0] = [os.path.join(ROOT, "oracle", "stubs"), os.path.join(ROOT, "oracle", "_ref"), REF]
+sys.dont_write_bytecode = True
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.Tensor.cuda = lambda self, *a, **k: self          # the reference hard-codes .cuda()
+torch.nn.Module.cuda = lambda self, *a, **k: self
+
+
+def ref_decoder(L, seed):
+    from AutoEncoder.models.cbndec import CbnDecoder
+    from AutoEncoder.models.coordsenc import CoordsEncoder
+    from surfd_b200.synth import synth_ae_rand
+    ck = synth_ae_rand(L, seed)
+    dec = CbnDecoder(63, L, 512, 5)
+    dec.load_state_dict(ck["decoder"], strict=True)
+    dec.eval()
+    for p in dec.parameters():
+        p.requires_grad = False
+    return dec, CoordsEncoder(), ck
+
+
+def golden_decoder():
+    from meshudf.meshudf import sample_udf, sample_grads
+    for L in (32, 64):
+        dec, enc, ck = ref_decoder(L, 4321)
+        g = torch.Generator().manual_seed(100 + L)
+        lat = 0.7 * torch.randn(1, L, generator=g)
+        pts = torch.rand(2048, 3, generator=g) * 2 - 1
+        # also a run of exact lattice coordinates (N=64) as the reference builds them
+        idx = torch.arange(0, 1024)
+        N = 64
+        vs = 2.0 / (N - 1)
+        lat_pts = torch.stack([(idx // 16 % 8).float() * vs + (-1), (idx // 4 % 4 * 5).float() * vs + (-1),
+                               (idx % 64).float() * vs + (-1)], -1)
+        pts = torch.cat([pts, lat_pts], 0)
+
+        def udf_func(c):
+            c = enc.encode(c.unsqueeze(0))
+            p = dec(c, lat).squeeze(0)
+            p = torch.sigmoid(p)
+            return (1 - p) * 0.1
+        udf = sample_udf(udf_func, pts, 2 ** 16)
+        grads = sample_grads(udf_func, pts, 2 ** 16)
+        np.savez_compressed(os.path.join(OUT, f"decoder_L{L}.npz"), lat=lat.numpy(), pts=pts.numpy(),
+                            udf=udf.numpy(), grads=grads.numpy())
+        print("decoder golden L", L, "udf range", float(udf.min()), float(udf.max()))
+
+
+def ref_poly(L):
+    from AutoEncoder.models.cbndec import CbnDecoder
+    from AutoEncoder.models.coordsenc import CoordsEncoder
+    from surfd_b200.synth import synth_ae_poly
+    ck = synth_ae_poly(L)
+    dec = CbnDecoder(63, L, 512, 5)
+    dec.load_state_dict(ck["decoder"], strict=True)
+    dec.eval()
+    for p in dec.parameters():
+        p.requires_grad = False
+    return dec, CoordsEncoder(), ck
+
+
+def golden_gridfiller():
+    """Reference GridFiller / dense lattice + reference marching cubes on the 'poly' decoder, N=64."""
+    from meshudf.meshudf import GridFiller, get_udf_and_grads
+    from meshudf._marching_cubes_lewiner import udf_mc_lewiner
+    L, N = 32, 64
+    dec, enc, ck = ref_poly(L)
+    g = torch.Generator().manual_seed(7)
+    lat = torch.randn(1, L, generator=g)
+    calls = {"n": 0}
+
+    def udf_func(c):
+        calls["n"] += c.shape[0]
+        c = enc.encode(c.unsqueeze(0))
+        p = dec(c, lat).squeeze(0)
+        p = torch.sigmoid(p)
+        return (1 - p) * 0.1
+    out = {"lat": lat.numpy()}
+    for mode in ("gf", "dense"):
+        calls["n"] = 0
+        if mode == "gf":
+            udf, grads = GridFiller(N).fill_grid(udf_func, 2 ** 16)
+        else:
+            udf, grads = get_udf_and_grads(udf_func, (-1, 1), 0.1, N, 2 ** 16)
+        udf = udf.clone(); udf[udf < 0] = 0
+        u, gr = udf.detach().numpy(), grads.detach().numpy()
+        v, f, _, _ = udf_mc_lewiner(u, gr, spacing=[2.0 / (N - 1)] * 3)
+        n_grad = int((np.abs(gr).sum(-1) > 0).sum())
+        print(mode, "calls", calls["n"], "grad pts", n_grad, "V", v.shape, "F", f.shape)
+        out[mode + "_udf"] = u.astype(np.float32)
+        out[mode + "_gradmask"] = np.packbits(np.abs(gr).sum(-1) > 0)
+        sel = np.abs(gr).sum(-1) > 0
+        out[mode + "_grads"] = gr[sel].astype(np.float16)
+        out[mode + "_calls"] = np.array([calls["n"], n_grad])
+        out[mode + "_nv_nf"] = np.array([v.shape[0], f.shape[0]])
+    out["gf_udf"] = out["gf_udf"].astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "gridfiller_poly_N64.npz"), **out)
+
+
+def golden_mc():
+    """Reference Cython marching_cubes_udf (compiled into oracle/_ref) on the analytic fields of tests/fields.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fields import analytic_field, MC_CASES
+    from meshudf import _marching_cubes_lewiner_cy as cy
+    from meshudf._marching_cubes_lewiner import _get_mc_luts
+    L = _get_mc_luts()
+    out = {}
+    for kind, N, noise in MC_CASES:
+        udf, g = analytic_field(kind, N, noise, seed=N)
+        v, f, _, _ = cy.marching_cubes_udf(udf, g, L, 1, 0, None)
+        key = f"{kind}_{N}_{noise}"
+        out[key + "_v"] = v
+        out[key + "_f"] = f.astype(np.int32)
+        print(key, v.shape, f.shape)
+    np.savez_compressed(os.path.join(OUT, "mc_fields.npz"), **out)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["decoder"]
+    for w in what:
+        globals()["golden_" + w]()

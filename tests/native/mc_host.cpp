@@ -5,7 +5,7 @@
 #include <cstring>
 #include <vector>
 #include "mc_core.h"
-using namespace surfd_mc;
+using namespace surfd_mccore;
 
 extern "C" int mc_host_run(const float* im, const float* grads, int N, float* verts, int64_t cap_v,
                            int32_t* faces, int64_t cap_f3, int64_t* n_v, int64_t* n_f3, int64_t* stats) {
