@@ -1,0 +1,89 @@
+"""GPU parity (-m gpu): device marching cubes (classification kernel + ordered replay) against the reference's
+outputs -- bit-exact vertices, faces and numbering."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from fields import analytic_field, MC_CASES
+from surfd_b200.meshudf import MarchingCubes, udf_mc_lewiner, get_mesh_from_udf, DecoderUdf
+from surfd_b200 import synth
+from surfd_b200.decoder import UdfDecoder
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", MC_CASES, ids=lambda c: f"{c[0]}-{c[1]}-{c[2]}")
+def test_device_mc_matches_reference_golden_bit_exact(case):
+    kind, N, noise = case
+    g = np.load(os.path.join(GOLDEN, "mc_fields.npz"))
+    udf, grads = analytic_field(kind, N, noise, seed=N)
+    mc = MarchingCubes()
+    v, f = mc.run_raw(torch.from_numpy(udf).cuda(), torch.from_numpy(grads).cuda())
+    key = f"{kind}_{N}_{noise}"
+    assert np.array_equal(v.cpu().numpy(), g[key + "_v"])
+    assert np.array_equal(f.cpu().numpy().reshape(-1), g[key + "_f"])
+
+
+def test_device_mc_matches_live_reference_at_larger_sizes(ref_mc):
+    if ref_mc is None:
+        pytest.skip("oracle/_ref not present on this machine")
+    mc = MarchingCubes()
+    for kind, N, noise, seed in [("sphere", 128, 0.3, 1), ("torus", 160, 1.0, 2), ("hemi", 96, 0.0, 3)]:
+        udf, grads = analytic_field(kind, N, noise, seed=seed)
+        rv, rf = ref_mc(udf, grads)
+        v, f = mc.run_raw(torch.from_numpy(udf).cuda(), torch.from_numpy(grads).cuda())
+        assert np.array_equal(v.cpu().numpy(), rv) and np.array_equal(f.cpu().numpy().reshape(-1), rf), (kind, N)
+
+
+def test_classification_matches_numpy_restating_the_thresholds():
+    for N in (33, 64):
+        udf, _ = analytic_field("torus", N, 0.3, seed=N)
+        n, bits = MarchingCubes().classify(torch.from_numpy(udf).cuda())
+        u = udf
+        c = [u[:-1, :-1, :-1], u[:-1, :-1, 1:], u[:-1, 1:, 1:], u[:-1, 1:, :-1], u[1:, :-1, :-1], u[1:, :-1, 1:], u[1:, 1:, 1:], u[1:, 1:, :-1]]
+        s = c[0].copy()
+        for k in c[1:]:
+            s = (s + k).astype(np.float32)
+        avg = (np.float32(0.125) * s).astype(np.float32)
+        mx = np.maximum.reduce(c)
+        vox = 2.0 / (N - 1)
+        cand = (avg < np.float32(1.05 * vox)) & (mx <= np.float32(1.74 * vox))
+        full = np.zeros((N, N, N), bool); full[:-1, :-1, :-1] = cand
+        mine = np.unpackbits(bits.cpu().numpy().view(np.uint8), bitorder="little")[:N ** 3].astype(bool).reshape(N, N, N)
+        assert n == int(cand.sum()) and (mine == full).all()
+
+
+def test_wrapper_contract_and_errors():
+    udf, grads = analytic_field("sphere", 32, 0.0, seed=32)
+    v, f, _, _ = udf_mc_lewiner(torch.from_numpy(udf).cuda(), torch.from_numpy(grads).cuda(), spacing=[2.0 / 31] * 3)
+    g = np.load(os.path.join(GOLDEN, "mc_fields.npz"))
+    ref_v = np.fliplr(g["sphere_32_0.0_v"]) * np.r_[[2.0 / 31] * 3]           # _marching_cubes_lewiner.py:134-151
+    ref_f = np.fliplr(g["sphere_32_0.0_f"].reshape(-1, 3))
+    assert v.dtype == torch.float64 and f.dtype == torch.int32
+    assert np.array_equal(v.cpu().numpy(), ref_v) and np.array_equal(f.cpu().numpy(), ref_f)
+    with pytest.raises(RuntimeError, match="No surface found"):
+        udf_mc_lewiner(torch.full((16, 16, 16), 0.1).cuda(), torch.zeros(16, 16, 16, 3).cuda())
+    with pytest.raises(ValueError):
+        udf_mc_lewiner(torch.zeros(16, 16).cuda(), torch.zeros(16, 16, 3).cuda())
+    with pytest.raises(ValueError):
+        udf_mc_lewiner(torch.zeros(1, 1, 1).cuda(), torch.zeros(1, 1, 1, 3).cuda())
+
+
+@pytest.mark.parametrize("fast", [True, False])
+def test_end_to_end_mesh_from_decoder_lies_on_the_polytope(fast):
+    L, N = 32, 64
+    dec = UdfDecoder(synth.synth_ae_poly(L)["decoder"], L)
+    g = np.load(os.path.join(GOLDEN, "gridfiller_poly_N64.npz"))
+    lat = torch.from_numpy(g["lat"][0])
+    verts, faces, stats = get_mesh_from_udf(DecoderUdf(dec, lat), (-1, 1), 0.1, N=N, differentiable=False,
+                                            use_fast_grid_filler=fast, max_batch=2 ** 16, return_stats=True)
+    # the reference pipeline on the same decoder gives V=4888, F=9772 before the face filter
+    key = "gf" if fast else "dense"
+    assert verts.shape[0] == int(g[key + "_nv_nf"][0]) and stats["n_faces_mc"] == int(g[key + "_nv_nf"][1])
+    assert verts.dtype == torch.float32 and faces.dtype == torch.int64 and verts.is_cuda
+    exact, m = synth.poly_udf(verts.cpu(), lat)
+    assert float(m.abs().max()) < 0.6 * 2.0 / (N - 1)           # every vertex within ~half a voxel of the surface
+    assert stats["n_faces_kept"] > 0.95 * stats["n_faces_mc"]

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Quick stage timings on the GPU box (not the benchmark of record): decoder throughput, lattice, marching cubes."""
+import json, sys, time
+import torch
+sys.path.insert(0, ".")
+from surfd_b200 import synth, _lib
+from surfd_b200.decoder import UdfDecoder
+from surfd_b200.meshudf import MarchingCubes, get_mesh_from_udf, DecoderUdf
+
+
+def timed(fn, n=3):
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / 1e3)
+    return best, out
+
+
+def main():
+    res = {"gpu": torch.cuda.get_device_name(0)}
+    L = 32
+    dec = UdfDecoder(synth.synth_ae_poly(L)["decoder"], L)
+    gen = torch.Generator().manual_seed(0)
+    lat = torch.randn(L, generator=gen)
+    dec.set_latent(lat)
+    M = 37888 * 8
+    pts = (torch.rand(M, 3, generator=gen) * 2 - 1).cuda()
+    t, _ = timed(lambda: dec.query(pts))
+    res["fwd_pts_per_s"] = M / t; res["fwd_tflops"] = M * 5.308e6 / t / 1e12
+    t, _ = timed(lambda: dec.query(pts, want_grad=True))
+    res["fwdbwd_pts_per_s"] = M / t; res["fwdbwd_tflops"] = M * (5.308e6 + 10.617e6) / t / 1e12
+    mc = MarchingCubes()
+    for N in (128, 256):
+        for fast in (True, False):
+            t, (u, g, c) = timed(lambda: dec.lattice(N, fast), n=2)
+            res[f"lattice_N{N}_{'gf' if fast else 'dense'}_s"] = t; res[f"lattice_N{N}_{'gf' if fast else 'dense'}_counts"] = c
+        t, (v, f) = timed(lambda: mc.run_raw(u.clamp(min=0), g), n=2)
+        res[f"mc_N{N}_s"] = t; res[f"mc_N{N}_VF"] = [v.shape[0], f.shape[0]]; res[f"mc_N{N}_stats"] = mc.last_stats
+        t, n = timed(lambda: mc.classify(u), n=3)
+        res[f"classify_N{N}_s"] = t
+        t, out = timed(lambda: get_mesh_from_udf(DecoderUdf(dec, lat), (-1, 1), 0.1, N=N, differentiable=False, max_batch=2**16, return_stats=True), n=2)
+        res[f"mesh_N{N}_s"] = t; res[f"mesh_N{N}_stats"] = out[2]
+    res["launches"] = int(_lib.load().surfd_launch_count(0))
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main()
