@@ -96,9 +96,11 @@ int surfd_face_filter(surfd_decoder* d, const double* verts64_dev, const int32_t
  *   diffusion/respace.py:63-132, models/mdm.py:91-110, models/openaimodel.py:710-749
  * ------------------------------------------------------------------------------------------- */
 typedef struct surfd_unet surfd_unet;
-/* packed: float32 blob from surfd_b200.unet.pack_unet() (layout in DESIGN.md); L = 32 or 64 */
-int surfd_unet_create(const float* packed, size_t n_floats, int packed_on_device, int L, int max_batch,
-                      surfd_unet** out);
+/* packed: float32 weight blob and `program`: int64 op program, both from surfd_b200.unet.pack_unet() (the
+ * architecture walk of models/openaimodel.py:443-692 happens on the host; the device side interprets
+ * GN / token-GEMM / attention ops -- layout in DESIGN.md); L = 32 or 64.  Pointers may be host or device. */
+int surfd_unet_create(const float* packed, size_t n_floats, const int64_t* program, size_t n_program, int L,
+                      int max_batch, surfd_unet** out);
 void surfd_unet_destroy(surfd_unet* u);
 size_t surfd_unet_packed_floats(void);
 /* one model evaluation x0_hat = model(x_t, t, context/labels): teacher-forced parity entry.

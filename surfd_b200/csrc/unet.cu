@@ -1,9 +1,598 @@
-// unet.cu -- placeholder until the sampler kernels land (next commit); keeps the C ABI complete.
+// unet.cu -- the denoiser (MDM / UNetModel forward) as an op program interpreted on the device, and the
+// reverse-diffusion loop around it, captured once as a CUDA graph and replayed per step.
+//
+// Reference being replaced (read-only, /root/reference):
+//   models/openaimodel.py:710-749   UNetModel.forward          :255-275 ResBlock._forward
+//   models/openaimodel.py:318-324   AttentionBlock._forward    :356-372 QKVAttentionLegacy.forward
+//   models/openaimodel.py:91-119,134-160  Upsample (nearest x2 + conv3) / Downsample (conv3 stride 2)
+//   utils/ldm_utils.py:165-185      timestep_embedding         :244-249 GroupNorm32(32, C), eps 1e-5
+//   diffusion/gaussian_diffusion.py:471-520 p_sample, :234-256 q_posterior_mean_variance, :635-708 loop
+//   diffusion/respace.py:116-132    _WrappedModel timestep remap
+//
+// Layout: activations channels-last [B][T][C] fp32 (the reference is [B][C][T]); conv weights repacked to
+// [tap][Cout][Cin] so a k=3 convolution is three token-shifted GEMMs over contiguous channel vectors; the
+// UNet's skip concatenation and the 1x1 skip convolution are extra K segments of the same GEMM; the 22
+// emb_layers linears are one batched GEMM per step.  The reference issues ~450 library kernels and 6 host->device
+// table uploads per step; here a step is one graph launch of ~170 small kernels reading the step index from
+// device memory.
+#include <math.h>
+#include <vector>
+
 #include "common.cuh"
+
+namespace surfd {
+
+enum { OP_GN = 1, OP_CONV = 2, OP_ATTN = 3, OP_INCONV = 4, OP_OUTCONV = 5 };
+constexpr int REC = 32;
+constexpr int EMB = 896;
+constexpr int TCH = 224;
+constexpr int CTX = 512;
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm(32, C) (+ SiLU) over a virtual channel concat [in1 | in2]; one CTA per (batch, group)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+gn_kernel(const float* __restrict__ in1, int C1, const float* __restrict__ in2, int C2, int T, const float* __restrict__ gamma,
+          const float* __restrict__ beta, int silu, float* __restrict__ out, float* __restrict__ raw) {
+  const int C = C1 + C2;
+  const int cg = C / 32;
+  const int b = blockIdx.x >> 5, g = blockIdx.x & 31;
+  const int n = T * cg;
+  __shared__ float red[4];
+  auto load = [&](int idx) -> float {
+    const int t = idx / cg, c = g * cg + idx % cg;
+    return c < C1 ? in1[((size_t)b * T + t) * C1 + c] : in2[((size_t)b * T + t) * C2 + (c - C1)];
+  };
+  auto block_sum = [&](float v) -> float {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return red[0] + red[1] + red[2] + red[3];
+  };
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 128) s += load(i);
+  const float mean = block_sum(s) / (float)n;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < n; i += 128) { const float d = load(i) - mean; q += d * d; }
+  const float var = block_sum(q) / (float)n;
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+  for (int i = threadIdx.x; i < n; i += 128) {
+    const int t = i / cg, c = g * cg + i % cg;
+    const float x = load(i);
+    float y = (x - mean) * rstd * gamma[c] + beta[c];
+    if (silu) y = y / (1.0f + expf(-y));
+    const size_t o = ((size_t)b * T + t) * C + c;
+    out[o] = y;
+    if (raw) raw[o] = x;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Token GEMM: out[m][n] = sum over K segments/taps of A[token(m,tap)][ci] * W[tap][n][ci]  (+bias +emb +residual)
+// CTA tile 32 tokens x 32 outputs; 8 warps split the K chunks (32 channels each) and reduce through smem.
+// ------------------------------------------------------------------------------------------------
+struct Seg {
+  const float* A;  // [B][T_in][Cin]
+  const float* W;  // [taps][N][Cin]
+  int Cin, taps, stride, up, T_in;
+};
+struct ConvArgs {
+  Seg seg[2];
+  int nseg;
+  int B, T_out, N;
+  const float* bias;      // [N]
+  const float* emb;       // [B][emb_ld] (already offset to this block's columns) or null
+  int emb_ld;
+  const float* residual;  // [B][T_out][N] or null
+  float* out;             // [B][T_out][N]
+};
+
+constexpr int CT = 32;        // tile edge
+constexpr int CTP = CT + 4;   // padded row (floats)
+
+__global__ void __launch_bounds__(256)
+conv_gemm_kernel(ConvArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* As = smem + warp * (2 * CT * CTP);
+  float* Ws = As + CT * CTP;
+  const int n0 = blockIdx.x * CT;
+  const int m0 = blockIdx.y * CT;
+  const int M = a.B * a.T_out;
+
+  // this lane's token row for loading
+  const int m_row = m0 + lane;
+  const int rb = m_row / a.T_out, rl = m_row % a.T_out;
+  const bool row_ok = m_row < M;
+
+  const int ly = lane >> 3, lx = lane & 7;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  int chunk = 0;
+  for (int s = 0; s < a.nseg; ++s) {
+    const Seg sg = a.seg[s];
+    const int cpt = sg.Cin / CT;  // chunks per tap
+    const int pad = sg.taps >> 1;
+    const int T_eff = sg.up ? 2 * sg.T_in : sg.T_in;
+    for (int tap = 0; tap < sg.taps; ++tap) {
+      const int src = rl * sg.stride + tap - pad;
+      const bool ok = row_ok && src >= 0 && src < T_eff;
+      const int st = sg.up ? (src >> 1) : src;
+      const float* arow = sg.A + ((size_t)rb * sg.T_in + (ok ? st : 0)) * sg.Cin;
+      const float* wrow = sg.W + ((size_t)tap * a.N + n0 + lane) * sg.Cin;
+      for (int c = 0; c < cpt; ++c, ++chunk) {
+        if ((chunk & 7) != warp) continue;
+        const int ci0 = c * CT;
+        float4 av[8], wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          av[j] = ok ? *reinterpret_cast<const float4*>(arow + ci0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          wv[j] = *reinterpret_cast<const float4*>(wrow + ci0 + 4 * j);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          *reinterpret_cast<float4*>(As + lane * CTP + 4 * j) = av[j];
+          *reinterpret_cast<float4*>(Ws + lane * CTP + 4 * j) = wv[j];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int kk = 0; kk < CT; kk += 4) {
+          float4 wj[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) wj[j] = *reinterpret_cast<const float4*>(Ws + (lx + 8 * j) * CTP + kk);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 ai = *reinterpret_cast<const float4*>(As + (ly + 4 * i) * CTP + kk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[i][j] = fmaf(ai.x, wj[j].x, acc[i][j]);
+              acc[i][j] = fmaf(ai.y, wj[j].y, acc[i][j]);
+              acc[i][j] = fmaf(ai.z, wj[j].z, acc[i][j]);
+              acc[i][j] = fmaf(ai.w, wj[j].w, acc[i][j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // cross-warp reduction through smem: red[warp][row][col], rows padded to 33
+  __syncthreads();
+  float* red = smem;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[(warp * CT + (ly + 4 * i)) * 33 + (lx + 8 * j)] = acc[i][j];
+  __syncthreads();
+  // 256 threads: thread -> (row = tid/8, 4 columns (tid%8)*4 ..)
+  const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
+  const int m = m0 + r;
+  if (m < M) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += red[(w * CT + r) * 33 + c0 + j];
+      v[j] = sum;
+    }
+    const int n = n0 + c0;
+    const int b = m / a.T_out;
+    const float4 bias = *reinterpret_cast<const float4*>(a.bias + n);
+    v[0] += bias.x; v[1] += bias.y; v[2] += bias.z; v[3] += bias.w;
+    if (a.emb) {
+      const float4 e = *reinterpret_cast<const float4*>(a.emb + (size_t)b * a.emb_ld + n);
+      v[0] += e.x; v[1] += e.y; v[2] += e.z; v[3] += e.w;
+    }
+    const size_t o = (size_t)m * a.N + n;
+    if (a.residual) {
+      const float4 rr = *reinterpret_cast<const float4*>(a.residual + o);
+      v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+    }
+    *reinterpret_cast<float4*>(a.out + o) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// QKVAttentionLegacy: one CTA per (batch, head).  qkv [B][T][3C] with per-head [q|k|v] channel interleave.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+attn_kernel(const float* __restrict__ qkv, int C, int T, int heads, float scale, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  const int ch = C / heads;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  float* q = sm;               // [T][ch] (scaled)
+  float* k = q + T * ch;       // [T][ch] (scaled)
+  float* v = k + T * ch;       // [T][ch]
+  float* w = v + T * ch;       // [T][T+1]
+  const float* base = qkv + (size_t)b * T * 3 * C + (size_t)h * 3 * ch;
+  for (int i = threadIdx.x; i < T * ch; i += 128) {
+    const int t = i / ch, c = i % ch;
+    const float* p = base + (size_t)t * 3 * C + c;
+    q[i] = p[0] * scale;
+    k[i] = p[ch] * scale;
+    v[i] = p[2 * ch];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += 128) {
+    const int t = i / T, s = i % T;
+    float acc = 0.f;
+    for (int c = 0; c < ch; ++c) acc = fmaf(q[t * ch + c], k[s * ch + c], acc);
+    w[t * (T + 1) + s] = acc;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += 128) {
+    float mx = -INFINITY;
+    for (int s = 0; s < T; ++s) mx = fmaxf(mx, w[t * (T + 1) + s]);
+    float sum = 0.f;
+    for (int s = 0; s < T; ++s) { const float e = expf(w[t * (T + 1) + s] - mx); w[t * (T + 1) + s] = e; sum += e; }
+    const float inv = 1.0f / sum;
+    for (int s = 0; s < T; ++s) w[t * (T + 1) + s] *= inv;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * ch; i += 128) {
+    const int t = i / ch, c = i % ch;
+    float acc = 0.f;
+    for (int s = 0; s < T; ++s) acc = fmaf(w[t * (T + 1) + s], v[s * ch + c], acc);
+    out[((size_t)b * T + t) * C + h * ch + c] = acc;
+  }
+}
+
+// first conv (1 -> 224, k=3, pad 1) and last conv (224 -> 1)
+__global__ void inconv_kernel(const float* __restrict__ x, int B, int L, int N, const float* __restrict__ W /*[3][N][1]*/,
+                              const float* __restrict__ bias, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * L * N) return;
+  const int n = i % N, l = (i / N) % L, b = i / (N * L);
+  const float* xr = x + (size_t)b * L;
+  float acc = 0.f;
+  if (l > 0) acc = fmaf(W[n], xr[l - 1], acc);
+  acc = fmaf(W[N + n], xr[l], acc);
+  if (l < L - 1) acc = fmaf(W[2 * N + n], xr[l + 1], acc);
+  out[i] = acc + bias[n];
+}
+
+__global__ void outconv_kernel(const float* __restrict__ a, int B, int L, int C, const float* __restrict__ W /*[3][1][C]*/,
+                               const float* __restrict__ bias, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * L) return;
+  const int l = warp % L, b = warp / L;
+  float acc = 0.f;
+  for (int tap = 0; tap < 3; ++tap) {
+    const int src = l + tap - 1;
+    if (src < 0 || src >= L) continue;
+    const float* ar = a + ((size_t)b * L + src) * C;
+    const float* wr = W + (size_t)tap * C;
+    for (int c = lane; c < C; c += 32) acc = fmaf(ar[c], wr[c], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[warp] = acc + bias[0];
+}
+
+// ---- embedding path ----------------------------------------------------------------------------
+// timestep_embedding: [cos(t*f_k) | sin(t*f_k)], f_k = exp(-ln(1e4) * k / 112) in fp32 (utils/ldm_utils.py:165-185)
+__global__ void temb_kernel(const int64_t* __restrict__ t, int B, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * (TCH / 2)) return;
+  const int k = i % (TCH / 2), b = i / (TCH / 2);
+  const float c = -9.210340371976184f;  // (float)(-math.log(10000))
+  const float f = expf(__fdiv_rn(__fmul_rn(c, (float)k), 112.0f));
+  const float arg = __fmul_rn((float)t[b], f);
+  out[(size_t)b * TCH + k] = cosf(arg);
+  out[(size_t)b * TCH + TCH / 2 + k] = sinf(arg);
+}
+
+// out[m][n] (+)= sum_k act(in[m][k]) * W[n][k] + bias[n];  M small (<= 8 rows per CTA pass); one warp per n.
+__global__ void __launch_bounds__(256)
+linear_rows_kernel(const float* __restrict__ in, int M, int K, const float* __restrict__ W, const float* __restrict__ bias, int N,
+                   int in_silu, int out_silu, int accumulate, float* __restrict__ out) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int mb = blockIdx.y * 8;
+  if (n >= N) return;
+  float acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+  const float* wr = W + (size_t)n * K;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 w = *reinterpret_cast<const float4*>(wr + k);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (mb + r < M) {
+        float4 x = *reinterpret_cast<const float4*>(in + (size_t)(mb + r) * K + k);
+        if (in_silu) {
+          x.x = x.x / (1.0f + expf(-x.x)); x.y = x.y / (1.0f + expf(-x.y));
+          x.z = x.z / (1.0f + expf(-x.z)); x.w = x.w / (1.0f + expf(-x.w));
+        }
+        acc[r] = fmaf(x.x, w.x, acc[r]); acc[r] = fmaf(x.y, w.y, acc[r]);
+        acc[r] = fmaf(x.z, w.z, acc[r]); acc[r] = fmaf(x.w, w.w, acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+  if (lane == 0) {
+    const float bv = bias[n];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (mb + r < M) {
+        float v = acc[r] + bv;
+        if (out_silu) v = v / (1.0f + expf(-v));
+        float* o = out + (size_t)(mb + r) * N + n;
+        *o = accumulate ? (*o + v) : v;
+      }
+    }
+  }
+}
+
+__global__ void label_add_kernel(const int64_t* __restrict__ y, int B, const float* __restrict__ table, float* __restrict__ emb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * EMB) return;
+  const int b = i / EMB, c = i % EMB;
+  emb[i] += table[(size_t)y[b] * EMB + c];
+}
+
+// ---- reverse-diffusion step bookkeeping -----------------------------------------------------------
+struct StepState {
+  int iter;        // loop iteration 0..n_steps-1 (step index = n_steps-1-iter)
+  int n_steps;
+};
+
+__global__ void step_begin_kernel(const StepState* __restrict__ st, const int64_t* __restrict__ tmap, int B, int64_t* __restrict__ t_cur) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const int idx = st->n_steps - 1 - st->iter;
+  t_cur[i] = tmap[idx];   // _WrappedModel: new_ts = map_tensor[ts]
+}
+
+// sample = (c1*x0 + c2*x_t) + ((t != 0) * std) * noise   -- unfused multiplies/adds like the reference's torch ops.
+// x0b != null: classifier-free guidance replay  x0 = x0b + scale * (x0a - x0b)   (models/cfg_sampler.py:19-26)
+__global__ void ddpm_update_kernel(StepState* __restrict__ st, const float* __restrict__ coef, const float* __restrict__ x0a,
+                                   const float* __restrict__ x0b, float scale, const float* __restrict__ noise, int n, float* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iter = st->iter, ns = st->n_steps;
+  const int idx = ns - 1 - iter;
+  if (i < n) {
+    float x0 = x0a[i];
+    if (x0b) x0 = __fadd_rn(x0b[i], __fmul_rn(scale, __fsub_rn(x0a[i], x0b[i])));
+    const float c1 = coef[idx], c2 = coef[ns + idx], sd = coef[2 * ns + idx];
+    const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x[i]));
+    const float mask = idx != 0 ? 1.0f : 0.0f;
+    const float nz = noise[(size_t)(1 + iter) * n + i];
+    x[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(mask, sd), nz));
+  }
+}
+
+__global__ void step_advance_kernel(StepState* st) { st->iter += 1; }
+
+}  // namespace surfd
+
 using namespace surfd;
-struct surfd_unet { int dummy; };
-extern "C" size_t surfd_unet_packed_floats(void) { return 0; }
-extern "C" int surfd_unet_create(const float*, size_t, int, int, int, surfd_unet**) { return set_error(SURFD_BAD_ARGUMENT, "sampler not built yet", __FILE__, __LINE__); }
-extern "C" void surfd_unet_destroy(surfd_unet*) {}
-extern "C" int surfd_unet_forward(surfd_unet*, int, const float*, const int64_t*, const float*, const int64_t*, float*, void*) { return set_error(SURFD_BAD_ARGUMENT, "sampler not built yet", __FILE__, __LINE__); }
-extern "C" int surfd_sample(surfd_unet*, int, int, const int64_t*, const float*, const float*, const float*, const int64_t*, float, float*, void*) { return set_error(SURFD_BAD_ARGUMENT, "sampler not built yet", __FILE__, __LINE__); }
+
+struct surfd_unet {
+  int L = 0, max_batch = 0;
+  DevBuf weights, pool, emb_all, temb, e1, emb, semb_unused, t_cur, x0a, x0b, xcur, state;
+  std::vector<int64_t> hdr, buf_sizes;
+  std::vector<std::vector<int64_t>> prog;
+  std::vector<size_t> buf_off;   // float offset per buffer for max_batch
+  int emb_cols = 0;
+  size_t n_floats = 0;
+  // cached step graph
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_B = -1;
+  const float* graph_ctx = nullptr;
+  const int64_t* graph_lab = nullptr;
+  const int64_t* graph_tmap = nullptr;
+  const float* graph_coef = nullptr;
+  const float* graph_noise = nullptr;
+  float graph_guidance = 1.f;
+  int64_t graph_launches = 0;
+
+  const float* w(int64_t off) const { return weights.as<float>() + off; }
+  float* buf(int64_t id) const { return pool.as<float>() + buf_off[(size_t)id]; }
+};
+
+extern "C" size_t surfd_unet_packed_floats(void) { return 0; }  // size depends on cond_mode; python validates via the arch walk
+
+extern "C" int surfd_unet_create(const float* packed, size_t n_floats, const int64_t* program, size_t n_prog, int L, int max_batch,
+                                 surfd_unet** out) {
+  SURFD_REQUIRE(packed && program && out, "null argument");
+  SURFD_REQUIRE(n_prog >= 16, "program too short");
+  SURFD_REQUIRE(max_batch >= 1 && max_batch <= 4096, "max_batch out of range");
+  surfd_unet* u = new surfd_unet();
+  u->L = L; u->max_batch = max_batch; u->n_floats = n_floats;
+  u->hdr.assign(program, program + 16);
+  const int64_t nb = u->hdr[0], np = u->hdr[1];
+  if ((size_t)(16 + nb + np * REC) != n_prog || u->hdr[13] != L) {
+    delete u;
+    return set_error(SURFD_BAD_ARGUMENT, "program/packing mismatch", __FILE__, __LINE__);
+  }
+  u->emb_cols = (int)u->hdr[2];
+  u->buf_sizes.assign(program + 16, program + 16 + nb);
+  for (int64_t i = 0; i < np; ++i) u->prog.emplace_back(program + 16 + nb + i * REC, program + 16 + nb + (i + 1) * REC);
+  size_t tot = 0;
+  for (int64_t i = 0; i < nb; ++i) { u->buf_off.push_back(tot); tot += (size_t)u->buf_sizes[i] * max_batch; }
+  auto fail = [&](int code) { surfd_unet_destroy(u); return code; };
+  int st;
+  if ((st = u->weights.reserve(n_floats * sizeof(float)))) return fail(st);
+  cudaError_t ce = cudaMemcpy(u->weights.p, packed, n_floats * sizeof(float), cudaMemcpyDefault);
+  if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
+  const size_t B = (size_t)max_batch;
+  if ((st = u->pool.reserve(tot * sizeof(float)))) return fail(st);
+  if ((st = u->emb_all.reserve(B * u->emb_cols * sizeof(float)))) return fail(st);
+  if ((st = u->temb.reserve(B * TCH * sizeof(float)))) return fail(st);
+  if ((st = u->e1.reserve(B * EMB * sizeof(float)))) return fail(st);
+  if ((st = u->emb.reserve(B * EMB * sizeof(float)))) return fail(st);
+  if ((st = u->t_cur.reserve(B * sizeof(int64_t)))) return fail(st);
+  if ((st = u->x0a.reserve(B * L * sizeof(float)))) return fail(st);
+  if ((st = u->x0b.reserve(B * L * sizeof(float)))) return fail(st);
+  if ((st = u->xcur.reserve(B * L * sizeof(float)))) return fail(st);
+  if ((st = u->state.reserve(sizeof(StepState)))) return fail(st);
+  ce = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * CT * CTP * (int)sizeof(float));
+  if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
+  *out = u;
+  return 0;
+}
+
+extern "C" void surfd_unet_destroy(surfd_unet* u) {
+  if (!u) return;
+  if (u->graph_exec) cudaGraphExecDestroy(u->graph_exec);
+  u->weights.release(); u->pool.release(); u->emb_all.release(); u->temb.release(); u->e1.release(); u->emb.release();
+  u->t_cur.release(); u->x0a.release(); u->x0b.release(); u->xcur.release(); u->state.release();
+  delete u;
+}
+
+// one model evaluation: x [B][L], t [B] -> x0 [B][L]
+static int unet_run(surfd_unet* u, int B, const float* x, const int64_t* t, const float* ctx, const int64_t* lab, float* x0,
+                    cudaStream_t st) {
+  const auto& h = u->hdr;
+  // ---- embedding ----
+  temb_kernel<<<(unsigned)cdiv((int64_t)B * (TCH / 2), 128), 128, 0, st>>>(t, B, u->temb.as<float>());
+  SURFD_CHECK_LAUNCH();
+  const dim3 g1((unsigned)cdiv(EMB, 8), (unsigned)cdiv(B, 8));
+  linear_rows_kernel<<<g1, 256, 0, st>>>(u->temb.as<float>(), B, TCH, u->w(h[5]), u->w(h[6]), EMB, 0, 1, 0, u->e1.as<float>());
+  SURFD_CHECK_LAUNCH();
+  linear_rows_kernel<<<g1, 256, 0, st>>>(u->e1.as<float>(), B, EMB, u->w(h[7]), u->w(h[8]), EMB, 0, 0, 0, u->emb.as<float>());
+  SURFD_CHECK_LAUNCH();
+  if (lab) {
+    SURFD_REQUIRE(h[11] >= 0, "labels given but the checkpoint has no label_emb");
+    label_add_kernel<<<(unsigned)cdiv((int64_t)B * EMB, 256), 256, 0, st>>>(lab, B, u->w(h[11]), u->emb.as<float>());
+    SURFD_CHECK_LAUNCH();
+  }
+  if (ctx) {
+    linear_rows_kernel<<<g1, 256, 0, st>>>(ctx, B, CTX, u->w(h[9]), u->w(h[10]), EMB, 0, 0, 1, u->emb.as<float>());
+    SURFD_CHECK_LAUNCH();
+  }
+  const dim3 g2((unsigned)cdiv(u->emb_cols, 8), (unsigned)cdiv(B, 8));
+  linear_rows_kernel<<<g2, 256, 0, st>>>(u->emb.as<float>(), B, EMB, u->w(h[3]), u->w(h[4]), u->emb_cols, 1, 0, 0, u->emb_all.as<float>());
+  SURFD_CHECK_LAUNCH();
+  // ---- program ----
+  for (const auto& r : u->prog) {
+    switch (r[0]) {
+      case OP_INCONV: {
+        const int N = (int)r[2], L = (int)r[3];
+        inconv_kernel<<<(unsigned)cdiv((int64_t)B * L * N, 256), 256, 0, st>>>(x, B, L, N, u->w(r[4]), u->w(r[5]), u->buf(r[1]));
+        SURFD_CHECK_LAUNCH();
+        break;
+      }
+      case OP_GN: {
+        const int C1 = (int)r[2], C2 = (int)r[4], T = (int)r[5];
+        gn_kernel<<<(unsigned)(B * 32), 128, 0, st>>>(u->buf(r[1]), C1, r[3] >= 0 ? u->buf(r[3]) : nullptr, C2, T, u->w(r[9]), u->w(r[10]),
+                                                      (int)r[8], u->buf(r[6]), r[7] >= 0 ? u->buf(r[7]) : nullptr);
+        SURFD_CHECK_LAUNCH();
+        break;
+      }
+      case OP_CONV: {
+        ConvArgs a{};
+        a.out = u->buf(r[1]); a.N = (int)r[2]; a.T_out = (int)r[3]; a.nseg = (int)r[4]; a.B = B;
+        for (int s = 0; s < a.nseg; ++s) {
+          const int64_t* q = &r[5 + 7 * s];
+          a.seg[s].A = u->buf(q[0]); a.seg[s].Cin = (int)q[1]; a.seg[s].taps = (int)q[2]; a.seg[s].stride = (int)q[3];
+          a.seg[s].up = (int)q[4]; a.seg[s].T_in = (int)q[5]; a.seg[s].W = u->w(q[6]);
+        }
+        a.bias = u->w(r[19]);
+        a.emb = r[20] >= 0 ? u->emb_all.as<float>() + r[20] : nullptr;
+        a.emb_ld = u->emb_cols;
+        a.residual = r[21] >= 0 ? u->buf(r[21]) : nullptr;
+        const dim3 grid((unsigned)(a.N / CT), (unsigned)cdiv((int64_t)B * a.T_out, CT));
+        conv_gemm_kernel<<<grid, 256, 8 * 2 * CT * CTP * sizeof(float), st>>>(a);
+        SURFD_CHECK_LAUNCH();
+        break;
+      }
+      case OP_ATTN: {
+        const int C = (int)r[2], T = (int)r[3], heads = (int)r[5];
+        const int ch = C / heads;
+        const float scale = (float)(1.0 / sqrt(sqrt((double)ch)));
+        const size_t smem = ((size_t)3 * T * ch + (size_t)T * (T + 1)) * sizeof(float);
+        attn_kernel<<<(unsigned)(B * heads), 128, smem, st>>>(u->buf(r[1]), C, T, heads, scale, u->buf(r[4]));
+        SURFD_CHECK_LAUNCH();
+        break;
+      }
+      case OP_OUTCONV: {
+        const int C = (int)r[2], T = (int)r[3];
+        outconv_kernel<<<(unsigned)cdiv((int64_t)B * T * 32, 256), 256, 0, st>>>(u->buf(r[1]), B, T, C, u->w(r[4]), u->w(r[5]), x0);
+        SURFD_CHECK_LAUNCH();
+        break;
+      }
+      default:
+        return set_error(SURFD_BAD_ARGUMENT, "unknown op in program", __FILE__, __LINE__);
+    }
+  }
+  return 0;
+}
+
+extern "C" int surfd_unet_forward(surfd_unet* u, int B, const float* x_dev, const int64_t* t_dev, const float* context_dev,
+                                  const int64_t* labels_dev, float* out_dev, void* stream) {
+  SURFD_REQUIRE(u && x_dev && t_dev && out_dev, "null argument");
+  SURFD_REQUIRE(B >= 1 && B <= u->max_batch, "batch exceeds max_batch");
+  return unet_run(u, B, x_dev, t_dev, context_dev, labels_dev, out_dev, (cudaStream_t)stream);
+}
+
+static int record_step(surfd_unet* u, int B, const int64_t* tmap, const float* coef, const float* noise, const float* ctx,
+                       const int64_t* lab, float guidance, cudaStream_t st) {
+  StepState* ss = u->state.as<StepState>();
+  step_begin_kernel<<<(unsigned)cdiv(B, 128), 128, 0, st>>>(ss, tmap, B, u->t_cur.as<int64_t>());
+  SURFD_CHECK_LAUNCH();
+  SURFD_TRY(unet_run(u, B, u->xcur.as<float>(), u->t_cur.as<int64_t>(), ctx, lab, u->x0a.as<float>(), st));
+  const bool cfg = guidance != 1.0f;
+  if (cfg) SURFD_TRY(unet_run(u, B, u->xcur.as<float>(), u->t_cur.as<int64_t>(), ctx, lab, u->x0b.as<float>(), st));
+  const int n = B * u->L;
+  ddpm_update_kernel<<<(unsigned)cdiv(n, 128), 128, 0, st>>>(ss, coef, u->x0a.as<float>(), cfg ? u->x0b.as<float>() : nullptr, guidance, noise,
+                                                             n, u->xcur.as<float>());
+  SURFD_CHECK_LAUNCH();
+  step_advance_kernel<<<1, 1, 0, st>>>(ss);
+  SURFD_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int surfd_sample(surfd_unet* u, int B, int n_steps, const int64_t* tmap_dev, const float* coef_dev, const float* noise_dev,
+                            const float* context_dev, const int64_t* labels_dev, float guidance, float* out_dev, void* stream) {
+  SURFD_REQUIRE(u && tmap_dev && coef_dev && noise_dev && out_dev, "null argument");
+  SURFD_REQUIRE(B >= 1 && B <= u->max_batch, "batch exceeds max_batch");
+  SURFD_REQUIRE(n_steps >= 1, "n_steps must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nbytes = (size_t)B * u->L * sizeof(float);
+  SURFD_CUDA(cudaMemcpyAsync(u->xcur.p, noise_dev, nbytes, cudaMemcpyDeviceToDevice, st));   // x_T = noise row 0
+  StepState init{0, n_steps};
+  SURFD_CUDA(cudaMemcpyAsync(u->state.p, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+  const bool reuse = u->graph_exec && u->graph_B == B && u->graph_ctx == context_dev && u->graph_lab == labels_dev &&
+                     u->graph_tmap == tmap_dev && u->graph_coef == coef_dev && u->graph_noise == noise_dev && u->graph_guidance == guidance;
+  if (!reuse) {
+    if (u->graph_exec) { cudaGraphExecDestroy(u->graph_exec); u->graph_exec = nullptr; }
+    // capture on a private stream so the caller's stream (possibly the legacy default) is left alone
+    cudaStream_t cs;
+    SURFD_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    int rc = 0;
+    if (ce == cudaSuccess) {
+      const int64_t launches_before = g_launch_count;
+      rc = record_step(u, B, tmap_dev, coef_dev, noise_dev, context_dev, labels_dev, guidance, cs);
+      u->graph_launches = g_launch_count - launches_before;
+      g_launch_count = launches_before;   // capture is not execution; launches are counted per replay below
+      ce = cudaStreamEndCapture(cs, &graph);
+    }
+    if (ce == cudaSuccess && rc == 0) ce = cudaGraphInstantiate(&u->graph_exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    cudaStreamDestroy(cs);
+    if (rc) return rc;
+    if (ce != cudaSuccess) { u->graph_exec = nullptr; return set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__); }
+    u->graph_B = B; u->graph_ctx = context_dev; u->graph_lab = labels_dev; u->graph_tmap = tmap_dev; u->graph_coef = coef_dev;
+    u->graph_noise = noise_dev; u->graph_guidance = guidance;
+  }
+  for (int i = 0; i < n_steps; ++i) {
+    SURFD_CUDA(cudaGraphLaunch(u->graph_exec, st));
+    g_launch_count += u->graph_launches;
+  }
+  SURFD_CUDA(cudaMemcpyAsync(out_dev, u->xcur.p, nbytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}

@@ -174,3 +174,22 @@ def poly_udf(pts, latent, seed=4321, r0=0.5, amp=0.05):
     r = poly_offsets(latent, seed, r0, amp).to(torch.float64)
     m = (pts.to(torch.float64) @ n.T - r).max(-1).values
     return 0.1 * (1 - torch.sigmoid(poly_logit(m.abs()))), m
+
+
+def synth_mdm(L=32, cond_mode="no_cond", seed=1234, num_actions=9):
+    """All-parameter-randomised diffusion checkpoint in the `model{step:09d}.pt` layout (flat state_dict, 'Unet.' keys,
+    no clip_model.*): tensors with dim>=2 ~ N(0,1)/sqrt(fan_in) -- including every zero_module site, which literal
+    random init would leave at 0 and make the model output identically 0 -- 1-D biases ~ 0.02 N(0,1),
+    GroupNorm weights 1, label_emb ~ N(0,1)/sqrt(896)."""
+    from .unet import expected_keys as unet_keys
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in unet_keys(L, cond_mode, num_actions).items():
+        is_gn_weight = k.endswith(".weight") and len(shp) == 1
+        if is_gn_weight:
+            sd[k] = torch.ones(shp)
+        elif len(shp) >= 2:
+            sd[k] = _fill(shp, gen, "weight")
+        else:
+            sd[k] = _fill(shp, gen, "bias")
+    return sd

@@ -128,6 +128,68 @@ def golden_mc():
     np.savez_compressed(os.path.join(OUT, "mc_fields.npz"), **out)
 
 
+def golden_unet():
+    """Reference MDM / SpacedDiffusion on the synthetic diffusion checkpoint: teacher-forced forwards and a 10-step
+    respaced p_sample_loop with injected noise (torch.randn patched to replay the recorded draws)."""
+    import argparse
+    from utils.model_util import create_model_and_diffusion, load_model_wo_clip
+    from diffusion.respace import SpacedDiffusion, space_timesteps
+    from diffusion import gaussian_diffusion as gd
+    from models.cfg_sampler import ClassifierFreeSampleModel
+    from surfd_b200.synth import synth_mdm
+    out = {}
+    for tag, L, cond in (("uncond32", 32, "no_cond"), ("img64", 64, "img"), ("cat32", 32, "category")):
+        args = argparse.Namespace(cond_mode=cond, num_actions=9, arch="OpenUNet", dataset="x", noise_schedule="cosine",
+                                  sigma_small=True, clip_value=0.1)
+        model, _ = create_model_and_diffusion(args)
+        load_model_wo_clip(model, synth_mdm(L, cond))
+        model.eval()
+        g = torch.Generator().manual_seed({"uncond32": 11, "img64": 12, "cat32": 13}[tag])
+        B = 3
+        x = torch.randn(B, 1, L, generator=g)
+        t = torch.tensor([0, 500, 999])
+        ctx = 0.5 * torch.randn(B, 512, generator=g) if cond == "img" else None
+        lab = torch.tensor([0, 4, 8]) if cond == "category" else None
+        y = {"context": ctx} if ctx is not None else ({"action_text": lab} if lab is not None else {})
+        with torch.no_grad():
+            o = model(x, t, y=y)
+        out[tag + "_x"] = x.numpy(); out[tag + "_t"] = t.numpy(); out[tag + "_out"] = o.numpy()
+        if ctx is not None: out[tag + "_ctx"] = ctx.numpy()
+        if lab is not None: out[tag + "_lab"] = lab.numpy()
+        print(tag, "forward out absmax", float(o.abs().max()))
+        if tag == "cat32":
+            continue
+        # 10-step respaced loop (BASELINE config 1) with replayed noise; CFG wrapper for the img model (scale 4)
+        diff = SpacedDiffusion(use_timesteps=space_timesteps(1000, [10]), betas=gd.get_named_beta_schedule("cosine", 1000, 1.),
+                               model_mean_type=gd.ModelMeanType.START_X, model_var_type=gd.ModelVarType.FIXED_SMALL,
+                               loss_type=gd.LossType.MSE, rescale_timesteps=False, args=args)
+        B = 2
+        noise = torch.randn(11, B, L, generator=g)
+        draws = [noise[1 + k][:, None, :].clone() for k in range(10)]
+        orig = torch.randn_like
+        torch.randn_like = lambda ref, *a, **k: draws.pop(0)
+        mk = {"y": {}}
+        m = model
+        if cond == "img":
+            mk = {"y": {"context": ctx[:B], "scale": torch.ones(B) * 4.0}}
+            # ClassifierFreeSampleModel asserts cond_mode == 'text' (cfg_sampler.py:21) while MDM.forward must take the
+            # `context` branch (the text branch would need CLIP weights; the arithmetic is identical, SURVEY 8(c)):
+            class _Mode(str):
+                def __contains__(self, item):
+                    return item == "img"
+            model.cond_mode = _Mode("text")
+            m = ClassifierFreeSampleModel(model)
+        try:
+            with torch.no_grad():
+                res = diff.p_sample_loop(m, (B, 1, L), noise=noise[0][:, None, :].clone(), clip_denoised=False, model_kwargs=mk,
+                                         skip_timesteps=0, init_image=None, progress=False, dump_steps=None, const_noise=False)
+        finally:
+            torch.randn_like = orig
+        out[tag + "_noise"] = noise.numpy(); out[tag + "_sample"] = res.numpy()
+        print(tag, "10-step sample absmax", float(res.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "unet.npz"), **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["decoder"]
     for w in what:
