@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- shapes/sec of the Surf-D generation hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of synthetic input: a 1000-step DDPM reverse process over the
+MDM/UNet for B latents, then per shape the coarse-to-fine UDF(+gradient) lattice at resolution N, MeshUDF marching
+cubes and the UDF face filter (the meshudf.py:379 boundary).  Workload at --gpus 1 = BASELINE.json configs[1]:
+uncond, random-init (all-parameter-randomised) MDM + the closed-form 'poly' AE checkpoint, 1000 steps, --resolution 256,
+batch 8.  With N GPUs every rank runs the same per-GPU batch on its own shapes (weak scaling, no data-path collective;
+one NCCL broadcast of the packed weights at start-up).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [...]                         # the reference's CPU implementation, bounded sample
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+RES = 256
+BATCH = 8
+LAT = 32
+STEPS_DDPM = 1000
+SEED = 10          # the CLI default --seed 10 (utils/parser_util.py:45 in the reference)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "200"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, reasons, mx = [], set(), None
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["sm_max_mhz"] = mx
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def make_noise(world, rank, batch, steps, L):
+    """x_T and the per-step randn_like draws from torch.manual_seed(10) on the CPU in full-batch order, sliced per rank."""
+    g = torch.Generator().manual_seed(SEED)
+    full = torch.randn(steps + 1, world * batch, L, generator=g)
+    return full[:, rank * batch:(rank + 1) * batch].contiguous()
+
+
+def bench_gpu(args):
+    import torch.distributed as dist
+    from surfd_b200 import _lib, synth, unet as U
+    from surfd_b200.decoder import pack_decoder
+    from surfd_b200.pipeline import SurfDPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- weights: rank 0 builds + packs, one NCCL broadcast of the flat blobs (mirrors dist_util.sync_params) ----
+    a = U.arch(LAT, "no_cond")
+    n_dec = _lib.load().surfd_dec_packed_floats(LAT)
+    if rank == 0:
+        blob_u, prog, _ = U.pack_unet(synth.synth_mdm(LAT, "no_cond"), LAT, "no_cond")
+        blob_d = pack_decoder(synth.synth_ae_poly(LAT)["decoder"], LAT)
+        blob_u, prog, blob_d = blob_u.to(dev), prog.to(dev), blob_d.to(dev)
+    else:
+        blob_u = torch.empty(a.n_floats, dtype=torch.float32, device=dev)
+        prog = torch.empty(16 + len(a.buffers) + len(a.prog) * U.REC, dtype=torch.int64, device=dev)
+        blob_d = torch.empty(n_dec, dtype=torch.float32, device=dev)
+    if world > 1:
+        for t in (blob_u, prog, blob_d):
+            dist.broadcast(t, 0)
+    pipe = SurfDPipeline(None, None, LAT, "no_cond", device=dev, max_batch=BATCH, mc_parallel=BATCH,
+                         packed_unet=(blob_u, prog.cpu()), packed_decoder=blob_d)
+    noise_host = make_noise(world, rank, BATCH, STEPS_DDPM, LAT).pin_memory()
+    noise_dev = noise_host.to(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / 1e3
+
+    last = {}
+
+    def step_resident():
+        lat, meshes, stats = pipe.generate(noise_dev, RES, n_steps=STEPS_DDPM)
+        last["stats"] = stats
+
+    def step_host():
+        latc, meshes, stats, h2d, d2h = pipe.generate_host(noise_host, RES, n_steps=STEPS_DDPM)
+        last["h2d"], last["d2h"] = h2d, d2h
+
+    clocks = ClockSampler(local)
+    _lib.load().surfd_launch_count(1)
+    # launches are counted over the timed steps only: reset after warm-up by timing warm-up separately
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    _lib.load().surfd_launch_count(1)
+    clocks.start()
+    t_res = timed(step_resident, args.steps, 0)
+    clk = clocks.stop()
+    launches = int(_lib.load().surfd_launch_count(0))
+    t_e2e = timed(step_host, args.steps, 1)
+
+    # per-stage breakdown of one more step (not part of the timed region)
+    tm = {}
+    pipe.generate(noise_dev, RES, n_steps=STEPS_DDPM, timings=tm)
+    stats = last["stats"]
+
+    # ---- roofline of the dominant kernel: the decoder's 512x512 layer GEMM, timed live in isolation ----
+    pk = peaks()
+    ms_layer, m_layer = pipe.decoder.time_layer(iters=20)
+    flops_layer = 2.0 * m_layer * 512 * 512
+    achieved = flops_layer / (ms_layer * 1e-3) / 1e12
+    # the FFMA path computes in fp32; the tensor-pipe peak it is held against is TF32 = 1/2 of the measured bf16 burst figure
+    peak = pk["bf16_tflops"] / 2.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "sgemm_nt_kernel (decoder 512x512 layer, fused bias+CBN+ReLU epilogue)",
+                "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "peak_source": pk["source"] + " bf16 burst / 2 (TF32-class contraction held to the tensor pipe)",
+                "flops_per_launch": flops_layer, "ms_per_launch": round(ms_layer, 4), "points_per_launch": m_layer}
+
+    out = None
+    if rank == 0:
+        total_shapes = world * BATCH * args.steps
+        out = {
+            "metric": "shapes/sec end-to-end (1000-step sample + UDF extract)", "value": round(total_shapes / t_res, 4), "unit": "shapes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_res / args.steps, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"uncond, all-parameter-randomised MDM + closed-form 'poly' AE checkpoint, {STEPS_DDPM} DDPM steps, "
+                                   f"--resolution {RES}, batch {BATCH}/GPU, GridFiller lattice (the scripts' default)",
+                       "resolution": RES, "batch_per_gpu": BATCH, "ddpm_steps": STEPS_DDPM, "latent": LAT, "parallelism": f"dp{world} (independent shapes)",
+                       "l2": "working set >> L2: 553 MB of UNet weights streamed per DDPM step, 268 MB lattice per shape"},
+            "e2e": {"value": round(total_shapes / t_e2e, 4), "unit": "shapes/s", "h2d_bytes_per_step": last["h2d"], "d2h_bytes_per_step": last["d2h"]},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "stages_s_per_step": {k: round(v, 4) for k, v in tm.items()},
+            "shape_stats": {"n_udf": stats[0]["n_udf"], "n_grad": stats[0]["n_grad"], "n_cand": stats[0]["n_cand"], "verts": stats[0]["n_verts"],
+                            "faces": stats[0]["n_faces"]},
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_reference(stats[0], quick=True)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU leg: the reference's algorithm on the host cores, on a bounded sample of the same workload.
+# This is the one place (besides tests/ and smoke()) that executes oracle/.
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference(shape_stats=None, quick=True):
+    import numpy as np
+    from oracle import decoder_oracle as DO, unet_oracle as UO
+    from surfd_b200 import synth, unet as U
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # (1) sampler: a few DDPM steps at the workload's batch, scaled to 1000
+    sd = synth.synth_mdm(LAT, "no_cond")
+    n_s = 3 if quick else 10
+    sched = U.SpacedSchedule(U.cosine_betas(), U.space_timesteps(1000, [n_s]))
+    g = torch.Generator().manual_seed(SEED)
+    noise = torch.randn(n_s + 1, BATCH, LAT, generator=g)
+    with torch.no_grad():
+        t0 = time.time(); UO.p_sample_loop(sd, sched, noise); t_steps = time.time() - t0
+    t_sample_batch = t_steps / n_s * STEPS_DDPM
+    # (2) decoder queries: points/s forward and forward+gradient on a sample, scaled by the shape's query counts
+    dsd = synth.synth_ae_poly(LAT)["decoder"]
+    lat = torch.randn(LAT, generator=g).numpy()
+    n_pts = 16384 if quick else 65536
+    pts = (torch.rand(n_pts, 3, generator=g) * 2 - 1).numpy()
+    t0 = time.time(); DO.forward(dsd, lat, pts); t_f = time.time() - t0
+    t0 = time.time(); DO.forward(dsd, lat, pts[: n_pts // 4], want_grad=True); t_g = time.time() - t0
+    fwd_pps, grad_pps = n_pts / t_f, (n_pts // 4) / t_g
+    st = shape_stats or {"n_udf": 848415, "n_grad": 259081, "n_faces_mc": 157956, "n_cand": 101239}
+    n_faces = st.get("n_faces_mc", st.get("n_faces", 157956))
+    t_lattice = st["n_udf"] / fwd_pps + st["n_grad"] / grad_pps
+    t_filter = 9 * n_faces / fwd_pps
+    # (3) marching cubes: the reference's own compiled Cython (oracle/_ref) on an analytic sphere at the workload resolution
+    t_mc, mc_kind = None, "port"
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from meshudf import _marching_cubes_lewiner_cy as cy
+        from meshudf._marching_cubes_lewiner import _get_mc_luts
+        from fields import analytic_field
+        n_mc = 128 if quick else RES
+        udf, gr = analytic_field("sphere", n_mc, 0.0, 0)
+        t0 = time.time(); cy.marching_cubes_udf(udf, gr, _get_mc_luts(), 1, 0, None); t_mc = (time.time() - t0) * (RES / n_mc) ** 3
+        mc_kind = "reference"
+    except Exception:
+        t_mc = 0.757  # SURVEY section 6 [probe] figure for N=256 when oracle/_ref is unavailable
+    per_shape = t_sample_batch / BATCH + t_lattice + t_mc + t_filter
+    return {"value": round(1.0 / per_shape, 6), "unit": "shapes/s", "cores": cores, "kind": "port" if mc_kind == "port" else "port+reference-mc",
+            "sample": f"{n_s} DDPM steps at batch {BATCH} (x{STEPS_DDPM // n_s}), {n_pts} decoder points fwd / {n_pts // 4} fwd+grad scaled to the "
+                      f"shape's {st['n_udf']} udf + {st['n_grad']} grad + {9 * n_faces} filter queries, reference Cython MC on a sphere "
+                      f"({'N=128 scaled x8' if quick else 'N=' + str(RES)})",
+            "seconds_per_shape": {"sample": round(t_sample_batch / BATCH, 3), "lattice": round(t_lattice, 3), "mc": round(t_mc, 3), "filter": round(t_filter, 3)}}
+
+
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    per = []
+    for _ in range(args.warmup + args.steps):
+        per.append(cpu_reference(None, quick=True))
+    keep = per[args.warmup:] or per
+    v = sum(p["value"] for p in keep) / len(keep)
+    cb = dict(keep[-1]); cb["value"] = round(v, 6)
+    out = {"impl": "reference", "metric": "shapes/sec end-to-end (1000-step sample + UDF extract)", "value": round(v, 6), "unit": "shapes/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * BATCH / v, 1), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"uncond, {STEPS_DDPM} DDPM steps, --resolution {RES}, batch {BATCH} -- reference algorithm on host cores, bounded sample",
+                      "resolution": RES, "batch_per_gpu": BATCH, "ddpm_steps": STEPS_DDPM},
+           "cpu_baseline": cb, "e2e": {"value": round(v, 6), "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": round(time.time() - t0, 1)}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="surfd_b200", choices=["surfd_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ddpm-steps", type=int, default=STEPS_DDPM, help="profiling runs only (ncu launch lists); the metric is defined at 1000")
+    ap.add_argument("--resolution", type=int, default=RES, help="profiling runs only; the N=1 workload is 256")
+    args = ap.parse_args()
+    globals()["STEPS_DDPM"] = args.ddpm_steps
+    globals()["RES"] = args.resolution
+    if args.impl == "reference":
+        return bench_reference(args)
+    bench_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,11 @@ int surfd_dec_set_latent(surfd_decoder* d, const float* lat_dev, void* stream);
 /* precision: 0 = fp32 FFMA (parity mode), 1 = TF32 tcgen05 tensor cores (fast mode) */
 int surfd_dec_set_precision(surfd_decoder* d, int mode);
 
+/* measurement hooks (bench.py): points per internal chunk; average duration of the dominant kernel (one 512x512
+ * layer GEMM over M <= chunk points) timed with CUDA events on `stream`, `iters` back-to-back launches. */
+int surfd_dec_chunk_points(surfd_decoder* d);
+int surfd_dec_time_layer(surfd_decoder* d, int M, int iters, float* ms_per_launch, void* stream);
+
 /* udf (and optionally -normalize(d udf/dx), meshudf.py:231-251) at explicit points.
  * pts_dev [M][3]; udf_dev [M]; grad_dev [M][3] or NULL.  Replaces udf_func / sample_udf /
  * sample_grads (meshudf.py:209-251) for the (CbnDecoder, latent) closure. */
@@ -77,6 +82,11 @@ void surfd_mc_destroy(surfd_mc* m);
  * count) and reports the vertex / face counts; surfd_mc_fetch() then copies them to caller memory. */
 int surfd_mc_udf(surfd_mc* m, const float* udf_dev, const float* grad_dev, int N, int64_t* n_v, int64_t* n_f,
                  int64_t* stats_host /* [8] or NULL: n_cand, n_seed, n_accept, n_unsure, n_nontrivial */, void* stream);
+/* The same in two halves, so several shapes can be in flight on different streams: _launch enqueues everything
+ * without a host synchronisation (the candidate count stays on the device); _finish waits for that stream and
+ * returns counts/status.  SURFD_CAPACITY from _finish means the per-handle buffers were grown: launch again. */
+int surfd_mc_launch(surfd_mc* m, const float* udf_dev, const float* grad_dev, int N, void* stream);
+int surfd_mc_finish(surfd_mc* m, int64_t* n_v, int64_t* n_f, int64_t* stats_host);
 int surfd_mc_fetch(surfd_mc* m, float* verts_dev /* [n_v][3] */, int32_t* faces_dev /* [n_f][3] */, void* stream);
 /* classification pass alone (HBM-bound scan, pyx:1157-1158,1215-1218): candidate bitmask words
  * [ceil(N^3/32)] and count; used by the benchmarks / tests. */

@@ -72,9 +72,9 @@ struct Compactor {
   int init();
   void destroy();
   // count(): per-block popcounts + exclusive offsets + total (device scalar d_total).
-  // scatter(): must follow count() on the same bits; out_list capacity >= total.
+  // scatter(): must follow count() on the same bits; writes the first `cap` positions (total > cap = truncated).
   int count(const uint32_t* bits, int64_t n_words, cudaStream_t st);
-  int scatter(const uint32_t* bits, int64_t n_words, int32_t* out_list, cudaStream_t st);
+  int scatter(const uint32_t* bits, int64_t n_words, int32_t* out_list, int64_t cap, cudaStream_t st);
   // copies d_total to host and synchronises the stream
   int read_total(int64_t* total, cudaStream_t st);
 };

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(int32_t* __restrict__
 
 __global__ void __launch_bounds__(kThreads) scatter_bits_kernel(const uint32_t* __restrict__ bits, int64_t n_words,
                                                                 const int32_t* __restrict__ block_offsets,
-                                                                int32_t* __restrict__ out) {
+                                                                int32_t* __restrict__ out, int64_t cap) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   uint32_t w = i < n_words ? bits[i] : 0u;
   int c = __popc(w);
@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(kThreads) scatter_bits_kernel(const uint32_t* 
   const int32_t base = (int32_t)(i * 32);
   while (w) {
     int b = __ffs(w) - 1;
-    out[pos++] = base + b;
+    if (pos < cap) out[pos] = base + b;   // the caller compares the total with cap to detect truncation
+    ++pos;
     w &= w - 1;
   }
 }
@@ -122,10 +123,10 @@ int Compactor::count(const uint32_t* bits, int64_t n_words, cudaStream_t st) {
   return 0;
 }
 
-int Compactor::scatter(const uint32_t* bits, int64_t n_words, int32_t* out_list, cudaStream_t st) {
+int Compactor::scatter(const uint32_t* bits, int64_t n_words, int32_t* out_list, int64_t cap, cudaStream_t st) {
   const int64_t nb = cdiv(n_words, kThreads);
   if (nb == 0) return 0;
-  scatter_bits_kernel<<<(unsigned)nb, kThreads, 0, st>>>(bits, n_words, block_counts.as<int32_t>(), out_list);
+  scatter_bits_kernel<<<(unsigned)nb, kThreads, 0, st>>>(bits, n_words, block_counts.as<int32_t>(), out_list, cap);
   SURFD_CHECK_LAUNCH();
   return 0;
 }

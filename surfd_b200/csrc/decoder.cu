@@ -626,7 +626,7 @@ static int lattice_grads(surfd_decoder* d, int N, float thr, float* udf_dev, flo
   *n_grad = cnt;
   if (cnt == 0) return 0;
   SURFD_TRY(d->list.reserve((size_t)cnt * sizeof(int32_t)));
-  SURFD_TRY(d->comp.scatter(d->bits.as<uint32_t>(), words, d->list.as<int32_t>(), st));
+  SURFD_TRY(d->comp.scatter(d->bits.as<uint32_t>(), words, d->list.as<int32_t>(), cnt, st));
   return lattice_eval(d, d->list.as<int32_t>(), 0, cnt, N, 1, N, true, udf_dev, grad_dev, st);
 }
 
@@ -679,7 +679,7 @@ extern "C" int surfd_udf_lattice(surfd_decoder* d, int N, int mode, double max_d
       n_udf += cnt;
       if (cnt > 0) {
         SURFD_TRY(d->list.reserve((size_t)cnt * sizeof(int32_t)));
-        SURFD_TRY(d->comp.scatter(d->bits.as<uint32_t>(), words, d->list.as<int32_t>(), st));
+        SURFD_TRY(d->comp.scatter(d->bits.as<uint32_t>(), words, d->list.as<int32_t>(), cnt, st));
         SURFD_TRY(lattice_eval(d, d->list.as<int32_t>(), 0, cnt, NL, stride, N, false, udf_dev, grad_dev, st));
       }
       if (NL < N) {
@@ -701,6 +701,32 @@ extern "C" int surfd_udf_lattice(surfd_decoder* d, int N, int mode, double max_d
   if (counts_host) { counts_host[0] = n_udf; counts_host[1] = n_grad; }
   return 0;
 }
+
+// Times the dominant kernel in isolation: `iters` launches of one 512x512 layer GEMM (fc_0 of block 0 with its CBN+ReLU
+// epilogue) over M points already resident in the handle's activation buffers, CUDA events on `stream`.
+extern "C" int surfd_dec_time_layer(surfd_decoder* d, int M, int iters, float* ms_per_launch, void* stream) {
+  SURFD_REQUIRE(d && d->latent_set && ms_per_launch, "decoder latent not set");
+  SURFD_REQUIRE(M >= 1 && M <= d->chunk && iters >= 1, "M/iters out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  SURFD_CUDA(cudaEventCreate(&e0));
+  SURFD_CUDA(cudaEventCreate(&e1));
+  Epilogue e{};
+  e.ld = HID; e.bias = d->b0(0); e.act = d->act(1); e.s2 = d->s(1); e.t2 = d->t(1);
+  SURFD_CUDA(cudaMemsetAsync(d->act(0), 0, (size_t)M * HID * sizeof(float), st));
+  for (int i = 0; i < 3; ++i) SURFD_TRY(d->precision == 0 ? launch_gemm(d->act(0), HID, d->W0(0), HID, M, HID, HID, e, st) : 0);
+  SURFD_CUDA(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) SURFD_TRY(launch_gemm(d->act(0), HID, d->W0(0), HID, M, HID, HID, e, st));
+  SURFD_CUDA(cudaEventRecord(e1, st));
+  SURFD_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  SURFD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_launch = ms / iters;
+  return 0;
+}
+
+extern "C" int surfd_dec_chunk_points(surfd_decoder* d) { return d ? d->chunk : 0; }
 
 extern "C" int surfd_face_filter(surfd_decoder* d, const double* verts64_dev, const int32_t* faces_dev, int64_t n_f, int N,
                                  uint8_t* keep_dev, void* stream) {

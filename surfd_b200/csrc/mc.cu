@@ -73,8 +73,16 @@ classify_kernel(const float* __restrict__ im, int N, float avg_t, float max_t, u
   }
 }
 
-__global__ void replay_kernel(surfd_mccore::Grid* g) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) surfd_mccore::replay(*g);
+// n_cand comes from the device-side compaction total, so the host never has to read it before the launch.
+__global__ void replay_kernel(surfd_mccore::Grid* g, const int64_t* __restrict__ n_cand_dev, int64_t cap_cand) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int64_t n = *n_cand_dev;
+    g->n_cand = n < cap_cand ? n : cap_cand;
+    g->n_cand_total = n;
+    if (n == 0) { g->n_v = 0; g->n_f3 = 0; g->status = surfd_mccore::MC_EMPTY; return; }
+    surfd_mccore::replay(*g);
+    if (n > cap_cand) g->status = surfd_mccore::MC_CAPACITY;   // candidate list truncated: caller retries with more room
+  }
 }
 
 }  // namespace surfd
@@ -83,9 +91,14 @@ using namespace surfd;
 
 struct surfd_mc {
   DevBuf bits, list, sgn, flg, face_layer, verts, faces, queues, grid_dev;
-  surfd_mccore::Grid* grid_host = nullptr;  // pinned
+  surfd_mccore::Grid* grid_host = nullptr;   // pinned: results land here
+  surfd_mccore::Grid* grid_stage = nullptr;  // pinned: launch parameters
   Compactor comp;
   int64_t n_v = 0, n_f3 = 0;
+  int64_t cap_cand = 0;
+  int N = 0;
+  bool pending = false;
+  cudaStream_t pending_stream = nullptr;
 };
 
 extern "C" int surfd_mc_create(surfd_mc** out) {
@@ -94,6 +107,7 @@ extern "C" int surfd_mc_create(surfd_mc** out) {
   int st = m->comp.init();
   if (st) { delete m; return st; }
   cudaError_t e = cudaMallocHost(&m->grid_host, sizeof(surfd_mccore::Grid));
+  if (e == cudaSuccess) e = cudaMallocHost(&m->grid_stage, sizeof(surfd_mccore::Grid));
   if (e != cudaSuccess) { m->comp.destroy(); delete m; return set_error(-(int)e, cudaGetErrorString(e), __FILE__, __LINE__); }
   st = m->grid_dev.reserve(sizeof(surfd_mccore::Grid));
   if (st) { surfd_mc_destroy(m); return st; }
@@ -106,6 +120,7 @@ extern "C" void surfd_mc_destroy(surfd_mc* m) {
   m->bits.release(); m->list.release(); m->sgn.release(); m->flg.release(); m->face_layer.release();
   m->verts.release(); m->faces.release(); m->queues.release(); m->grid_dev.release();
   if (m->grid_host) cudaFreeHost(m->grid_host);
+  if (m->grid_stage) cudaFreeHost(m->grid_stage);
   m->comp.destroy();
   delete m;
 }
@@ -141,58 +156,90 @@ extern "C" int surfd_mc_classify(surfd_mc* m, const float* udf_dev, int N, uint3
   return 0;
 }
 
-extern "C" int surfd_mc_udf(surfd_mc* m, const float* udf_dev, const float* grad_dev, int N, int64_t* n_v, int64_t* n_f,
-                            int64_t* stats, void* stream) {
-  SURFD_REQUIRE(m && udf_dev && grad_dev && n_v && n_f, "null argument");
+// Enqueue classification + compaction + ordered replay on `stream` without any host synchronisation: the
+// candidate count stays on the device and every buffer is sized from a per-handle capacity (grown on retry).
+extern "C" int surfd_mc_launch(surfd_mc* m, const float* udf_dev, const float* grad_dev, int N, void* stream) {
+  SURFD_REQUIRE(m && udf_dev && grad_dev, "null argument");
   SURFD_REQUIRE(N >= 2 && N <= 1024, "Input array must be at least 2x2x2.");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n3 = (int64_t)N * N * N;
   const int64_t words = cdiv(n3, 32);
+  m->N = N;
   SURFD_TRY(run_classify(m, udf_dev, N, st));
-  int64_t n_cand = 0;
-  SURFD_TRY(m->comp.read_total(&n_cand, st));
-  *n_v = 0; *n_f = 0; m->n_v = 0; m->n_f3 = 0;
-  if (stats) { for (int i = 0; i < 8; ++i) stats[i] = 0; stats[0] = n_cand; }
-  if (n_cand == 0) return SURFD_EMPTY_SURFACE;
-  SURFD_TRY(m->list.reserve((size_t)n_cand * sizeof(int32_t)));
-  SURFD_TRY(m->comp.scatter(m->bits.as<uint32_t>(), words, m->list.as<int32_t>(), st));
-
+  // capacity: candidates live in a thin shell around the surface, O(N^2); start at 8*N^2 (a sphere of radius 0.5
+  // gives ~1.55*N^2) and let surfd_mc_finish() report SURFD_CAPACITY so the wrapper can grow it.
+  int64_t cap = m->cap_cand > 0 ? m->cap_cand : 8ll * N * N;
+  if (cap > n3) cap = n3;
+  m->cap_cand = cap;
+  SURFD_TRY(m->list.reserve((size_t)cap * sizeof(int32_t)));
+  SURFD_TRY(m->comp.scatter(m->bits.as<uint32_t>(), words, m->list.as<int32_t>(), cap, st));
   SURFD_TRY(m->sgn.reserve((size_t)n3));
   SURFD_TRY(m->flg.reserve((size_t)n3));
   SURFD_TRY(m->face_layer.reserve((size_t)n3 * 4 * sizeof(int32_t)));
   SURFD_CUDA(cudaMemsetAsync(m->sgn.p, 0, (size_t)n3, st));
   SURFD_CUDA(cudaMemsetAsync(m->flg.p, 0, (size_t)n3, st));
   SURFD_CUDA(cudaMemsetAsync(m->face_layer.p, 0xFF, (size_t)n3 * 4 * sizeof(int32_t), st));
-  // every emitted vertex owns one of the 4 slots of some cell adjacent to a candidate cube; 13 corners per
-  // accepted cube is the hard bound for faces (12 triangles x 3 in the largest Lewiner tiling).
-  const int64_t cap_v = 13 * n_cand + 64;
-  const int64_t cap_f3 = 36 * n_cand + 64;
+  // observed V ~ 0.8 n_cand, 3F ~ 4.7 n_cand on closed surfaces; 3x / 12x leaves room for noisy fields
+  const int64_t cap_v = 3 * cap + 64;
+  const int64_t cap_f3 = 12 * cap + 64;
   SURFD_TRY(m->verts.reserve((size_t)cap_v * 3 * sizeof(float)));
   SURFD_TRY(m->faces.reserve((size_t)cap_f3 * sizeof(int32_t)));
   uint32_t qcap = 1024;
-  while ((int64_t)qcap < 16 * n_cand + 1024) qcap <<= 1;
+  while ((int64_t)qcap < 16 * cap + 1024) qcap <<= 1;
   SURFD_TRY(m->queues.reserve((size_t)qcap * 3 * sizeof(int32_t)));
 
   surfd_mccore::Grid& g = *m->grid_host;
   memset(&g, 0, sizeof(g));
   g.N = N; g.im = udf_dev; g.grads = grad_dev;
-  g.cand_bits = m->bits.as<uint32_t>(); g.cand_list = m->list.as<int32_t>(); g.n_cand = n_cand;
+  g.cand_bits = m->bits.as<uint32_t>(); g.cand_list = m->list.as<int32_t>(); g.n_cand = 0;
   g.sgn = m->sgn.as<int8_t>(); g.flg = m->flg.as<uint8_t>(); g.face_layer = m->face_layer.as<int32_t>();
   g.verts = m->verts.as<float>(); g.cap_v = cap_v; g.faces = m->faces.as<int32_t>(); g.cap_f3 = cap_f3;
   g.q.buf = m->queues.as<int32_t>(); g.q_unsure.buf = g.q.buf + qcap; g.q_nontrivial.buf = g.q.buf + 2 * (size_t)qcap;
   g.q.mask = g.q_unsure.mask = g.q_nontrivial.mask = qcap - 1;
-  SURFD_CUDA(cudaMemcpyAsync(m->grid_dev.p, &g, sizeof(g), cudaMemcpyHostToDevice, st));
-  replay_kernel<<<1, 32, 0, st>>>(m->grid_dev.as<surfd_mccore::Grid>());
+  // the launch struct is staged through a second pinned copy so grid_host can receive the results
+  memcpy(m->grid_stage, &g, sizeof(g));
+  SURFD_CUDA(cudaMemcpyAsync(m->grid_dev.p, m->grid_stage, sizeof(g), cudaMemcpyHostToDevice, st));
+  replay_kernel<<<1, 32, 0, st>>>(m->grid_dev.as<surfd_mccore::Grid>(), m->comp.d_total, cap);
   SURFD_CHECK_LAUNCH();
   SURFD_CUDA(cudaMemcpyAsync(&g, m->grid_dev.p, sizeof(g), cudaMemcpyDeviceToHost, st));
-  SURFD_CUDA(cudaStreamSynchronize(st));
+  m->pending_stream = st;
+  m->pending = true;
+  return 0;
+}
+
+// Wait for the launch on its stream and report counts / status.
+extern "C" int surfd_mc_finish(surfd_mc* m, int64_t* n_v, int64_t* n_f, int64_t* stats) {
+  SURFD_REQUIRE(m && n_v && n_f, "null argument");
+  SURFD_REQUIRE(m->pending, "surfd_mc_finish without surfd_mc_launch");
+  SURFD_CUDA(cudaStreamSynchronize(m->pending_stream));
+  m->pending = false;
+  const surfd_mccore::Grid& g = *m->grid_host;
   m->n_v = g.n_v; m->n_f3 = g.n_f3;
   *n_v = g.n_v; *n_f = g.n_f3 / 3;
-  if (stats) { stats[1] = g.n_seed; stats[2] = g.n_accept; stats[3] = g.n_unsure_push; stats[4] = g.n_nontrivial_push; }
-  if (g.status == surfd_mccore::MC_EMPTY) return SURFD_EMPTY_SURFACE;
-  if (g.status == surfd_mccore::MC_CAPACITY) return set_error(SURFD_CAPACITY, "marching cubes output bound exceeded", __FILE__, __LINE__);
+  if (stats) {
+    for (int i = 0; i < 8; ++i) stats[i] = 0;
+    stats[0] = g.n_cand_total; stats[1] = g.n_seed; stats[2] = g.n_accept; stats[3] = g.n_unsure_push; stats[4] = g.n_nontrivial_push;
+  }
+  if (g.status == surfd_mccore::MC_EMPTY) { m->n_v = m->n_f3 = 0; return SURFD_EMPTY_SURFACE; }
+  if (g.status == surfd_mccore::MC_CAPACITY) {
+    // grow for the retry: enough for the whole candidate set, or double when vertices/faces overflowed
+    int64_t want = g.n_cand_total > m->cap_cand ? g.n_cand_total + g.n_cand_total / 8 : 2 * m->cap_cand;
+    m->cap_cand = want;
+    m->n_v = m->n_f3 = 0;
+    return set_error(SURFD_CAPACITY, "marching cubes capacity exceeded; call again (buffers were grown)", __FILE__, __LINE__);
+  }
   if (g.status == surfd_mccore::MC_QUEUE_OVERFLOW) return set_error(SURFD_QUEUE_OVERFLOW, "marching cubes BFS queue overflow", __FILE__, __LINE__);
   return 0;
+}
+
+extern "C" int surfd_mc_udf(surfd_mc* m, const float* udf_dev, const float* grad_dev, int N, int64_t* n_v, int64_t* n_f,
+                            int64_t* stats, void* stream) {
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    SURFD_TRY(surfd_mc_launch(m, udf_dev, grad_dev, N, stream));
+    const int rc = surfd_mc_finish(m, n_v, n_f, stats);
+    if (rc != SURFD_CAPACITY) return rc;
+  }
+  return set_error(SURFD_CAPACITY, "marching cubes capacity exceeded after retries", __FILE__, __LINE__);
 }
 
 extern "C" int surfd_mc_fetch(surfd_mc* m, float* verts_dev, int32_t* faces_dev, void* stream) {

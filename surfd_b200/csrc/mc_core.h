@@ -85,6 +85,7 @@ struct Grid {
   const uint32_t* cand_bits;  // 1 bit per lattice index: cube anchored there passes avg/max thresholds
   const int32_t* cand_list;   // raster-sorted candidate cube indices
   int64_t n_cand;
+  int64_t n_cand_total;       // device-side compaction total (may exceed the list capacity)
   int8_t* sgn;                // signed_im in {-1,0,+1}         (zero-initialised)
   uint8_t* flg;               // bit0 signed_im_mask, bit1 visited (zero-initialised)
   int32_t* face_layer;        // [4*N^3] vertex slot per (cell, edge slot), initialised to -1

@@ -126,6 +126,13 @@ class UdfDecoder:
                                               _lib.ptr(udf), _lib.ptr(grad), counts, _lib.stream_ptr()))
         return udf, grad, (int(counts[0]), int(counts[1]))
 
+    def time_layer(self, iters=20):
+        """(ms per launch, points per launch) of the dominant kernel, CUDA-event timed on the current stream"""
+        M = int(self.lib.surfd_dec_chunk_points(self._h))
+        ms = ctypes.c_float()
+        _lib.check(self.lib.surfd_dec_time_layer(self._h, M, int(iters), ctypes.byref(ms), _lib.stream_ptr()))
+        return float(ms.value), M
+
     def face_filter(self, verts64, faces, N):
         """keep mask [F] (uint8) of meshudf.py:356-379."""
         verts64 = verts64.to(self.device, torch.float64).contiguous()

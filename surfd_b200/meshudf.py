@@ -15,6 +15,22 @@ from . import _lib
 from .decoder import UdfDecoder
 
 
+class _nullctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def finish_mesh(verts_raw, faces_raw, N, coords_range=(-1, 1)):
+    """udf_mc_lewiner's finishing touches + `vertices += coords_range[0]` (float64), on device."""
+    spacing = (coords_range[1] - coords_range[0]) / (N - 1)
+    vertices = torch.flip(verts_raw, dims=[1]).to(torch.float64) * torch.tensor([spacing] * 3, dtype=torch.float64, device=verts_raw.device)
+    faces = torch.flip(faces_raw, dims=[1]).contiguous()
+    return vertices + coords_range[0], faces
+
+
 class MarchingCubes:
     """Handle owning the marching-cubes workspaces (reused across shapes)."""
 
@@ -57,6 +73,32 @@ class MarchingCubes:
         verts = torch.empty(nv.value, 3, device=self.device, dtype=torch.float32)
         faces = torch.empty(nf.value, 3, device=self.device, dtype=torch.int32)
         _lib.check(self.lib.surfd_mc_fetch(self._h, _lib.ptr(verts), _lib.ptr(faces), _lib.stream_ptr()))
+        return verts, faces
+
+    def launch(self, volume, grads, stream=None):
+        """enqueue classification + replay on `stream` (torch.cuda.Stream or None = current); no host sync"""
+        N = volume.shape[0]
+        assert volume.is_cuda and grads.is_cuda and volume.dtype == torch.float32 and volume.is_contiguous() and grads.is_contiguous()
+        self._inputs = (volume, grads)          # keep alive until finish()
+        sp = ctypes.c_void_p(stream.cuda_stream) if stream is not None else _lib.stream_ptr()
+        _lib.check(self.lib.surfd_mc_launch(self._h, _lib.ptr(volume), _lib.ptr(grads), N, sp))
+        self._stream = stream
+
+    def finish(self):
+        """wait for launch(); returns (verts float32 [V,3], faces int32 [F,3]) or None when the buffers had to grow
+        (call launch() again).  Raises RuntimeError('No surface found...') like the reference."""
+        nv, nf = ctypes.c_int64(), ctypes.c_int64()
+        stats = (ctypes.c_int64 * 8)()
+        rc = self.lib.surfd_mc_finish(self._h, ctypes.byref(nv), ctypes.byref(nf), stats)
+        self.last_stats = dict(n_cand=stats[0], n_seed=stats[1], n_accept=stats[2], n_unsure=stats[3], n_nontrivial=stats[4])
+        if rc == _lib.SURFD_CAPACITY:
+            return None
+        _lib.check(rc)
+        verts = torch.empty(nv.value, 3, device=self.device, dtype=torch.float32)
+        faces = torch.empty(nf.value, 3, device=self.device, dtype=torch.int32)
+        # surfd_mc_finish() synchronised the replay's stream, so the copy can run on the caller's current stream
+        _lib.check(self.lib.surfd_mc_fetch(self._h, _lib.ptr(verts), _lib.ptr(faces), _lib.stream_ptr()))
+        self._inputs = None
         return verts, faces
 
     def classify(self, volume):

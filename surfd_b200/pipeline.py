@@ -1,0 +1,126 @@
+"""The generation hot path end to end on one GPU: reverse diffusion -> per-shape UDF lattice -> marching cubes ->
+UDF face filter, i.e. what `sample/generate_*.py` run between "x_T drawn" and the meshudf.py:379 boundary.
+
+Shapes are independent.  The decoder work (lattice, face filter) runs on the main stream; each shape's ordered
+marching-cubes replay (a single-CTA, latency-bound kernel) runs on a side stream with its own workspace, so up to
+`mc_parallel` replays overlap with each other and with the next shapes' lattices.
+"""
+import time
+
+import torch
+
+from . import unet as U
+from .decoder import UdfDecoder
+from .meshudf import MarchingCubes, finish_mesh
+
+
+class SurfDPipeline:
+    def __init__(self, mdm_state, ae_state, latent_dim=32, cond_mode="no_cond", device="cuda", max_batch=64, mc_parallel=8,
+                 num_actions=9, packed_unet=None, packed_decoder=None):
+        self.device = torch.device(device)
+        self.L = latent_dim
+        self.sampler = U.UNetSampler(mdm_state, latent_dim, cond_mode, num_actions, device=device, max_batch=max_batch,
+                                     packed=packed_unet)
+        self.decoder = UdfDecoder(ae_state, latent_dim, device=device, packed=packed_decoder)
+        self.mcs = [MarchingCubes(device) for _ in range(mc_parallel)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(mc_parallel)]
+        self.schedule_cache = {}
+
+    def schedule(self, n_steps=1000, noise_schedule="cosine"):
+        key = (n_steps, noise_schedule)
+        if key not in self.schedule_cache:
+            betas = U.cosine_betas() if noise_schedule == "cosine" else U.linear_betas()
+            self.schedule_cache[key] = U.SpacedSchedule(betas, U.space_timesteps(1000, [n_steps]))
+        return self.schedule_cache[key]
+
+    def sample_latents(self, noise, context=None, labels=None, guidance=1.0, n_steps=1000, noise_schedule="cosine"):
+        return self.sampler.sample(self.schedule(n_steps, noise_schedule), noise, context, labels, guidance)
+
+    def extract(self, latents, N, use_fast_grid_filler=True, max_dist=0.1, timings=None):
+        """latents [B,1,L] (device) -> list of (verts float32 [V,3], faces int64 [F,3]) + per-shape stats"""
+        B = latents.shape[0]
+        dec = self.decoder
+        P = len(self.mcs)
+        meshes, stats = [None] * B, [None] * B
+        main = torch.cuda.current_stream(self.device)
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        t_lat = t_filter = 0.0
+        for w0 in range(0, B, P):
+            wave = list(range(w0, min(B, w0 + P)))
+            fields = {}
+            marks = []
+            for j, k in enumerate(wave):
+                e0, e1 = ev(), ev()
+                e0.record(main)
+                dec.set_latent(latents[k])
+                udf, grads, counts = dec.lattice(N, use_fast_grid_filler=use_fast_grid_filler, max_dist=max_dist)
+                udf.clamp_(min=0)                                    # udf[udf < 0] = 0  (meshudf.py:342)
+                e1.record(main)
+                marks.append((e0, e1))
+                fields[k] = (udf, grads, counts)
+                self.streams[j].wait_event(e1)
+                self.mcs[j].launch(udf, grads, self.streams[j])
+            for j, k in enumerate(wave):
+                udf, grads, counts = fields[k]
+                res = self.mcs[j].finish()
+                while res is None:                                   # buffers were grown: run this shape again
+                    self.mcs[j].launch(udf, grads, self.streams[j])
+                    res = self.mcs[j].finish()
+                verts_raw, faces_raw = res
+                e0, e1 = ev(), ev()
+                e0.record(main)
+                vertices, faces = finish_mesh(verts_raw, faces_raw, N)
+                dec.set_latent(latents[k])
+                keep = dec.face_filter(vertices, faces, N)
+                faces_kept = faces[keep.bool()]
+                e1.record(main)
+                marks.append((e0, e1, "f"))
+                meshes[k] = (vertices.to(torch.float32), faces_kept.to(torch.int64))
+                stats[k] = dict(n_udf=counts[0], n_grad=counts[1], n_verts=int(vertices.shape[0]), n_faces_mc=int(faces.shape[0]),
+                                n_faces=int(faces_kept.shape[0]), **self.mcs[j].last_stats)
+                del fields[k]
+            if timings is not None:
+                torch.cuda.synchronize(self.device)
+                for m in marks:
+                    dt = m[0].elapsed_time(m[1]) / 1e3
+                    if len(m) == 3:
+                        t_filter += dt
+                    else:
+                        t_lat += dt
+        if timings is not None:
+            timings["lattice_s"] = timings.get("lattice_s", 0.0) + t_lat
+            timings["filter_s"] = timings.get("filter_s", 0.0) + t_filter
+        return meshes, stats
+
+    def generate(self, noise, N, context=None, labels=None, guidance=1.0, n_steps=1000, use_fast_grid_filler=True,
+                 noise_schedule="cosine", timings=None):
+        """noise [n_steps+1, B, L] on the device.  Returns (latents [B,1,L], meshes, stats)."""
+        if timings is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        lat = self.sample_latents(noise, context, labels, guidance, n_steps, noise_schedule)
+        if timings is not None:
+            e1.record(); torch.cuda.synchronize(self.device)
+            timings["sample_s"] = timings.get("sample_s", 0.0) + e0.elapsed_time(e1) / 1e3
+        meshes, stats = self.extract(lat, N, use_fast_grid_filler, timings=timings)
+        return lat, meshes, stats
+
+    def generate_host(self, noise_host, N, context_host=None, labels_host=None, **kw):
+        """The call a user of the scripts makes, with HOST buffers: pinned noise/conditioning in, meshes out to host memory.
+        Returns (latents_cpu, [(verts_cpu, faces_cpu)], stats, h2d_bytes, d2h_bytes)."""
+        h2d = noise_host.numel() * noise_host.element_size()
+        noise = noise_host.to(self.device, non_blocking=True)
+        ctx = lab = None
+        if context_host is not None:
+            ctx = context_host.to(self.device, non_blocking=True); h2d += context_host.numel() * context_host.element_size()
+        if labels_host is not None:
+            lab = labels_host.to(self.device, non_blocking=True); h2d += labels_host.numel() * labels_host.element_size()
+        lat, meshes, stats = self.generate(noise, N, ctx, lab, **kw)
+        out, d2h = [], 0
+        for v, f in meshes:
+            vc, fc = v.cpu(), f.cpu()
+            d2h += vc.numel() * 4 + fc.numel() * 8
+            out.append((vc, fc))
+        latc = lat.cpu()
+        d2h += latc.numel() * 4
+        return latc, out, stats, h2d, d2h

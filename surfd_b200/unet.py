@@ -327,11 +327,17 @@ class SpacedSchedule:
 class UNetSampler:
     """Device-resident denoiser + reverse-diffusion loop (one per GPU process)."""
 
-    def __init__(self, state_dict, L=32, cond_mode="no_cond", num_actions=9, device="cuda", max_batch=64):
+    def __init__(self, state_dict, L=32, cond_mode="no_cond", num_actions=9, device="cuda", max_batch=64, packed=None):
+        """`packed` = (blob, prog) from pack_unet() (e.g. received by NCCL broadcast) instead of a state_dict."""
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.L, self.cond_mode = L, cond_mode
-        blob, prog, self.arch = pack_unet(state_dict, L, cond_mode, num_actions)
+        if packed is not None:
+            blob, prog = packed
+            self.arch = arch(L, cond_mode, num_actions)
+            assert blob.numel() == self.arch.n_floats
+        else:
+            blob, prog, self.arch = pack_unet(state_dict, L, cond_mode, num_actions)
         self.n_weight_floats = blob.numel()
         h = ctypes.c_void_p()
         with torch.cuda.device(self.device):

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Quick stage timings on the GPU box (not the benchmark of record): decoder throughput, lattice, marching cubes."""
-import json, sys, time
+"""Stage timings on the GPU box (not the benchmark of record): decoder throughput, lattice, marching cubes, sampler.
+Writes gpurun_out/probe.json."""
+import json, os, sys, time
 import torch
 sys.path.insert(0, ".")
-from surfd_b200 import synth, _lib
+from surfd_b200 import synth, _lib, unet as U
 from surfd_b200.decoder import UdfDecoder
 from surfd_b200.meshudf import MarchingCubes, get_mesh_from_udf, DecoderUdf
 
@@ -31,18 +32,32 @@ def main():
     res["fwd_pts_per_s"] = M / t; res["fwd_tflops"] = M * 5.308e6 / t / 1e12
     t, _ = timed(lambda: dec.query(pts, want_grad=True))
     res["fwdbwd_pts_per_s"] = M / t; res["fwdbwd_tflops"] = M * (5.308e6 + 10.617e6) / t / 1e12
+    ms, m = dec.time_layer(20)
+    res["layer_gemm_ms"] = ms; res["layer_gemm_tflops"] = 2 * m * 512 * 512 / ms / 1e9
     mc = MarchingCubes()
-    for N in (128, 256):
-        for fast in (True, False):
-            t, (u, g, c) = timed(lambda: dec.lattice(N, fast), n=2)
-            res[f"lattice_N{N}_{'gf' if fast else 'dense'}_s"] = t; res[f"lattice_N{N}_{'gf' if fast else 'dense'}_counts"] = c
+    sizes = [int(a) for a in sys.argv[1:]] or [128, 256]
+    for N in sizes:
+        t, (u, g, c) = timed(lambda: dec.lattice(N, True), n=2)
+        res[f"lattice_N{N}_gf_s"] = t; res[f"lattice_N{N}_gf_counts"] = c
         t, (v, f) = timed(lambda: mc.run_raw(u.clamp(min=0), g), n=2)
         res[f"mc_N{N}_s"] = t; res[f"mc_N{N}_VF"] = [v.shape[0], f.shape[0]]; res[f"mc_N{N}_stats"] = mc.last_stats
         t, n = timed(lambda: mc.classify(u), n=3)
-        res[f"classify_N{N}_s"] = t
+        res[f"classify_call_N{N}_s"] = t
         t, out = timed(lambda: get_mesh_from_udf(DecoderUdf(dec, lat), (-1, 1), 0.1, N=N, differentiable=False, max_batch=2**16, return_stats=True), n=2)
         res[f"mesh_N{N}_s"] = t; res[f"mesh_N{N}_stats"] = out[2]
+    # sampler
+    net = U.UNetSampler(synth.synth_mdm(L), L, max_batch=8)
+    for B in (1, 8):
+        x = torch.randn(B, 1, L, generator=gen); tt = torch.full((B,), 500)
+        t, _ = timed(lambda: net.forward(x, tt), n=5)
+        res[f"unet_forward_B{B}_ms"] = t * 1e3
+        S = U.SpacedSchedule(U.cosine_betas(), U.space_timesteps(1000, [100]))
+        noise = torch.randn(101, B, L, generator=gen).cuda()
+        t, _ = timed(lambda: net.sample(S, noise), n=2)
+        res[f"sample_100steps_B{B}_ms_per_step"] = t * 10
     res["launches"] = int(_lib.load().surfd_launch_count(0))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/probe.json", "w"), indent=1)
     print(json.dumps(res, indent=1))
 
 
