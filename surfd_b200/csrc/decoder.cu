@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "decoder_common.cuh"
 
 namespace surfd {
 
@@ -30,18 +31,6 @@ constexpr int NCBN = 11;
 // ------------------------------------------------------------------------------------------------
 // SGEMM (NT): C[m][n] = sum_k A[m][k] * W[n][k], fp32 FFMA, 128x128x16 tiles, 8x8 per thread.
 // ------------------------------------------------------------------------------------------------
-struct Epilogue {
-  const float* bias;    // [N] or null
-  const float* mask;    // [M][ld] activation buffer: v = mask>0 ? v*mscale[n] : 0   (relu/CBN backward)
-  const float* mscale;  // [N]
-  const float* R;       // residual [M][ld] or null (may alias C)
-  float* C;             // [M][ld] or null
-  float* act;           // [M][ld] or null : relu(s2[n]*v + t2[n])
-  const float* s2;
-  const float* t2;
-  int ld;
-};
-
 constexpr int BM = 128, BN = 128, BK = 16;
 
 __global__ void __launch_bounds__(256, 2)
@@ -135,11 +124,16 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
         const float4 r = *reinterpret_cast<const float4*>(e.R + off);
         v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
       }
-      if (e.C) *reinterpret_cast<float4*>(e.C + off) = v;
+      if (e.C) {
+        float4 o = v;
+        if (e.round_c) { o.x = round_to_tf32(o.x); o.y = round_to_tf32(o.y); o.z = round_to_tf32(o.z); o.w = round_to_tf32(o.w); }
+        *reinterpret_cast<float4*>(e.C + off) = o;
+      }
       if (e.act) {
         float4 a;
         a.x = fmaxf(fmaf(s2.x, v.x, t2.x), 0.f); a.y = fmaxf(fmaf(s2.y, v.y, t2.y), 0.f);
         a.z = fmaxf(fmaf(s2.z, v.z, t2.z), 0.f); a.w = fmaxf(fmaf(s2.w, v.w, t2.w), 0.f);
+        if (e.round_act) { a.x = round_to_tf32(a.x); a.y = round_to_tf32(a.y); a.z = round_to_tf32(a.z); a.w = round_to_tf32(a.w); }
         *reinterpret_cast<float4*>(e.act + off) = a;
       }
     }
@@ -411,6 +405,9 @@ struct surfd_decoder {
   int precision = 0;
   DevBuf weights;    // packed blob
   DevBuf wT;         // transposes: WpT [64][512], then 5x{W0T, W1T}
+  DevBuf wR;         // TF32-rounded (rna) copies for the tensor-core path: 5x{W0, W1}, then 5x{W0T, W1T}
+  DevBuf err;        // int error flag written by the tcgen05 kernel's bounded waits
+  int num_sms = 148;
   DevBuf fold;       // s[11][512], t[11][512]
   DevBuf acts;       // 11 x [chunk][512]
   DevBuf net, dnet, dh, enc, de, pts, dudf, udf_tmp;
@@ -432,6 +429,10 @@ struct surfd_decoder {
   const float* WpT() const { return wT.as<float>(); }
   const float* W0T(int i) const { return WpT() + ENC * HID + (size_t)i * 2 * HID * HID; }
   const float* W1T(int i) const { return W0T(i) + HID * HID; }
+  const float* W0r(int i) const { return wR.as<float>() + (size_t)i * 2 * HID * HID; }
+  const float* W1r(int i) const { return W0r(i) + HID * HID; }
+  const float* W0Tr(int i) const { return wR.as<float>() + (size_t)NBLK * 2 * HID * HID + (size_t)i * 2 * HID * HID; }
+  const float* W1Tr(int i) const { return W0Tr(i) + HID * HID; }
   const float* s(int layer) const { return fold.as<float>() + layer * HID; }
   const float* t(int layer) const { return fold.as<float>() + (NCBN + layer) * HID; }
   float* act(int i) const { return acts.as<float>() + (size_t)i * chunk * HID; }
@@ -442,6 +443,14 @@ extern "C" size_t surfd_dec_packed_floats(int L) {
          (size_t)NCBN * ((size_t)HID * L * 2 + 4 * HID);
 }
 
+__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(in[i]));
+  out[i] = __uint_as_float(u);
+}
+
 static int launch_gemm(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const Epilogue& e,
                        cudaStream_t st) {
   const int tiles = (int)(cdiv(M, BM) * cdiv(N, BN));
@@ -449,6 +458,9 @@ static int launch_gemm(const float* A, int lda, const float* W, int ldw, int M, 
   SURFD_CHECK_LAUNCH();
   return 0;
 }
+
+// a 512x512 layer: FFMA kernel (precision 0) or tcgen05 TF32 kernel (precision 1; Wr = TF32-rounded weights)
+static int gemm512(surfd_decoder* d, const float* A, const float* W, const float* Wr, int M, Epilogue e, cudaStream_t st);
 
 extern "C" int surfd_dec_create(const float* packed, size_t n_floats, int L, int packed_on_device, int max_chunk,
                                 surfd_decoder** out) {
@@ -480,6 +492,14 @@ extern "C" int surfd_dec_create(const float* packed, size_t n_floats, int L, int
   if ((st = d->udf_tmp.reserve(c * sizeof(float)))) return fail(st);
   if ((st = d->dst.reserve(c * sizeof(int32_t)))) return fail(st);
   if ((st = d->comp.init())) return fail(st);
+  if ((st = d->wR.reserve((size_t)4 * NBLK * HID * HID * sizeof(float)))) return fail(st);
+  if ((st = d->err.reserve(sizeof(int)))) return fail(st);
+  cudaMemset(d->err.p, 0, sizeof(int));
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) d->num_sms = sms;
+  }
   // transposed weight copies for the input-gradient pass
   {
     dim3 blk(32, 8);
@@ -490,6 +510,16 @@ extern "C" int surfd_dec_create(const float* packed, size_t n_floats, int L, int
       transpose_kernel<<<dim3(HID / 32, HID / 32), blk>>>(d->W1(i), HID, HID, const_cast<float*>(d->W1T(i)));
       g_launch_count += 2;
     }
+    // TF32 (round-to-nearest) copies for the tensor-core path
+    const size_t nn = (size_t)HID * HID;
+    for (int i = 0; i < NBLK; ++i) {
+      const float* src[4] = {d->W0(i), d->W1(i), d->W0T(i), d->W1T(i)};
+      float* dst[4] = {const_cast<float*>(d->W0r(i)), const_cast<float*>(d->W1r(i)), const_cast<float*>(d->W0Tr(i)), const_cast<float*>(d->W1Tr(i))};
+      for (int k = 0; k < 4; ++k) {
+        round_tf32_kernel<<<(unsigned)cdiv(nn, 256), 256>>>(src[k], dst[k], nn);
+        ++g_launch_count;
+      }
+    }
     ce = cudaDeviceSynchronize();
     if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
   }
@@ -499,6 +529,7 @@ extern "C" int surfd_dec_create(const float* packed, size_t n_floats, int L, int
 
 extern "C" void surfd_dec_destroy(surfd_decoder* d) {
   if (!d) return;
+  d->wR.release(); d->err.release();
   d->weights.release(); d->wT.release(); d->fold.release(); d->acts.release(); d->net.release(); d->dnet.release();
   d->dh.release(); d->enc.release(); d->de.release(); d->pts.release(); d->dudf.release(); d->udf_tmp.release();
   d->dst.release(); d->bits.release(); d->list.release(); d->gf_state.release();
@@ -508,9 +539,14 @@ extern "C" void surfd_dec_destroy(surfd_decoder* d) {
 
 extern "C" int surfd_dec_set_precision(surfd_decoder* d, int mode) {
   SURFD_REQUIRE(d != nullptr, "null decoder");
-  SURFD_REQUIRE(mode == 0, "only precision mode 0 (fp32) is built in this version");
+  SURFD_REQUIRE(mode == 0 || mode == 1, "precision mode must be 0 (fp32 FFMA) or 1 (TF32 tcgen05)");
   d->precision = mode;
   return 0;
+}
+
+static int gemm512(surfd_decoder* d, const float* A, const float* W, const float* Wr, int M, Epilogue e, cudaStream_t st) {
+  if (d->precision == 0) return launch_gemm(A, HID, W, HID, M, HID, HID, e, st);
+  return launch_gemm_tc(A, Wr, M, e, d->err.as<int>(), d->num_sms, st);
 }
 
 extern "C" int surfd_dec_set_latent(surfd_decoder* d, const float* lat_dev, void* stream) {
@@ -531,20 +567,22 @@ static int dec_forward(surfd_decoder* d, int M, bool keep_acts, float* udf_out, 
   encode_kernel<<<(unsigned)cdiv(M, 128), 128, 0, st>>>(d->pts.as<float>(), M, E);
   SURFD_CHECK_LAUNCH();
   auto A = [&](int layer) { return keep_acts ? d->act(layer) : d->act(layer & 1); };
+  const int tcm = d->precision == 1 ? 1 : 0;
   Epilogue e{};
   e.ld = HID;
-  // net = fc_p(E);  act0 = relu(cbn_0(net))
-  e.bias = d->bp(); e.C = net; e.act = A(0); e.s2 = d->s(0); e.t2 = d->t(0);
+  // net = fc_p(E);  act0 = relu(cbn_0(net))   (K = 64: always the fp32 FFMA kernel, the positional encoding stays exact)
+  e.bias = d->bp(); e.C = net; e.act = A(0); e.s2 = d->s(0); e.t2 = d->t(0); e.round_act = tcm;
   SURFD_TRY(launch_gemm(E, ENC, d->Wp(), ENC, M, HID, ENC, e, st));
   for (int i = 0; i < NBLK; ++i) {
     // h = fc_0(act);  act' = relu(cbn_1(h))
     Epilogue e0{};
-    e0.ld = HID; e0.bias = d->b0(i); e0.act = A(2 * i + 1); e0.s2 = d->s(2 * i + 1); e0.t2 = d->t(2 * i + 1);
-    SURFD_TRY(launch_gemm(A(2 * i), HID, d->W0(i), HID, M, HID, HID, e0, st));
+    e0.ld = HID; e0.bias = d->b0(i); e0.act = A(2 * i + 1); e0.s2 = d->s(2 * i + 1); e0.t2 = d->t(2 * i + 1); e0.round_act = tcm;
+    SURFD_TRY(gemm512(d, A(2 * i), d->W0(i), d->W0r(i), M, e0, st));
     // net += fc_1(act');  act'' = relu(cbn_next(net))
     Epilogue e1{};
     e1.ld = HID; e1.bias = d->b1(i); e1.R = net; e1.C = net; e1.act = A(2 * i + 2); e1.s2 = d->s(2 * i + 2); e1.t2 = d->t(2 * i + 2);
-    SURFD_TRY(launch_gemm(A(2 * i + 1), HID, d->W1(i), HID, M, HID, HID, e1, st));
+    e1.round_act = (tcm && i < NBLK - 1) ? 1 : 0;   // the last activation feeds the fp32 fc_out reduction only
+    SURFD_TRY(gemm512(d, A(2 * i + 1), d->W1(i), d->W1r(i), M, e1, st));
   }
   out_kernel<<<(unsigned)cdiv((int64_t)M * 32, 256), 256, 0, st>>>(A(10), M, d->wout(), d->bout(), udf_out, dst,
                                                                   keep_acts ? d->dudf.as<float>() : nullptr);
@@ -562,12 +600,12 @@ static int dec_backward(surfd_decoder* d, int M, float* grad_out, const int32_t*
   for (int i = NBLK - 1; i >= 0; --i) {
     // dh = (dnet * W1) (.) relu'(act_{2i+1}) (.) s_{2i+1}
     Epilogue e1{};
-    e1.ld = HID; e1.mask = d->act(2 * i + 1); e1.mscale = d->s(2 * i + 1); e1.C = dh;
-    SURFD_TRY(launch_gemm(dnet, HID, d->W1T(i), HID, M, HID, HID, e1, st));
+    e1.ld = HID; e1.mask = d->act(2 * i + 1); e1.mscale = d->s(2 * i + 1); e1.C = dh; e1.round_c = d->precision == 1 ? 1 : 0;
+    SURFD_TRY(gemm512(d, dnet, d->W1T(i), d->W1Tr(i), M, e1, st));
     // dnet += (dh * W0) (.) relu'(act_{2i}) (.) s_{2i}
     Epilogue e0{};
     e0.ld = HID; e0.mask = d->act(2 * i); e0.mscale = d->s(2 * i); e0.R = dnet; e0.C = dnet;
-    SURFD_TRY(launch_gemm(dh, HID, d->W0T(i), HID, M, HID, HID, e0, st));
+    SURFD_TRY(gemm512(d, dh, d->W0T(i), d->W0Tr(i), M, e0, st));
   }
   Epilogue ee{};
   ee.ld = ENC; ee.C = d->de.as<float>();
@@ -714,9 +752,9 @@ extern "C" int surfd_dec_time_layer(surfd_decoder* d, int M, int iters, float* m
   Epilogue e{};
   e.ld = HID; e.bias = d->b0(0); e.act = d->act(1); e.s2 = d->s(1); e.t2 = d->t(1);
   SURFD_CUDA(cudaMemsetAsync(d->act(0), 0, (size_t)M * HID * sizeof(float), st));
-  for (int i = 0; i < 3; ++i) SURFD_TRY(d->precision == 0 ? launch_gemm(d->act(0), HID, d->W0(0), HID, M, HID, HID, e, st) : 0);
+  for (int i = 0; i < 3; ++i) SURFD_TRY(gemm512(d, d->act(0), d->W0(0), d->W0r(0), M, e, st));
   SURFD_CUDA(cudaEventRecord(e0, st));
-  for (int i = 0; i < iters; ++i) SURFD_TRY(launch_gemm(d->act(0), HID, d->W0(0), HID, M, HID, HID, e, st));
+  for (int i = 0; i < iters; ++i) SURFD_TRY(gemm512(d, d->act(0), d->W0(0), d->W0r(0), M, e, st));
   SURFD_CUDA(cudaEventRecord(e1, st));
   SURFD_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;

@@ -1,0 +1,293 @@
+// decoder_tc.cu -- the decoder's 512x512 layer GEMM on the 5th-generation tensor cores (sm_100a):
+// C[M][512] = A[M][512] * W[512][512]^T with the same fused epilogue as the FFMA kernel (bias, CBN/ReLU mask,
+// residual, next layer's CBN+ReLU activation), operands in TF32 (kind::tf32, fp32 accumulate in TMEM).
+//
+// Structure (one persistent CTA per SM, 6 warps, no cluster):
+//   warp 0  TMA producer : cp.async.bulk.tensor.2d of the A tile (128 x 32 fp32, 128B-swizzled) and the W tile
+//                          (256 x 32) into a 4-stage shared-memory ring, mbarrier complete_tx
+//   warp 1  MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=256, K=8) x4 per
+//                          stage, tcgen05.commit frees the stage; the 128x256 fp32 accumulator lives in TMEM and
+//                          is double-buffered (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2-5 epilogue   : tcgen05.ld 32x32b (one accumulator row per thread), fused epilogue, vectorised row stores
+// Both operands are K-major (activations [points][K], weights [out][K], K contiguous), so A and B tiles use the same
+// canonical SWIZZLE_128B K-major layout that TMA writes and the UMMA shared-memory descriptor reads.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "decoder_common.cuh"
+
+namespace surfd {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;               // 16 KB
+constexpr int B_BYTES = BN * BK * 4;               // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;     // 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int K_TOTAL = 512, KBLOCKS = K_TOTAL / BK;
+constexpr int THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 27;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded spin: a protocol bug traps (error reported by the runtime) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > SPIN_LIMIT) {
+      if (err) *err = code;
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row atoms of 1024 B (SBO), version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+  d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset = 1024 B [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell) [46,48)
+  d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B [61,64)
+  return d;
+}
+
+// kind::tf32 instruction descriptor: D=F32, A=B=TF32, both K-major, N=256, M=128
+__device__ __forceinline__ uint32_t umma_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, Epilogue e, int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = 2 * m_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile >> 1) * BM, n0 = (tile & 1) * BN;
+        for (int kb = 0; kb < KBLOCKS; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, err, 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_2d(&tmA, &full[stage], sa, kb * BK, m0);
+          tma_load_2d(&tmB, &full[stage], sa + A_BYTES, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc();
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1, err, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < KBLOCKS; ++kb) {
+          mbar_wait(&full[stage], phase, err, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = umma_desc(sa), bdesc = umma_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);                      // stage reusable once these MMAs have read it
+          if (kb == KBLOCKS - 1) umma_commit(&tfull[acc]);  // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = (tile >> 1) * BM, n0 = (tile & 1) * BN;
+      mbar_wait(&tfull[acc], acc_phase, err, 4);
+      tc_fence_after();
+      const int m = m0 + row;
+      const bool ok = m < M;
+      const size_t rbase = (size_t)m * e.ld;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        if (ok) {
+          const int nb = n0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = nb + j;
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            if (e.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n)); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+            if (e.mask) {
+              const float4 mk = *reinterpret_cast<const float4*>(e.mask + rbase + n);
+              const float4 ms = __ldg(reinterpret_cast<const float4*>(e.mscale + n));
+              v.x = mk.x > 0.f ? v.x * ms.x : 0.f; v.y = mk.y > 0.f ? v.y * ms.y : 0.f;
+              v.z = mk.z > 0.f ? v.z * ms.z : 0.f; v.w = mk.w > 0.f ? v.w * ms.w : 0.f;
+            }
+            if (e.R) { const float4 rr = *reinterpret_cast<const float4*>(e.R + rbase + n); v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+            if (e.C) {
+              float4 o = v;
+              if (e.round_c) { o.x = round_to_tf32(o.x); o.y = round_to_tf32(o.y); o.z = round_to_tf32(o.z); o.w = round_to_tf32(o.w); }
+              *reinterpret_cast<float4*>(e.C + rbase + n) = o;
+            }
+            if (e.act) {
+              const float4 s2 = __ldg(reinterpret_cast<const float4*>(e.s2 + n));
+              const float4 t2 = __ldg(reinterpret_cast<const float4*>(e.t2 + n));
+              float4 a;
+              a.x = fmaxf(fmaf(s2.x, v.x, t2.x), 0.f); a.y = fmaxf(fmaf(s2.y, v.y, t2.y), 0.f);
+              a.z = fmaxf(fmaf(s2.z, v.z, t2.z), 0.f); a.w = fmaxf(fmaf(s2.w, v.w, t2.w), 0.f);
+              if (e.round_act) { a.x = round_to_tf32(a.x); a.y = round_to_tf32(a.y); a.z = round_to_tf32(a.z); a.w = round_to_tf32(a.w); }
+              *reinterpret_cast<float4*>(e.act + rbase + n) = a;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows][512] row-major, box = [box_rows][32 floats], 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(SURFD_BAD_ARGUMENT, "cuTensorMapEncodeTiled not available from the driver", __FILE__, __LINE__);
+  cuuint64_t dims[2] = {(cuuint64_t)K_TOTAL, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K_TOTAL * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(SURFD_BAD_ARGUMENT, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__);
+  return 0;
+}
+
+}  // namespace tc
+
+int launch_gemm_tc(const float* A, const float* W, int M, const Epilogue& e, int* err_flag, int num_sms, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SURFD_CUDA(cudaFuncSetAttribute(tc::tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap ma, mb;
+  SURFD_TRY(tc::make_map(&ma, A, M, tc::BM));
+  SURFD_TRY(tc::make_map(&mb, W, 512, tc::BN));
+  const int tiles = 2 * (int)cdiv(M, tc::BM);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  tc::tc_gemm_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(ma, mb, M, e, err_flag);
+  SURFD_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace surfd

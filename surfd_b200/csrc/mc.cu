@@ -73,16 +73,23 @@ classify_kernel(const float* __restrict__ im, int N, float avg_t, float max_t, u
   }
 }
 
+// One warp per shape: all 32 lanes run replay_w() on a private copy of the bookkeeping (identical control flow, same-value
+// stores) and split the neighbourhood fetch / edge votes of each visit (mc_core.h, "warp-cooperative variant").
 // n_cand comes from the device-side compaction total, so the host never has to read it before the launch.
-__global__ void replay_kernel(surfd_mccore::Grid* g, const int64_t* __restrict__ n_cand_dev, int64_t cap_cand) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const int64_t n = *n_cand_dev;
-    g->n_cand = n < cap_cand ? n : cap_cand;
-    g->n_cand_total = n;
-    if (n == 0) { g->n_v = 0; g->n_f3 = 0; g->status = surfd_mccore::MC_EMPTY; return; }
-    surfd_mccore::replay(*g);
-    if (n > cap_cand) g->status = surfd_mccore::MC_CAPACITY;   // candidate list truncated: caller retries with more room
+__global__ void __launch_bounds__(32) replay_kernel(surfd_mccore::Grid* gp, const int64_t* __restrict__ n_cand_dev, int64_t cap_cand) {
+  __shared__ surfd_mccore::CubeCache cc;
+  surfd_mccore::Grid g = *gp;
+  const int64_t n = *n_cand_dev;
+  g.n_cand = n < cap_cand ? n : cap_cand;
+  g.n_cand_total = n;
+  if (n == 0) {
+    g.n_v = 0; g.n_f3 = 0; g.status = surfd_mccore::MC_EMPTY;
+  } else {
+    surfd_mccore::replay_w(g, cc);
+    if (n > cap_cand) g.status = surfd_mccore::MC_CAPACITY;   // candidate list truncated: caller retries with more room
   }
+  __syncwarp();
+  if (threadIdx.x == 0) *gp = g;
 }
 
 }  // namespace surfd

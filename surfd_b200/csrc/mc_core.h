@@ -631,4 +631,322 @@ MC_HD_NOINLINE void replay(Grid& g) {
   if (g.status == MC_OK && g.n_v == 0) g.status = MC_EMPTY;
 }
 
+// =====================================================================================================
+// Warp-cooperative variant (what the replay kernel runs).  Same visiting order and arithmetic as
+// visit_cube()/replay() above; the difference is how a visit touches memory.  All 32 lanes execute the
+// scalar control flow redundantly on a per-lane copy of the Grid bookkeeping (identical values, same-value
+// stores), and the lanes split only the memory-heavy, order-independent parts:
+//   phase 1  the 4x4x4 lattice neighbourhood of the cube (udf, sign, flags, gradients) and its 13 vertex
+//            slots are fetched with one load per lane into a shared-memory CubeCache (one L2 latency
+//            instead of ~50 dependent ones);
+//   phase 2  the 8x6 edge votes (pure functions of the gradients) are computed one per lane;
+//   then the order-dependent chain (corner by corner, direction by direction, vote_accumulate) runs
+//   from the cache.  Cubes that need the reference's "look one vertex further past an exact zero" rule
+//   fall back to visit_cube().  On the host (logic tests) the lane loops run sequentially.
+// =====================================================================================================
+#if defined(__CUDA_ARCH__)
+#define MC_LANE_LOOP(l) for (int l = (int)(threadIdx.x & 31), _mc_once = 1; _mc_once; _mc_once = 0)
+#define MC_WARP_SYNC() __syncwarp()
+#else
+#define MC_LANE_LOOP(l) for (int l = 0; l < 32; ++l)
+#define MC_WARP_SYNC()
+#endif
+
+struct CubeCache {
+  float im[64];
+  float gr[64 * 3];
+  float vote[48];
+  int32_t fl[13];
+  int8_t sgn[64];
+  uint8_t flg[64];
+  uint8_t vstat[48];   // 0: skipped by the bounds rule, 1: usable, 2: neighbour udf == 0 (needs the extension rule)
+};
+
+MC_HD int64_t facelayer_index_xyz(int64_t nx, int x, int y, int z, int vi) {
+  int64_t i = nx * nx * z + nx * y + x;
+  int j = 0, k = 0;
+  if (vi < 8) {
+    if (vi >= 4) { vi -= 4; k = 1; }
+    if (vi == 1) { i += 1; j = 1; }
+    else if (vi == 2) { i += nx; }
+    else if (vi == 3) { j = 1; }
+  } else if (vi < 12) {
+    j = 2;
+    if (vi == 9) i += 1;
+    else if (vi == 10) i += nx + 1;
+    else if (vi == 11) i += nx;
+  } else {
+    j = 3;
+  }
+  i += nx * nx * k;
+  return 4 * i + j;
+}
+
+#define MC_BLK(bz, by, bx) (((bz) << 4) | ((by) << 2) | (bx))
+
+MC_HD int check_tiling_c(const CubeCache& cc, const Tiling& t, int config) {
+  int seen[36];
+  int n = 0, result = 0;
+  for (int k = 0; k < t.nt * 3; ++k) {
+    const int fl = cc.fl[tiling_edge(t, config, k)];
+    bool found = false;
+    for (int m = 0; m < n; ++m) found = found || (seen[m] == fl);
+    if (!found && fl >= 0) ++result;
+    seen[n++] = fl;
+  }
+  return result;
+}
+
+MC_HD void add_face_from_edge_c(Grid& g, CubeCache& cc, Cell& c, int vi) {
+  int idx = cc.fl[vi];
+  if (idx < 0) {
+    double px, py, pz;
+    if (vi == 12) {
+      if (!c.v12_done) center_vertex(c);
+      px = c.v12x; py = c.v12y; pz = c.v12z;
+    } else {
+      int dx1 = lut2(LUT_EDGESRELX, vi, 0), dx2 = lut2(LUT_EDGESRELX, vi, 1);
+      int dy1 = lut2(LUT_EDGESRELY, vi, 0), dy2 = lut2(LUT_EDGESRELY, vi, 1);
+      int dz1 = lut2(LUT_EDGESRELZ, vi, 0), dz2 = lut2(LUT_EDGESRELZ, vi, 1);
+      double w1 = 1.0 / (MC_FLT_EPS + dabs(c.vv[dz1 * 4 + dy1 * 2 + dx1]));
+      double w2 = 1.0 / (MC_FLT_EPS + dabs(c.vv[dz2 * 4 + dy2 * 2 + dx2]));
+      double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
+      fx += (double)dx1 * w1; fy += (double)dy1 * w1; fz += (double)dz1 * w1; ff += w1;
+      fx += (double)dx2 * w2; fy += (double)dy2 * w2; fz += (double)dz2 * w2; ff += w2;
+      px = (double)c.x + 1.0 * fx / ff;
+      py = (double)c.y + 1.0 * fy / ff;
+      pz = (double)c.z + 1.0 * fz / ff;
+    }
+    idx = (int)g.n_v;
+    if (g.n_v < g.cap_v) {
+      g.verts[3 * g.n_v + 0] = (float)px;
+      g.verts[3 * g.n_v + 1] = (float)py;
+      g.verts[3 * g.n_v + 2] = (float)pz;
+    } else {
+      g.status = MC_CAPACITY;
+    }
+    ++g.n_v;
+    cc.fl[vi] = idx;
+    g.face_layer[facelayer_index_xyz(g.N, c.x, c.y, c.z, vi)] = idx;
+  } else if (vi == 12 && !c.v12_done) {
+    center_vertex(c);
+  }
+  if (g.n_f3 < g.cap_f3) g.faces[g.n_f3] = idx;
+  else g.status = MC_CAPACITY;
+  ++g.n_f3;
+}
+
+MC_HD_NOINLINE bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, int mode) {
+  const int N = g.N;
+  const int nb = N - 2;
+  // ---- phase 1: cooperative fetch of the 4x4x4 neighbourhood (origin z-1,y-1,x-1) and the 13 vertex slots ----
+  MC_WARP_SYNC();
+  MC_LANE_LOOP(l) {
+    for (int v = l; v < 64; v += 32) {
+      const int cz = z - 1 + (v >> 4), cy = y - 1 + ((v >> 2) & 3), cx = x - 1 + (v & 3);
+      const bool inside = cz >= 0 && cz < N && cy >= 0 && cy < N && cx >= 0 && cx < N;
+      float im = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+      int8_t sg = 0; uint8_t fg = 0;
+      if (inside) {
+        const int64_t i = lin(g, cz, cy, cx);
+        im = g.im[i]; sg = g.sgn[i]; fg = g.flg[i];
+        g0 = g.grads[3 * i]; g1 = g.grads[3 * i + 1]; g2 = g.grads[3 * i + 2];
+      }
+      cc.im[v] = im; cc.sgn[v] = sg; cc.flg[v] = fg;
+      cc.gr[3 * v] = g0; cc.gr[3 * v + 1] = g1; cc.gr[3 * v + 2] = g2;
+    }
+    if (l < 13) cc.fl[l] = g.face_layer[facelayer_index_xyz(N, x, y, z, l)];
+  }
+  MC_WARP_SYNC();
+  // ---- phase 2: one (corner, direction) edge vote per lane ----
+  MC_LANE_LOOP(l) {
+    for (int it = l; it < 48; it += 32) {
+      const int c = it / 6, d = it - 6 * c;
+      const int dz = (d == 0) - (d == 1), dy = (d == 2) - (d == 3), dx = (d == 4) - (d == 5);
+      const int bz = 1 + MC_CZ(c), by = 1 + MC_CY(c), bx = 1 + MC_CX(c);
+      const int cz = z - 1 + bz + dz, cy = y - 1 + by + dy, cx = x - 1 + bx + dx;
+      uint8_t st = 0; float vt = 0.f;
+      if (!(cz > nb || cz < 0 || cy > nb || cy < 0 || cx > nb || cx < 0)) {
+        const int nv = MC_BLK(bz + dz, by + dy, bx + dx);
+        if (cc.im[nv] == 0.0f) st = 2;
+        else { st = 1; vt = edge_vote(cc.gr + 3 * MC_BLK(bz, by, bx), cc.gr + 3 * nv, dz, dy, dx); }
+      }
+      cc.vstat[it] = st; cc.vote[it] = vt;
+    }
+  }
+  MC_WARP_SYNC();
+  // ---- uniform part ----
+  int cb[8];
+  float cim[8];
+  int64_t ci[8];
+  for (int i = 0; i < 8; ++i) {
+    cb[i] = MC_BLK(1 + MC_CZ(i), 1 + MC_CY(i), 1 + MC_CX(i));
+    cim[i] = cc.im[cb[i]];
+    ci[i] = lin(g, z + MC_CZ(i), y + MC_CY(i), x + MC_CX(i));
+  }
+  // the "exact zero neighbour" extension (pyx:1287-1292) reaches outside the cached block: generic path
+  for (int i = 0; i < 8; ++i) {
+    if ((cc.flg[cb[i]] & 1) || cim[i] == 0.0f) continue;
+    for (int d = 0; d < 6; ++d)
+      if (cc.vstat[i * 6 + d] == 2) return visit_cube(g, z, y, x, mode);
+  }
+  int visited_vs[8];
+  float sign_vs[8];
+  for (int vtx = 0; vtx < 8; ++vtx) {
+    visited_vs[vtx] = 0;
+    sign_vs[vtx] = 0.0f;
+    const int b0 = cb[vtx];
+    if (cc.flg[b0] & 1) {
+      visited_vs[vtx] = 1;
+      sign_vs[vtx] = (float)cc.sgn[b0];
+      continue;
+    }
+    if (cim[vtx] == 0.0f) {
+      visited_vs[vtx] = 1;
+      continue;
+    }
+    const int bz = 1 + MC_CZ(vtx), by = 1 + MC_CY(vtx), bx = 1 + MC_CX(vtx);
+    for (int d = 0; d < 6; ++d) {
+      if (cc.vstat[vtx * 6 + d] != 1) continue;
+      const int dz = (d == 0) - (d == 1), dy = (d == 2) - (d == 3), dx = (d == 4) - (d == 5);
+      const int8_t sn = cc.sgn[MC_BLK(bz + dz, by + dy, bx + dx)];
+      if (sn == 0) continue;
+      visited_vs[vtx] += 1;
+      sign_vs[vtx] = vote_accumulate(sign_vs[vtx], (float)sn, cc.vote[vtx * 6 + d]);
+    }
+    if (mode != 0) {
+      if (visited_vs[vtx] >= 1 &&
+          (double)(sign_vs[vtx] < 0 ? -sign_vs[vtx] : sign_vs[vtx]) / (double)visited_vs[vtx] < (double)0.707f &&
+          !g.q.empty()) {
+        if (mode == 1) {
+          if (!g.q_unsure.push((int32_t)lin(g, z, y, x))) g.status = MC_QUEUE_OVERFLOW;
+          ++g.n_unsure_push;
+        }
+        return false;
+      }
+    }
+    const int8_t ns = (int8_t)my_sign(sign_vs[vtx]);
+    cc.sgn[b0] = ns;
+    g.sgn[ci[vtx]] = ns;
+  }
+
+  bool all_voted = true;
+  for (int i = 0; i < 8; ++i) all_voted = all_voted && (visited_vs[i] >= 1);
+  if (!all_voted) {
+    const int order[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+    float base[3] = {0.f, 0.f, 0.f};
+    float anchor_sign = 1.f;
+    bool found = false;
+    for (int k = 0; k < 8 && !found; ++k) {
+      const int b0 = cb[order[k]];
+      if ((cc.flg[b0] & 1) && non_zero_norm(cc.gr + 3 * b0)) {
+        anchor_sign = my_sign((float)cc.sgn[b0]);
+        base[0] = cc.gr[3 * b0]; base[1] = cc.gr[3 * b0 + 1]; base[2] = cc.gr[3 * b0 + 2];
+        found = true;
+      }
+    }
+    for (int k = 0; k < 8 && !found; ++k) {
+      const int b0 = cb[order[k]];
+      if (non_zero_norm(cc.gr + 3 * b0)) {
+        base[0] = cc.gr[3 * b0]; base[1] = cc.gr[3 * b0 + 1]; base[2] = cc.gr[3 * b0 + 2];
+        found = true;
+      }
+    }
+    base[0] = anchor_sign * base[0]; base[1] = anchor_sign * base[1]; base[2] = anchor_sign * base[2];
+    const bool check_unsure = (mode == 1) && !g.q.empty();
+    for (int i = 0; i < 8; ++i) {
+      if (visited_vs[i] != 0) continue;
+      const float s = dot3(base, cc.gr + 3 * cb[i]);
+      if (check_unsure) {
+        sign_vs[i] = s;
+        if ((s < 0 ? -s : s) < 0.707f) {
+          if (!g.q_unsure.push((int32_t)lin(g, z, y, x))) g.status = MC_QUEUE_OVERFLOW;
+          ++g.n_unsure_push;
+          return false;
+        }
+      }
+      const int8_t ns = (int8_t)my_sign(s);
+      cc.sgn[cb[i]] = ns;
+      g.sgn[ci[i]] = ns;
+    }
+  }
+
+  if (mode == 2) return false;
+
+  double v[8];
+  for (int i = 0; i < 8; ++i) {
+    float p = (float)cc.sgn[cb[i]] * cim[i];
+    v[i] = (double)p;
+  }
+  Cell c;
+  cell_set(c, x, y, z, v);
+  for (int i = 0; i < 8; ++i) g.flg[ci[i]] = (uint8_t)(cc.flg[cb[i]] | 1);
+
+  const int kase = lut2(LUT_CASES, c.index, 0);
+  const int64_t me = ci[0];
+  if (kase > 0) {
+    if (mode == 1) {
+      const bool trivial = (kase == 1 || kase == 2 || kase == 5 || kase == 8 || kase == 9);
+      if (!trivial && (!g.q.empty() || !g.q_unsure.empty())) {
+        if (!g.q_nontrivial.push((int32_t)me)) g.status = MC_QUEUE_OVERFLOW;
+        ++g.n_nontrivial_push;
+        return false;
+      }
+    }
+    const int config = lut2(LUT_CASES, c.index, 1);
+    const Tiling t = select_tiling(c, kase, config);
+    if (mode == 1) {
+      if (check_tiling_c(cc, t, config) < 2) return false;
+    }
+    g.flg[me] = (uint8_t)(cc.flg[cb[0]] | 1 | 2);
+    for (int k = 0; k < t.nt * 3; ++k) add_face_from_edge_c(g, cc, c, tiling_edge(t, config, k));
+    push_neighbours(g, z, y, x);
+    ++g.n_accept;
+    return true;
+  }
+  g.flg[me] = (uint8_t)(cc.flg[cb[0]] | 1 | 2);
+  return false;
+}
+
+// replay() with visit_cube_w(); `g` is the caller's private (per-lane) copy of the bookkeeping.
+MC_HD_NOINLINE void replay_w(Grid& g, CubeCache& cc) {
+  const int N = g.N;
+  g.n_v = 0; g.n_f3 = 0; g.status = MC_OK;
+  g.n_seed = g.n_accept = g.n_unsure_push = g.n_nontrivial_push = 0;
+  for (int64_t k = 0; k < g.n_cand; ++k) {
+    const int32_t cidx = g.cand_list[k];
+    if (g.flg[cidx] & 2) continue;
+    int x = cidx % N, y = (cidx / N) % N, z = cidx / (N * N);
+    ++g.n_seed;
+    if (!visit_cube_w(g, cc, z, y, x, 0)) continue;
+    bool visit_neighbours = true;
+    while (!g.q.empty() || !g.q_unsure.empty() || !g.q_nontrivial.empty()) {
+      if (g.status == MC_QUEUE_OVERFLOW) return;
+      int32_t cur;
+      if (g.q.empty()) {
+        if (g.q_unsure.empty()) {
+          cur = g.q_nontrivial.front(); g.q_nontrivial.pop();
+        } else {
+          cur = g.q_unsure.front();
+          if (visit_neighbours) {
+            if (g.flg[cur] & 2) { g.q_unsure.pop(); continue; }
+            push_neighbours(g, cur / (N * N), (cur / N) % N, cur % N);
+            visit_neighbours = false;
+            continue;
+          } else {
+            g.q_unsure.pop();
+            visit_neighbours = true;
+          }
+        }
+      } else {
+        cur = g.q.front(); g.q.pop();
+      }
+      if (g.flg[cur] & 2) continue;
+      if (!is_candidate(g, cur)) continue;
+      visit_cube_w(g, cc, cur / (N * N), (cur / N) % N, cur % N, visit_neighbours ? 1 : 2);
+    }
+  }
+  if (g.status == MC_OK && g.n_v == 0) g.status = MC_EMPTY;
+}
+
 }  // namespace surfd_mccore

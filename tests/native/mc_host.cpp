@@ -7,8 +7,21 @@
 #include "mc_core.h"
 using namespace surfd_mccore;
 
+static int run_impl(const float* im, const float* grads, int N, float* verts, int64_t cap_v, int32_t* faces, int64_t cap_f3,
+                    int64_t* n_v, int64_t* n_f3, int64_t* stats, int warp_variant);
+
 extern "C" int mc_host_run(const float* im, const float* grads, int N, float* verts, int64_t cap_v,
                            int32_t* faces, int64_t cap_f3, int64_t* n_v, int64_t* n_f3, int64_t* stats) {
+  return run_impl(im, grads, N, verts, cap_v, faces, cap_f3, n_v, n_f3, stats, 0);
+}
+// the warp-cooperative variant with its lane loops run sequentially (what the kernel executes, emulated)
+extern "C" int mc_host_run_w(const float* im, const float* grads, int N, float* verts, int64_t cap_v,
+                             int32_t* faces, int64_t cap_f3, int64_t* n_v, int64_t* n_f3, int64_t* stats) {
+  return run_impl(im, grads, N, verts, cap_v, faces, cap_f3, n_v, n_f3, stats, 1);
+}
+
+static int run_impl(const float* im, const float* grads, int N, float* verts, int64_t cap_v, int32_t* faces, int64_t cap_f3,
+                    int64_t* n_v, int64_t* n_f3, int64_t* stats, int warp_variant) {
   const int64_t n3 = (int64_t)N * N * N;
   // candidate classification, same arithmetic as pyx:1157-1158,1215-1218,1825-1841
   const double voxel = 2.0 / (N - 1);
@@ -38,7 +51,7 @@ extern "C" int mc_host_run(const float* im, const float* grads, int N, float* ve
   std::vector<int32_t> b0(cap), b1(cap), b2(cap);
   g.q.buf = b0.data(); g.q_unsure.buf = b1.data(); g.q_nontrivial.buf = b2.data();
   g.q.mask = g.q_unsure.mask = g.q_nontrivial.mask = cap - 1;
-  replay(g);
+  if (warp_variant) { CubeCache cc; replay_w(g, cc); } else replay(g);
   *n_v = g.n_v; *n_f3 = g.n_f3;
   if (stats) { stats[0] = g.n_cand; stats[1] = g.n_seed; stats[2] = g.n_accept; stats[3] = g.n_unsure_push; stats[4] = g.n_nontrivial_push; }
   return g.status;

@@ -21,14 +21,15 @@ def host_mc():
                                src, "-o", so])
     lib = ctypes.CDLL(so)
 
-    def run(udf, g):
+    def run(udf, g, fn="mc_host_run_w"):
+        """fn: mc_host_run = scalar replay; mc_host_run_w = the warp-cooperative variant the kernel runs (lanes emulated)"""
         N = udf.shape[0]
         cap_v, cap_f = 600_000, 3_600_000
         v = np.empty((cap_v, 3), np.float32); f = np.empty(cap_f, np.int32)
         nv, nf = ctypes.c_int64(), ctypes.c_int64()
         st = (ctypes.c_int64 * 5)()
         P = ctypes.c_void_p
-        rc = lib.mc_host_run(P(udf.ctypes.data), P(g.ctypes.data), N, P(v.ctypes.data), ctypes.c_int64(cap_v), P(f.ctypes.data),
+        rc = getattr(lib, fn)(P(udf.ctypes.data), P(g.ctypes.data), N, P(v.ctypes.data), ctypes.c_int64(cap_v), P(f.ctypes.data),
                              ctypes.c_int64(cap_f), ctypes.byref(nv), ctypes.byref(nf), st)
         return rc, v[:nv.value].copy(), f[:nf.value].copy(), list(st)
     return run
@@ -39,11 +40,12 @@ def test_core_matches_reference_golden_bit_exact(host_mc, case):
     kind, N, noise = case
     g = np.load(os.path.join(GOLDEN, "mc_fields.npz"))
     udf, grads = analytic_field(kind, N, noise, seed=N)
-    rc, v, f, st = host_mc(udf, grads)
     key = f"{kind}_{N}_{noise}"
-    assert rc == 0
-    assert np.array_equal(v, g[key + "_v"])      # vertex positions and numbering, bit for bit
-    assert np.array_equal(f, g[key + "_f"])      # face indices and order
+    for fn in ("mc_host_run", "mc_host_run_w"):
+        rc, v, f, st = host_mc(udf, grads, fn)
+        assert rc == 0
+        assert np.array_equal(v, g[key + "_v"])      # vertex positions and numbering, bit for bit
+        assert np.array_equal(f, g[key + "_f"])      # face indices and order
 
 
 def test_core_matches_live_reference_on_fresh_fields(host_mc, ref_mc):
@@ -54,6 +56,18 @@ def test_core_matches_live_reference_on_fresh_fields(host_mc, ref_mc):
         rv, rf = ref_mc(udf, grads)
         rc, v, f, st = host_mc(udf, grads)
         assert rc == 0 and np.array_equal(v, rv) and np.array_equal(f, rf), (kind, N, noise)
+
+
+def test_core_exact_zero_udf_extension_rule(host_mc, ref_mc):
+    if ref_mc is None:
+        pytest.skip("oracle/_ref not built (reference absent)")
+    for kind, N, noise, zf in [("sphere", 48, 0.0, 0.4), ("torus", 64, 0.3, 0.15), ("hemi", 56, 1.0, 0.4)]:
+        udf, grads = analytic_field(kind, N, noise, seed=7)
+        udf = udf.copy(); udf[udf < zf * 2 / (N - 1)] = 0.0
+        rv, rf = ref_mc(udf, grads)
+        for fn in ("mc_host_run", "mc_host_run_w"):
+            rc, v, f, st = host_mc(udf, grads, fn)
+            assert rc == 0 and np.array_equal(v, rv) and np.array_equal(f, rf), (kind, fn)
 
 
 def test_empty_field_reports_empty_surface(host_mc):

@@ -38,6 +38,34 @@ def test_device_mc_matches_live_reference_at_larger_sizes(ref_mc):
         assert np.array_equal(v.cpu().numpy(), rv) and np.array_equal(f.cpu().numpy().reshape(-1), rf), (kind, N)
 
 
+def test_device_mc_exact_zero_udf_uses_the_extension_rule(ref_mc):
+    """udf values that are exactly 0 (saturated sigmoid) trigger the reference's 'look one vertex further' rule"""
+    if ref_mc is None:
+        pytest.skip("oracle/_ref not present on this machine")
+    mc = MarchingCubes()
+    for kind, N, noise, zf in [("sphere", 48, 0.0, 0.4), ("torus", 64, 0.3, 0.15), ("hemi", 56, 1.0, 0.4)]:
+        udf, grads = analytic_field(kind, N, noise, seed=7)
+        udf = udf.copy(); udf[udf < zf * 2 / (N - 1)] = 0.0
+        rv, rf = ref_mc(udf, grads)
+        v, f = mc.run_raw(torch.from_numpy(udf).cuda(), torch.from_numpy(grads).cuda())
+        assert np.array_equal(v.cpu().numpy(), rv) and np.array_equal(f.cpu().numpy().reshape(-1), rf), (kind, N)
+
+
+def test_launch_finish_on_side_streams_matches_blocking_call():
+    udf, grads = analytic_field("torus", 64, 0.3, seed=64)
+    u, g = torch.from_numpy(udf).cuda(), torch.from_numpy(grads).cuda()
+    v0, f0 = MarchingCubes().run_raw(u, g)
+    mcs = [MarchingCubes() for _ in range(3)]
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    torch.cuda.synchronize()
+    for m, s in zip(mcs, streams):
+        m.launch(u, g, s)
+    for m in mcs:
+        res = m.finish()
+        assert res is not None
+        assert torch.equal(res[0], v0) and torch.equal(res[1], f0)
+
+
 def test_classification_matches_numpy_restating_the_thresholds():
     for N in (33, 64):
         udf, _ = analytic_field("torus", N, 0.3, seed=N)
