@@ -131,6 +131,8 @@ def bench_gpu(args):
             dist.broadcast(t, 0)
     pipe = SurfDPipeline(None, None, LAT, "no_cond", device=dev, max_batch=BATCH, mc_parallel=BATCH,
                          packed_unet=(blob_u, prog.cpu()), packed_decoder=blob_d)
+    if args.precision == "tf32":
+        pipe.decoder.set_precision(1)
     noise_host = make_noise(world, rank, BATCH, STEPS_DDPM, LAT).pin_memory()
     noise_dev = noise_host.to(dev)
 
@@ -194,7 +196,8 @@ def bench_gpu(args):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "sgemm_nt_kernel (decoder 512x512 layer, fused bias+CBN+ReLU epilogue)",
+    kname = "tc_gemm_kernel (tcgen05 kind::tf32" if args.precision == "tf32" else "sgemm_nt_kernel (fp32 FFMA"
+    roofline = {"bound": "tensor", "kernel": kname + ", decoder 512x512 layer, fused bias+CBN+ReLU epilogue)",
                 "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": pk["source"] + " bf16 burst / 2 (TF32-class contraction held to the tensor pipe)",
                 "flops_per_launch": flops_layer, "ms_per_launch": round(ms_layer, 4), "points_per_launch": m_layer}
@@ -205,7 +208,7 @@ def bench_gpu(args):
         out = {
             "metric": "shapes/sec end-to-end (1000-step sample + UDF extract)", "value": round(total_shapes / t_res, 4), "unit": "shapes/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_res / args.steps, 2),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": f"uncond, all-parameter-randomised MDM + closed-form 'poly' AE checkpoint, {STEPS_DDPM} DDPM steps, "
                                    f"--resolution {RES}, batch {BATCH}/GPU, GridFiller lattice (the scripts' default)",
                        "resolution": RES, "batch_per_gpu": BATCH, "ddpm_steps": STEPS_DDPM, "latent": LAT, "parallelism": f"dp{world} (independent shapes)",
@@ -308,6 +311,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="surfd_b200", choices=["surfd_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"], help="decoder layer GEMMs: fp32 FFMA or TF32 tcgen05")
     ap.add_argument("--ddpm-steps", type=int, default=STEPS_DDPM, help="profiling runs only (ncu launch lists); the metric is defined at 1000")
     ap.add_argument("--resolution", type=int, default=RES, help="profiling runs only; the N=1 workload is 256")
     args = ap.parse_args()

@@ -1,0 +1,152 @@
+"""Drop-in command line for the generation path: `python -m sample.generate_{uncond,cat,sketch,image,text}` with the
+reference's flags (utils/parser_util.py:40-170: --model_path --output_dir --cond_mode --ae_dir --num_samples --resolution
+--guidance_param --device --batch_size --seed --category --sketch_path --image_path --mask_path --prompt --watertight
+--noise_schedule --sigma_small --cond_mask_prob --dataset ...) and checkpoint layouts.
+
+What runs here is the hot path only: reverse diffusion -> UDF lattice -> MeshUDF marching cubes -> UDF face filter, one
+`.obj` per sample.  The trimesh / pymeshlab clean-up the reference applies afterwards (meshudf.py:379-434,
+generate_uncond.py:113-122) is outside this path; the CLIP encoders are too, so conditional modes take
+pre-computed 512-d embeddings through --context_path (or use an installed `clip` package if there is one).
+Extra flags: --context_path, --dense_grid (use_fast_grid_filler=False), --precision {fp32,tf32}.
+Multi-GPU: launch with torchrun; samples are sharded contiguously over ranks, weights broadcast once over NCCL.
+"""
+import argparse
+import os
+import time
+
+import torch
+
+
+def generate_args(argv=None):
+    p = argparse.ArgumentParser()
+    g = p.add_argument_group("base")
+    g.add_argument("--num_actions", default=9, type=int, help="num_classes.")
+    g.add_argument("--cuda", default=True, type=bool, help="Use cuda device, otherwise use CPU.")
+    g.add_argument("--device", default=0, type=int, help="Device id to use.")
+    g.add_argument("--seed", default=10, type=int, help="For fixing random seed.")
+    g.add_argument("--batch_size", default=64, type=int, help="Batch size during training.")
+    g.add_argument("--distributed", default=False, type=bool, help="Use ddp to train model")
+    g = p.add_argument_group("sampling")
+    g.add_argument("--model_path", required=True, type=str, help="Path to model####.pt file to be sampled.")
+    g.add_argument("--output_dir", default="", type=str, help="Path to results dir (auto created by the script).")
+    g.add_argument("--num_samples", default=1, type=int, help="Maximal number of prompts to sample.")
+    g.add_argument("--guidance_param", default=1.0, type=float, help="For classifier-free sampling - the s parameter.")
+    g.add_argument("--if_clip", action="store_true")
+    g.add_argument("--clip_value", default=0.1, type=float, help="max_clipping value (0-max).")
+    g = p.add_argument_group("generate")
+    g.add_argument("--grid_size", default=128, type=int, help="grid size.")
+    g.add_argument("--category", default=0, type=int, help="Condition category.")
+    g.add_argument("--sketch_path", default=None, type=str, help="Path to the condition sketch image.")
+    g.add_argument("--image_path", default=None, type=str, help="Path to the condition image.")
+    g.add_argument("--mask_path", default=None, type=str, help="Path to the condition mask.")
+    g.add_argument("--prompt", default=None, type=str, help="text prompt for generation.")
+    g.add_argument("--watertight", action="store_true", help="mesh attributes.")
+    g.add_argument("--resolution", default=512, type=int, help="mesh resolution.")
+    g.add_argument("--ae_dir", default=None, type=str, help="Path to ae")
+    g = p.add_argument_group("dataset")
+    g.add_argument("--dataset", default="deepfashion3d", choices=["deepfashion3d", "text2shape", "pix3d", "kcars"], type=str)
+    g.add_argument("--data_dir", default="", type=str)
+    g = p.add_argument_group("model")
+    g.add_argument("--arch", default="OpenUNet", choices=["OpenUNet"], type=str)
+    g.add_argument("--cond_mask_prob", default=0, type=float)
+    g.add_argument("--unconstrained", action="store_true")
+    g.add_argument("--cond_mode", choices=["no_cond", "text", "sketch", "category", "img"], type=str, required=True, help="condition type")
+    g = p.add_argument_group("diffusion")
+    g.add_argument("--noise_schedule", default="cosine", choices=["linear", "cosine"], type=str)
+    g.add_argument("--diffusion_steps", default=1000, type=int, help="parsed and ignored like the reference (steps = 1000, SURVEY F6)")
+    g.add_argument("--sigma_small", default=True, type=bool)
+    g = p.add_argument_group("surfd_b200 extensions")
+    g.add_argument("--context_path", default=None, type=str, help="torch file with pre-computed [B,512] CLIP embeddings")
+    g.add_argument("--dense_grid", action="store_true", help="use_fast_grid_filler=False (dense lattice)")
+    g.add_argument("--precision", default="fp32", choices=["fp32", "tf32"], help="decoder GEMM precision")
+    args = p.parse_args(argv)
+    if args.cond_mask_prob == 0:          # parse_and_load_from_model (utils/parser_util.py:18-19)
+        args.guidance_param = 1
+    return args
+
+
+def write_obj(path, verts, faces):
+    """minimal Wavefront writer (the reference goes through open3d, utils/utils.py:79-121)"""
+    v = verts.detach().cpu().numpy()
+    f = faces.detach().cpu().numpy() + 1
+    with open(path, "w") as fh:
+        fh.write("# surfd_b200\n")
+        for a in v:
+            fh.write("v %.6f %.6f %.6f\n" % (a[0], a[1], a[2]))
+        for a in f:
+            fh.write("f %d %d %d\n" % (a[0], a[1], a[2]))
+
+
+def _context(args, kind, B, device):
+    if args.context_path:
+        ctx = torch.load(args.context_path, map_location="cpu")
+        ctx = torch.as_tensor(ctx, dtype=torch.float32).reshape(-1, 512)
+        if ctx.shape[0] == 1:
+            ctx = ctx.repeat(B, 1)
+        return ctx[:B].contiguous()
+    try:
+        import clip  # noqa: F401  (not shipped here)
+    except Exception:
+        raise SystemExit(f"cond_mode={kind}: the CLIP encoders are outside this path; pass --context_path with [B,512] embeddings")
+    model, preprocess = clip.load("ViT-B/32", device="cpu", jit=False)
+    with torch.no_grad():
+        if kind == "text":
+            return model.encode_text(clip.tokenize([args.prompt] * B, truncate=True)).float()
+        from PIL import Image
+        img = preprocess(Image.open(args.image_path or args.sketch_path)).unsqueeze(0)
+        return model.encode_image(img).float().repeat(B, 1)
+
+
+def main(kind, argv=None):
+    """kind in {'uncond','cat','sketch','image','text'}; mirrors sample/generate_*.py main()."""
+    import torch.distributed as dist
+    from .pipeline import SurfDPipeline
+    args = generate_args(argv)
+    out_path = args.output_dir
+    os.makedirs(out_path, exist_ok=True)
+    assert args.num_samples <= args.batch_size, \
+        f"Please either increase batch_size({args.batch_size}) or reduce num_samples({args.num_samples})"
+    args.batch_size = args.num_samples
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", str(args.device)))
+    if not torch.cuda.is_available():
+        raise SystemExit("surfd_b200 has no CPU path: a CUDA device is required")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    latent = 64 if kind in ("image", "text") else 32      # generate_image.py:76, generate_text.py:80 vs generate_uncond.py:55
+    cond_mode = args.cond_mode
+    print("Creating model and diffusion...")
+    print(f"Loading checkpoints from [{args.model_path}]...")
+    state = torch.load(args.model_path, map_location="cpu")
+    ckpt = torch.load(args.ae_dir, map_location="cpu")
+    print(f"Load AutoEncoder From: {args.ae_dir}")
+    B = args.batch_size
+    per = (B + world - 1) // world
+    lo, hi = min(B, rank * per), min(B, (rank + 1) * per)
+    pipe = SurfDPipeline(state, ckpt["decoder"], latent, cond_mode, device=dev, max_batch=max(1, per), num_actions=args.num_actions,
+                         mc_parallel=min(8, max(1, per)))
+    if args.precision == "tf32":
+        pipe.decoder.set_precision(1)
+    # noise: CPU generator, full-batch order, sliced per rank (identical for any GPU count)
+    gen = torch.Generator().manual_seed(args.seed)
+    noise = torch.randn(1001, B, latent, generator=gen)[:, lo:hi].contiguous()
+    ctx = lab = None
+    if kind in ("sketch", "image", "text"):
+        ctx = _context(args, kind, B, dev)[lo:hi]
+    if kind == "cat":
+        lab = torch.full((B,), args.category, dtype=torch.int64)[lo:hi]
+    t0 = time.time()
+    if hi > lo:
+        lat, meshes, stats = pipe.generate(noise.to(dev), args.resolution, ctx, lab, guidance=float(args.guidance_param),
+                                           n_steps=1000, use_fast_grid_filler=not args.dense_grid, noise_schedule=args.noise_schedule)
+        torch.cuda.synchronize()
+        for k, (v, f) in enumerate(meshes):
+            mesh_path = os.path.join(args.output_dir, f"{lo + k}.obj")
+            write_obj(mesh_path, v, f)
+        print(f"rank {rank}: {hi - lo} shapes in {time.time() - t0:.2f}s; saved results to {mesh_path}")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()

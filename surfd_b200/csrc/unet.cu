@@ -18,7 +18,11 @@
 #include <math.h>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace surfd {
 
@@ -91,10 +95,18 @@ struct ConvArgs {
 
 constexpr int CT = 32;        // tile edge
 constexpr int CTP = CT + 4;   // padded row (floats)
+constexpr int KSPLIT = 8;     // CTAs per cluster: the K reduction is split over a thread-block cluster
 
+// One output tile (32 tokens x 32 channels) is owned by a cluster of KSPLIT CTAs.  K chunks (32 input channels of one
+// tap of one segment) are dealt round-robin to the 8 x 8 = 64 warps of the cluster, so even the deepest layers
+// (M = 32 tokens, K = 5376) put 200+ CTAs on the machine and every weight byte is fetched exactly once.  Partial
+// tiles are reduced first across the warps of a CTA (shared memory) and then across the cluster through distributed
+// shared memory in a fixed order -- deterministic, no atomics, no second kernel.
 __global__ void __launch_bounds__(256)
 conv_gemm_kernel(ConvArgs a) {
   extern __shared__ __align__(16) float smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* As = smem + warp * (2 * CT * CTP);
   float* Ws = As + CT * CTP;
@@ -114,6 +126,7 @@ conv_gemm_kernel(ConvArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+  const int my_slot = warp * KSPLIT + crank;   // chunk c belongs to slot c % 64; consecutive chunks go to different CTAs
   int chunk = 0;
   for (int s = 0; s < a.nseg; ++s) {
     const Seg sg = a.seg[s];
@@ -127,7 +140,7 @@ conv_gemm_kernel(ConvArgs a) {
       const float* arow = sg.A + ((size_t)rb * sg.T_in + (ok ? st : 0)) * sg.Cin;
       const float* wrow = sg.W + ((size_t)tap * a.N + n0 + lane) * sg.Cin;
       for (int c = 0; c < cpt; ++c, ++chunk) {
-        if ((chunk & 7) != warp) continue;
+        if ((chunk & (8 * KSPLIT - 1)) != my_slot) continue;
         const int ci0 = c * CT;
         float4 av[8], wv[8];
 #pragma unroll
@@ -162,41 +175,44 @@ conv_gemm_kernel(ConvArgs a) {
       }
     }
   }
-  // cross-warp reduction through smem: red[warp][row][col], rows padded to 33
+  // (1) cross-warp reduction inside the CTA: red[warp][row][col] (rows padded to 33) -> part[row][col]
   __syncthreads();
   float* red = smem;
+  float* part = smem + 8 * CT * 33;   // [32][32] CTA partial, read by the other CTAs of the cluster
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) red[(warp * CT + (ly + 4 * i)) * 33 + (lx + 8 * j)] = acc[i][j];
   __syncthreads();
-  // 256 threads: thread -> (row = tid/8, 4 columns (tid%8)*4 ..)
-  const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
-  const int m = m0 + r;
-  if (m < M) {
-    float v[4];
+  {
+    const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float sum = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) sum += red[(w * CT + r) * 33 + c0 + j];
-      v[j] = sum;
+      part[r * CT + c0 + j] = sum;
     }
-    const int n = n0 + c0;
-    const int b = m / a.T_out;
-    const float4 bias = *reinterpret_cast<const float4*>(a.bias + n);
-    v[0] += bias.x; v[1] += bias.y; v[2] += bias.z; v[3] += bias.w;
-    if (a.emb) {
-      const float4 e = *reinterpret_cast<const float4*>(a.emb + (size_t)b * a.emb_ld + n);
-      v[0] += e.x; v[1] += e.y; v[2] += e.z; v[3] += e.w;
-    }
-    const size_t o = (size_t)m * a.N + n;
-    if (a.residual) {
-      const float4 rr = *reinterpret_cast<const float4*>(a.residual + o);
-      v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-    }
-    *reinterpret_cast<float4*>(a.out + o) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  // (2) cross-CTA reduction over distributed shared memory: CTA `crank` finishes rows 4*crank .. 4*crank+3
+  cluster.sync();
+  if (threadIdx.x < 128) {
+    const int r = 4 * crank + (threadIdx.x >> 5), col = threadIdx.x & 31;
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < KSPLIT; ++j) v += cluster.map_shared_rank(part, j)[r * CT + col];
+    const int m = m0 + r;
+    if (m < M) {
+      const int n = n0 + col;
+      const int b = m / a.T_out;
+      v += a.bias[n];
+      if (a.emb) v += a.emb[(size_t)b * a.emb_ld + n];
+      const size_t o = (size_t)m * a.N + n;
+      if (a.residual) v += a.residual[o];
+      a.out[o] = v;
+    }
+  }
+  cluster.sync();   // keep this CTA's shared memory alive until every peer has read it
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -378,6 +394,9 @@ __global__ void step_advance_kernel(StepState* st) { st->iter += 1; }
 
 using namespace surfd;
 
+// per-warp A/W staging (8 warps x 2 x 32 x 36 floats) is reused for the 8 x 32 x 33 warp partials; + the 32x32 CTA partial
+static constexpr int CONV_SMEM = (8 * 2 * CT * CTP + CT * CT) * (int)sizeof(float);
+
 struct surfd_unet {
   int L = 0, max_batch = 0;
   DevBuf weights, pool, emb_all, temb, e1, emb, semb_unused, t_cur, x0a, x0b, xcur, state;
@@ -437,7 +456,7 @@ extern "C" int surfd_unet_create(const float* packed, size_t n_floats, const int
   if ((st = u->x0b.reserve(B * L * sizeof(float)))) return fail(st);
   if ((st = u->xcur.reserve(B * L * sizeof(float)))) return fail(st);
   if ((st = u->state.reserve(sizeof(StepState)))) return fail(st);
-  ce = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * CT * CTP * (int)sizeof(float));
+  ce = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM);
   if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
   *out = u;
   return 0;
@@ -503,8 +522,16 @@ static int unet_run(surfd_unet* u, int B, const float* x, const int64_t* t, cons
         a.emb = r[20] >= 0 ? u->emb_all.as<float>() + r[20] : nullptr;
         a.emb_ld = u->emb_cols;
         a.residual = r[21] >= 0 ? u->buf(r[21]) : nullptr;
-        const dim3 grid((unsigned)(a.N / CT), (unsigned)cdiv((int64_t)B * a.T_out, CT));
-        conv_gemm_kernel<<<grid, 256, 8 * 2 * CT * CTP * sizeof(float), st>>>(a);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(a.N / CT), (unsigned)cdiv((int64_t)B * a.T_out, CT), KSPLIT);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = CONV_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = KSPLIT;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        SURFD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel, a));
         SURFD_CHECK_LAUNCH();
         break;
       }

@@ -316,7 +316,16 @@ class SpacedSchedule:
 
     def device_tables(self, device):
         """[3][n] float32: coef1, coef2, exp(0.5*logvar) -- each rounded the way _extract_into_tensor(...).float() and the
-        fp32 `th.exp(0.5 * log_variance)` of p_sample do (gaussian_diffusion.py:1329-1342, :519)."""
+        fp32 `th.exp(0.5 * log_variance)` of p_sample do (gaussian_diffusion.py:1329-1342, :519).  Cached per device so the
+        sampler's captured CUDA graph (keyed on these pointers) is reused across calls."""
+        key = str(device)
+        cache = self.__dict__.setdefault("_dev_tables", {})
+        if key in cache:
+            return cache[key]
+        cache[key] = self._device_tables(device)
+        return cache[key]
+
+    def _device_tables(self, device):
         c1 = torch.from_numpy(self.posterior_mean_coef1).float()
         c2 = torch.from_numpy(self.posterior_mean_coef2).float()
         lv = torch.from_numpy(self.posterior_log_variance_clipped).float()

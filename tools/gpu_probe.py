@@ -34,6 +34,19 @@ def main():
     res["fwdbwd_pts_per_s"] = M / t; res["fwdbwd_tflops"] = M * (5.308e6 + 10.617e6) / t / 1e12
     ms, m = dec.time_layer(20)
     res["layer_gemm_ms"] = ms; res["layer_gemm_tflops"] = 2 * m * 512 * 512 / ms / 1e9
+    # tensor-core (TF32 tcgen05) path
+    if os.environ.get("PROBE_TC", "1") == "1":
+        dtc = UdfDecoder(synth.synth_ae_poly(L)["decoder"], L)
+        dtc.set_precision(1); dtc.set_latent(lat)
+        t, u_tc = timed(lambda: dtc.query(pts))
+        res["tc_fwd_pts_per_s"] = M / t; res["tc_fwd_tflops"] = M * 5.308e6 / t / 1e12
+        res["tc_vs_fp32_maxabs"] = float((u_tc - dec.query(pts)).abs().max())
+        t, _ = timed(lambda: dtc.query(pts, want_grad=True))
+        res["tc_fwdbwd_tflops"] = M * (5.308e6 + 10.617e6) / t / 1e12
+        ms, m = dtc.time_layer(20)
+        res["tc_layer_gemm_ms"] = ms; res["tc_layer_gemm_tflops"] = 2 * m * 512 * 512 / ms / 1e9
+        t, (u, g, c) = timed(lambda: dtc.lattice(256, True), n=2)
+        res["tc_lattice_N256_gf_s"] = t
     mc = MarchingCubes()
     sizes = [int(a) for a in sys.argv[1:]] or [128, 256]
     for N in sizes:
