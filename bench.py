@@ -239,13 +239,23 @@ def cpu_reference(shape_stats=None, quick=True):
     from oracle import decoder_oracle as DO, unet_oracle as UO
     from surfd_b200 import synth, unet as U
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    # (1) sampler: a few DDPM steps at the workload's batch, scaled to 1000
+    # (1) sampler: a few DDPM steps at the workload's batch, scaled to 1000.  The UNet's tensors are tiny (<= 256 tokens), so
+    # torch's intra-op pool is slower with every core than with a few: pick the fastest thread count on one step first.
     sd = synth.synth_mdm(LAT, "no_cond")
     n_s = 3 if quick else 10
-    sched = U.SpacedSchedule(U.cosine_betas(), U.space_timesteps(1000, [n_s]))
     g = torch.Generator().manual_seed(SEED)
     noise = torch.randn(n_s + 1, BATCH, LAT, generator=g)
+    one = U.SpacedSchedule(U.cosine_betas(), U.space_timesteps(1000, [1]))
+    best_thr, best_t = cores, None
+    for thr in sorted({cores, min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+        torch.set_num_threads(thr)
+        with torch.no_grad():
+            UO.p_sample_loop(sd, one, noise[:2])
+            t0 = time.time(); UO.p_sample_loop(sd, one, noise[:2]); dt = time.time() - t0
+        if best_t is None or dt < best_t:
+            best_thr, best_t = thr, dt
+    torch.set_num_threads(best_thr)
+    sched = U.SpacedSchedule(U.cosine_betas(), U.space_timesteps(1000, [n_s]))
     with torch.no_grad():
         t0 = time.time(); UO.p_sample_loop(sd, sched, noise); t_steps = time.time() - t0
     t_sample_batch = t_steps / n_s * STEPS_DDPM
@@ -276,7 +286,7 @@ def cpu_reference(shape_stats=None, quick=True):
     except Exception:
         t_mc = 0.757  # SURVEY section 6 [probe] figure for N=256 when oracle/_ref is unavailable
     per_shape = t_sample_batch / BATCH + t_lattice + t_mc + t_filter
-    return {"value": round(1.0 / per_shape, 6), "unit": "shapes/s", "cores": cores, "kind": "port" if mc_kind == "port" else "port+reference-mc",
+    return {"value": round(1.0 / per_shape, 6), "unit": "shapes/s", "cores": cores, "torch_threads_sampler": best_thr, "kind": "port" if mc_kind == "port" else "port+reference-mc",
             "sample": f"{n_s} DDPM steps at batch {BATCH} (x{STEPS_DDPM // n_s}), {n_pts} decoder points fwd / {n_pts // 4} fwd+grad scaled to the "
                       f"shape's {st['n_udf']} udf + {st['n_grad']} grad + {9 * n_faces} filter queries, reference Cython MC on a sphere "
                       f"({'N=128 scaled x8' if quick else 'N=' + str(RES)})",

@@ -51,13 +51,23 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  // Grow-only, with 25% head-room rounded to 2 MiB: sizes that creep up from shape to shape (query lists) must not
+  // re-allocate every time -- cudaFree() is device-synchronising and would wait for the marching-cubes replays that
+  // run on other streams.
   int reserve(size_t need) {
     if (need <= bytes) return 0;
+    size_t want = need + need / 4;
+    const size_t gran = (size_t)2 << 20;
+    want = (want + gran - 1) / gran * gran;
     if (p) cudaFree(p);
     p = nullptr; bytes = 0;
-    cudaError_t e = cudaMalloc(&p, need);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, need);   // fall back to the exact size when memory is tight
+      want = need;
+    }
     if (e != cudaSuccess) return set_error(-(int)e, cudaGetErrorString(e), __FILE__, __LINE__);
-    bytes = need;
+    bytes = want;
     return 0;
   }
   void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }

@@ -52,6 +52,11 @@ namespace surfd_mccore {
 #define MC_LUTL2(id) MC_LUT_L2[id]
 #endif
 
+// named-table accessors: the directory entries are compile-time constants (no dependent loads)
+#define LUT1(name, i0) ((int)MC_LUTV(LUTOFF_##name + (i0)))
+#define LUT2(name, i0, i1) ((int)MC_LUTV(LUTOFF_##name + (i0) * LUTL1_##name + (i1)))
+#define LUT3(name, i0, i1, i2) ((int)MC_LUTV(LUTOFF_##name + ((i0) * LUTL1_##name + (i1)) * LUTL2_##name + (i2)))
+
 MC_HD int lut1(int id, int i0) { return MC_LUTV(MC_LUTOFF(id) + i0); }
 MC_HD int lut2(int id, int i0, int i1) { return MC_LUTV(MC_LUTOFF(id) + i0 * MC_LUTL1(id) + i1); }
 MC_HD int lut3(int id, int i0, int i1, int i2) {
@@ -205,7 +210,7 @@ MC_HD void center_vertex(Cell& c) {  // pyx:806-835 (gradient part dropped: norm
 }
 
 // Which tiling row the Lewiner switch selects (shared by the "check" and the "add" pass).
-struct Tiling { int lut; int i1; int nt; };  // i1 < 0: 2-D table
+struct Tiling { int lut; int i1; int nt; int off, l1, l2; };  // i1 < 0: 2-D table; off/l1/l2: resolved directory entry
 
 MC_HD bool test_face(const Cell& c, int face) {  // pyx:2403-2432
   int af = face < 0 ? -face : face;
@@ -243,10 +248,10 @@ MC_HD_NOINLINE bool test_internal(const Cell& c, int kase, int config, int subco
     Ct = v[2] + (v[6] - v[2]) * t;
     Dt = v[1] + (v[5] - v[1]) * t;
   } else {
-    if (kase == 6) edge = lut2(LUT_TEST6, config, 2);
-    else if (kase == 7) edge = lut2(LUT_TEST7, config, 4);
-    else if (kase == 12) edge = lut2(LUT_TEST12, config, 3);
-    else if (kase == 13) edge = lut3(LUT_TILING13_5_1, config, subconfig, 0);
+    if (kase == 6) edge = LUT2(TEST6, config, 2);
+    else if (kase == 7) edge = LUT2(TEST7, config, 4);
+    else if (kase == 12) edge = LUT2(TEST12, config, 3);
+    else if (kase == 13) edge = LUT3(TILING13_5_1, config, subconfig, 0);
     // per edge: t = va/(va - vb + eps); Bt,Ct,Dt interpolate three parallel edges
     // rows: {a, b, B0,B1, C0,C1, D0,D1}
     const signed char T[12][8] = {
@@ -277,29 +282,29 @@ MC_HD_NOINLINE bool test_internal(const Cell& c, int kase, int config, int subco
 
 // pyx:1847-2121 (and its twin :2124-2400): pick the tiling for (case, config) with the ambiguity tests.
 MC_HD_NOINLINE Tiling select_tiling(const Cell& c, int kase, int config) {
-  Tiling r; r.lut = -1; r.i1 = -1; r.nt = 0;
+  Tiling r; r.lut = -1; r.i1 = -1; r.nt = 0; r.off = 0; r.l1 = 1; r.l2 = 1;
   int sub = 0;
   switch (kase) {
     case 1: r.lut = LUT_TILING1; r.nt = 1; break;
     case 2: r.lut = LUT_TILING2; r.nt = 2; break;
     case 3:
-      if (test_face(c, lut1(LUT_TEST3, config))) { r.lut = LUT_TILING3_2; r.nt = 4; }
+      if (test_face(c, LUT1(TEST3, config))) { r.lut = LUT_TILING3_2; r.nt = 4; }
       else { r.lut = LUT_TILING3_1; r.nt = 2; }
       break;
     case 4:
-      if (test_internal(c, kase, config, sub, lut1(LUT_TEST4, config))) { r.lut = LUT_TILING4_1; r.nt = 2; }
+      if (test_internal(c, kase, config, sub, LUT1(TEST4, config))) { r.lut = LUT_TILING4_1; r.nt = 2; }
       else { r.lut = LUT_TILING4_2; r.nt = 6; }
       break;
     case 5: r.lut = LUT_TILING5; r.nt = 3; break;
     case 6:
-      if (test_face(c, lut2(LUT_TEST6, config, 0))) { r.lut = LUT_TILING6_2; r.nt = 5; }
-      else if (test_internal(c, kase, config, sub, lut2(LUT_TEST6, config, 1))) { r.lut = LUT_TILING6_1_1; r.nt = 3; }
+      if (test_face(c, LUT2(TEST6, config, 0))) { r.lut = LUT_TILING6_2; r.nt = 5; }
+      else if (test_internal(c, kase, config, sub, LUT2(TEST6, config, 1))) { r.lut = LUT_TILING6_1_1; r.nt = 3; }
       else { r.lut = LUT_TILING6_1_2; r.nt = 9; }
       break;
     case 7:
-      if (test_face(c, lut2(LUT_TEST7, config, 0))) sub += 1;
-      if (test_face(c, lut2(LUT_TEST7, config, 1))) sub += 2;
-      if (test_face(c, lut2(LUT_TEST7, config, 2))) sub += 4;
+      if (test_face(c, LUT2(TEST7, config, 0))) sub += 1;
+      if (test_face(c, LUT2(TEST7, config, 1))) sub += 2;
+      if (test_face(c, LUT2(TEST7, config, 2))) sub += 4;
       switch (sub) {
         case 0: r.lut = LUT_TILING7_1; r.nt = 3; break;
         case 1: r.lut = LUT_TILING7_2; r.i1 = 0; r.nt = 5; break;
@@ -309,44 +314,44 @@ MC_HD_NOINLINE Tiling select_tiling(const Cell& c, int kase, int config) {
         case 5: r.lut = LUT_TILING7_3; r.i1 = 1; r.nt = 9; break;
         case 6: r.lut = LUT_TILING7_3; r.i1 = 2; r.nt = 9; break;
         default:
-          if (test_internal(c, kase, config, sub, lut2(LUT_TEST7, config, 3))) { r.lut = LUT_TILING7_4_2; r.nt = 9; }
+          if (test_internal(c, kase, config, sub, LUT2(TEST7, config, 3))) { r.lut = LUT_TILING7_4_2; r.nt = 9; }
           else { r.lut = LUT_TILING7_4_1; r.nt = 5; }
       }
       break;
     case 8: r.lut = LUT_TILING8; r.nt = 2; break;
     case 9: r.lut = LUT_TILING9; r.nt = 4; break;
     case 10:
-      if (test_face(c, lut2(LUT_TEST10, config, 0))) {
-        if (test_face(c, lut2(LUT_TEST10, config, 1))) { r.lut = LUT_TILING10_1_1_; r.nt = 4; }
+      if (test_face(c, LUT2(TEST10, config, 0))) {
+        if (test_face(c, LUT2(TEST10, config, 1))) { r.lut = LUT_TILING10_1_1_; r.nt = 4; }
         else { r.lut = LUT_TILING10_2; r.nt = 8; }
       } else {
-        if (test_face(c, lut2(LUT_TEST10, config, 1))) { r.lut = LUT_TILING10_2_; r.nt = 8; }
-        else if (test_internal(c, kase, config, sub, lut2(LUT_TEST10, config, 2))) { r.lut = LUT_TILING10_1_1; r.nt = 4; }
+        if (test_face(c, LUT2(TEST10, config, 1))) { r.lut = LUT_TILING10_2_; r.nt = 8; }
+        else if (test_internal(c, kase, config, sub, LUT2(TEST10, config, 2))) { r.lut = LUT_TILING10_1_1; r.nt = 4; }
         else { r.lut = LUT_TILING10_1_2; r.nt = 8; }
       }
       break;
     case 11: r.lut = LUT_TILING11; r.nt = 4; break;
     case 12:
-      if (test_face(c, lut2(LUT_TEST12, config, 0))) {
-        if (test_face(c, lut2(LUT_TEST12, config, 1))) { r.lut = LUT_TILING12_1_1_; r.nt = 4; }
+      if (test_face(c, LUT2(TEST12, config, 0))) {
+        if (test_face(c, LUT2(TEST12, config, 1))) { r.lut = LUT_TILING12_1_1_; r.nt = 4; }
         else { r.lut = LUT_TILING12_2; r.nt = 8; }
       } else {
-        if (test_face(c, lut2(LUT_TEST12, config, 1))) { r.lut = LUT_TILING12_2_; r.nt = 8; }
-        else if (test_internal(c, kase, config, sub, lut2(LUT_TEST12, config, 2))) { r.lut = LUT_TILING12_1_1; r.nt = 4; }
+        if (test_face(c, LUT2(TEST12, config, 1))) { r.lut = LUT_TILING12_2_; r.nt = 8; }
+        else if (test_internal(c, kase, config, sub, LUT2(TEST12, config, 2))) { r.lut = LUT_TILING12_1_1; r.nt = 4; }
         else { r.lut = LUT_TILING12_1_2; r.nt = 8; }
       }
       break;
     case 13: {
       for (int b = 0; b < 6; ++b)
-        if (test_face(c, lut2(LUT_TEST13, config, b))) sub += (1 << b);
-      sub = lut1(LUT_SUBCONFIG13, sub);
+        if (test_face(c, LUT2(TEST13, config, b))) sub += (1 << b);
+      sub = LUT1(SUBCONFIG13, sub);
       if (sub == 0) { r.lut = LUT_TILING13_1; r.nt = 4; }
       else if (sub <= 6) { r.lut = LUT_TILING13_2; r.i1 = sub - 1; r.nt = 6; }
       else if (sub <= 18) { r.lut = LUT_TILING13_3; r.i1 = sub - 7; r.nt = 10; }
       else if (sub <= 22) { r.lut = LUT_TILING13_4; r.i1 = sub - 19; r.nt = 12; }
       else if (sub <= 26) {
         int s2 = sub - 23;
-        if (test_internal(c, kase, config, s2, lut2(LUT_TEST13, config, 6))) { r.lut = LUT_TILING13_5_1; r.i1 = s2; r.nt = 6; }
+        if (test_internal(c, kase, config, s2, LUT2(TEST13, config, 6))) { r.lut = LUT_TILING13_5_1; r.i1 = s2; r.nt = 6; }
         else { r.lut = LUT_TILING13_5_2; r.i1 = s2; r.nt = 10; }
       }
       else if (sub <= 38) { r.lut = LUT_TILING13_3_; r.i1 = sub - 27; r.nt = 10; }
@@ -358,11 +363,12 @@ MC_HD_NOINLINE Tiling select_tiling(const Cell& c, int kase, int config) {
     case 14: r.lut = LUT_TILING14; r.nt = 4; break;
     default: break;
   }
+  if (r.lut >= 0) { r.off = MC_LUTOFF(r.lut); r.l1 = MC_LUTL1(r.lut); r.l2 = MC_LUTL2(r.lut); }
   return r;
 }
 
 MC_HD int tiling_edge(const Tiling& t, int config, int k) {
-  return t.i1 < 0 ? lut2(t.lut, config, k) : lut3(t.lut, config, t.i1, k);
+  return t.i1 < 0 ? (int)MC_LUTV(t.off + config * t.l1 + k) : (int)MC_LUTV(t.off + (config * t.l1 + t.i1) * t.l2 + k);
 }
 
 // pyx:467-526 check_triangles(2): number of distinct already-existing vertices among the tiling's
@@ -391,9 +397,9 @@ MC_HD void add_face_from_edge(Grid& g, Cell& c, int vi) {
       if (!c.v12_done) center_vertex(c);
       px = c.v12x; py = c.v12y; pz = c.v12z;
     } else {
-      int dx1 = lut2(LUT_EDGESRELX, vi, 0), dx2 = lut2(LUT_EDGESRELX, vi, 1);
-      int dy1 = lut2(LUT_EDGESRELY, vi, 0), dy2 = lut2(LUT_EDGESRELY, vi, 1);
-      int dz1 = lut2(LUT_EDGESRELZ, vi, 0), dz2 = lut2(LUT_EDGESRELZ, vi, 1);
+      int dx1 = LUT2(EDGESRELX, vi, 0), dx2 = LUT2(EDGESRELX, vi, 1);
+      int dy1 = LUT2(EDGESRELY, vi, 0), dy2 = LUT2(EDGESRELY, vi, 1);
+      int dz1 = LUT2(EDGESRELZ, vi, 0), dz2 = LUT2(EDGESRELZ, vi, 1);
       double w1 = 1.0 / (MC_FLT_EPS + dabs(c.vv[dz1 * 4 + dy1 * 2 + dx1]));
       double w2 = 1.0 / (MC_FLT_EPS + dabs(c.vv[dz2 * 4 + dy2 * 2 + dx2]));
       double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
@@ -563,7 +569,7 @@ MC_HD_NOINLINE bool visit_cube(Grid& g, int z, int y, int x, int mode) {
   cell_set(c, x, y, z, v);
   for (int i = 0; i < 8; ++i) g.flg[ci[i]] |= 1;
 
-  const int kase = lut2(LUT_CASES, c.index, 0);
+  const int kase = LUT2(CASES, c.index, 0);
   const int64_t me = lin(g, z, y, x);
   if (kase > 0) {
     if (mode == 1) {
@@ -574,7 +580,7 @@ MC_HD_NOINLINE bool visit_cube(Grid& g, int z, int y, int x, int mode) {
         return false;
       }
     }
-    const int config = lut2(LUT_CASES, c.index, 1);
+    const int config = LUT2(CASES, c.index, 1);
     const Tiling t = select_tiling(c, kase, config);
     if (mode == 1) {
       if (check_tiling(g, c, t, config) < 2) return false;
@@ -705,9 +711,9 @@ MC_HD void add_face_from_edge_c(Grid& g, CubeCache& cc, Cell& c, int vi) {
       if (!c.v12_done) center_vertex(c);
       px = c.v12x; py = c.v12y; pz = c.v12z;
     } else {
-      int dx1 = lut2(LUT_EDGESRELX, vi, 0), dx2 = lut2(LUT_EDGESRELX, vi, 1);
-      int dy1 = lut2(LUT_EDGESRELY, vi, 0), dy2 = lut2(LUT_EDGESRELY, vi, 1);
-      int dz1 = lut2(LUT_EDGESRELZ, vi, 0), dz2 = lut2(LUT_EDGESRELZ, vi, 1);
+      int dx1 = LUT2(EDGESRELX, vi, 0), dx2 = LUT2(EDGESRELX, vi, 1);
+      int dy1 = LUT2(EDGESRELY, vi, 0), dy2 = LUT2(EDGESRELY, vi, 1);
+      int dz1 = LUT2(EDGESRELZ, vi, 0), dz2 = LUT2(EDGESRELZ, vi, 1);
       double w1 = 1.0 / (MC_FLT_EPS + dabs(c.vv[dz1 * 4 + dy1 * 2 + dx1]));
       double w2 = 1.0 / (MC_FLT_EPS + dabs(c.vv[dz2 * 4 + dy2 * 2 + dx2]));
       double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
@@ -736,7 +742,7 @@ MC_HD void add_face_from_edge_c(Grid& g, CubeCache& cc, Cell& c, int vi) {
   ++g.n_f3;
 }
 
-MC_HD_NOINLINE bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, int mode) {
+MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, int mode) {
   const int N = g.N;
   const int nb = N - 2;
   // ---- phase 1: cooperative fetch of the 4x4x4 neighbourhood (origin z-1,y-1,x-1) and the 13 vertex slots ----
@@ -788,7 +794,12 @@ MC_HD_NOINLINE bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, in
   for (int i = 0; i < 8; ++i) {
     if ((cc.flg[cb[i]] & 1) || cim[i] == 0.0f) continue;
     for (int d = 0; d < 6; ++d)
-      if (cc.vstat[i * 6 + d] == 2) return visit_cube(g, z, y, x, mode);
+      if (cc.vstat[i * 6 + d] == 2) {
+        Grid tmp = g;            // the generic path takes the struct by address; keep `g` itself register-promotable
+        const bool r = visit_cube(tmp, z, y, x, mode);
+        g = tmp;
+        return r;
+      }
   }
   int visited_vs[8];
   float sign_vs[8];
@@ -882,7 +893,7 @@ MC_HD_NOINLINE bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, in
   cell_set(c, x, y, z, v);
   for (int i = 0; i < 8; ++i) g.flg[ci[i]] = (uint8_t)(cc.flg[cb[i]] | 1);
 
-  const int kase = lut2(LUT_CASES, c.index, 0);
+  const int kase = LUT2(CASES, c.index, 0);
   const int64_t me = ci[0];
   if (kase > 0) {
     if (mode == 1) {
@@ -893,7 +904,7 @@ MC_HD_NOINLINE bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, in
         return false;
       }
     }
-    const int config = lut2(LUT_CASES, c.index, 1);
+    const int config = LUT2(CASES, c.index, 1);
     const Tiling t = select_tiling(c, kase, config);
     if (mode == 1) {
       if (check_tiling_c(cc, t, config) < 2) return false;
@@ -909,7 +920,7 @@ MC_HD_NOINLINE bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, in
 }
 
 // replay() with visit_cube_w(); `g` is the caller's private (per-lane) copy of the bookkeeping.
-MC_HD_NOINLINE void replay_w(Grid& g, CubeCache& cc) {
+MC_HD void replay_w(Grid& g, CubeCache& cc) {
   const int N = g.N;
   g.n_v = 0; g.n_f3 = 0; g.status = MC_OK;
   g.n_seed = g.n_accept = g.n_unsure_push = g.n_nontrivial_push = 0;

@@ -373,7 +373,8 @@ __global__ void step_begin_kernel(const StepState* __restrict__ st, const int64_
 // sample = (c1*x0 + c2*x_t) + ((t != 0) * std) * noise   -- unfused multiplies/adds like the reference's torch ops.
 // x0b != null: classifier-free guidance replay  x0 = x0b + scale * (x0a - x0b)   (models/cfg_sampler.py:19-26)
 __global__ void ddpm_update_kernel(StepState* __restrict__ st, const float* __restrict__ coef, const float* __restrict__ x0a,
-                                   const float* __restrict__ x0b, float scale, const float* __restrict__ noise, int n, float* __restrict__ x) {
+                                   const float* __restrict__ x0b, float scale, const float* __restrict__ noise, int64_t noise_row_stride, int n,
+                                   float* __restrict__ x) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int iter = st->iter, ns = st->n_steps;
   const int idx = ns - 1 - iter;
@@ -383,7 +384,7 @@ __global__ void ddpm_update_kernel(StepState* __restrict__ st, const float* __re
     const float c1 = coef[idx], c2 = coef[ns + idx], sd = coef[2 * ns + idx];
     const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x[i]));
     const float mask = idx != 0 ? 1.0f : 0.0f;
-    const float nz = noise[(size_t)(1 + iter) * n + i];
+    const float nz = noise[(size_t)(1 + iter) * noise_row_stride + i];   // noise is [n_steps+1][B_total][L]; this lane owns a column block
     x[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(mask, sd), nz));
   }
 }
@@ -397,15 +398,14 @@ using namespace surfd;
 // per-warp A/W staging (8 warps x 2 x 32 x 36 floats) is reused for the 8 x 32 x 33 warp partials; + the 32x32 CTA partial
 static constexpr int CONV_SMEM = (8 * 2 * CT * CTP + CT * CT) * (int)sizeof(float);
 
-struct surfd_unet {
-  int L = 0, max_batch = 0;
-  DevBuf weights, pool, emb_all, temb, e1, emb, semb_unused, t_cur, x0a, x0b, xcur, state;
-  std::vector<int64_t> hdr, buf_sizes;
-  std::vector<std::vector<int64_t>> prog;
-  std::vector<size_t> buf_off;   // float offset per buffer for max_batch
-  int emb_cols = 0;
-  size_t n_floats = 0;
-  // cached step graph
+// One lane = private activation pool + step state + captured step graph + stream.  The denoiser is latency-bound (about 170
+// dependent small kernels per step on <= 256 tokens), so a batch is split over lanes that run concurrently on their own
+// streams; the weights are shared.
+struct Lane {
+  DevBuf pool, emb_all, temb, e1, emb, t_cur, x0a, x0b, xcur, state;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  int cap = 0;   // batch capacity of the buffers
   cudaGraphExec_t graph_exec = nullptr;
   int graph_B = -1;
   const float* graph_ctx = nullptr;
@@ -413,14 +413,68 @@ struct surfd_unet {
   const int64_t* graph_tmap = nullptr;
   const float* graph_coef = nullptr;
   const float* graph_noise = nullptr;
+  int64_t graph_stride = 0;
   float graph_guidance = 1.f;
   int64_t graph_launches = 0;
-
-  const float* w(int64_t off) const { return weights.as<float>() + off; }
+  std::vector<size_t> buf_off;
   float* buf(int64_t id) const { return pool.as<float>() + buf_off[(size_t)id]; }
+  void release() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    graph_exec = nullptr;
+    pool.release(); emb_all.release(); temb.release(); e1.release(); emb.release(); t_cur.release(); x0a.release(); x0b.release();
+    xcur.release(); state.release();
+    if (stream) cudaStreamDestroy(stream);
+    if (done) cudaEventDestroy(done);
+    stream = nullptr; done = nullptr;
+  }
+};
+
+struct surfd_unet {
+  int L = 0, max_batch = 0;
+  DevBuf weights;
+  std::vector<int64_t> hdr, buf_sizes;
+  std::vector<std::vector<int64_t>> prog;
+  int emb_cols = 0;
+  size_t n_floats = 0;
+  std::vector<Lane> lanes;
+  cudaEvent_t fork = nullptr;
+  const float* w(int64_t off) const { return weights.as<float>() + off; }
 };
 
 extern "C" size_t surfd_unet_packed_floats(void) { return 0; }  // size depends on cond_mode; python validates via the arch walk
+
+static int lane_init(surfd_unet* u, Lane& ln, int cap) {
+  ln.cap = cap;
+  size_t tot = 0;
+  ln.buf_off.clear();
+  for (size_t i = 0; i < u->buf_sizes.size(); ++i) { ln.buf_off.push_back(tot); tot += (size_t)u->buf_sizes[i] * cap; }
+  const size_t B = (size_t)cap;
+  SURFD_TRY(ln.pool.reserve(tot * sizeof(float)));
+  SURFD_TRY(ln.emb_all.reserve(B * u->emb_cols * sizeof(float)));
+  SURFD_TRY(ln.temb.reserve(B * TCH * sizeof(float)));
+  SURFD_TRY(ln.e1.reserve(B * EMB * sizeof(float)));
+  SURFD_TRY(ln.emb.reserve(B * EMB * sizeof(float)));
+  SURFD_TRY(ln.t_cur.reserve(B * sizeof(int64_t)));
+  SURFD_TRY(ln.x0a.reserve(B * u->L * sizeof(float)));
+  SURFD_TRY(ln.x0b.reserve(B * u->L * sizeof(float)));
+  SURFD_TRY(ln.xcur.reserve(B * u->L * sizeof(float)));
+  SURFD_TRY(ln.state.reserve(sizeof(StepState)));
+  if (!ln.stream) SURFD_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+  if (!ln.done) SURFD_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+  return 0;
+}
+
+extern "C" int surfd_unet_set_lanes(surfd_unet* u, int n_lanes) {
+  SURFD_REQUIRE(u != nullptr, "null argument");
+  SURFD_REQUIRE(n_lanes >= 1 && n_lanes <= 64, "n_lanes out of range");
+  SURFD_CUDA(cudaDeviceSynchronize());
+  for (auto& ln : u->lanes) ln.release();
+  u->lanes.assign((size_t)n_lanes, Lane());
+  const int cap0 = u->max_batch;                                   // lane 0 also serves surfd_unet_forward at full batch
+  const int cap = (u->max_batch + n_lanes - 1) / n_lanes;
+  for (int i = 0; i < n_lanes; ++i) SURFD_TRY(lane_init(u, u->lanes[(size_t)i], i == 0 ? cap0 : cap));
+  return 0;
+}
 
 extern "C" int surfd_unet_create(const float* packed, size_t n_floats, const int64_t* program, size_t n_prog, int L, int max_batch,
                                  surfd_unet** out) {
@@ -438,90 +492,82 @@ extern "C" int surfd_unet_create(const float* packed, size_t n_floats, const int
   u->emb_cols = (int)u->hdr[2];
   u->buf_sizes.assign(program + 16, program + 16 + nb);
   for (int64_t i = 0; i < np; ++i) u->prog.emplace_back(program + 16 + nb + i * REC, program + 16 + nb + (i + 1) * REC);
-  size_t tot = 0;
-  for (int64_t i = 0; i < nb; ++i) { u->buf_off.push_back(tot); tot += (size_t)u->buf_sizes[i] * max_batch; }
   auto fail = [&](int code) { surfd_unet_destroy(u); return code; };
   int st;
   if ((st = u->weights.reserve(n_floats * sizeof(float)))) return fail(st);
   cudaError_t ce = cudaMemcpy(u->weights.p, packed, n_floats * sizeof(float), cudaMemcpyDefault);
   if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
-  const size_t B = (size_t)max_batch;
-  if ((st = u->pool.reserve(tot * sizeof(float)))) return fail(st);
-  if ((st = u->emb_all.reserve(B * u->emb_cols * sizeof(float)))) return fail(st);
-  if ((st = u->temb.reserve(B * TCH * sizeof(float)))) return fail(st);
-  if ((st = u->e1.reserve(B * EMB * sizeof(float)))) return fail(st);
-  if ((st = u->emb.reserve(B * EMB * sizeof(float)))) return fail(st);
-  if ((st = u->t_cur.reserve(B * sizeof(int64_t)))) return fail(st);
-  if ((st = u->x0a.reserve(B * L * sizeof(float)))) return fail(st);
-  if ((st = u->x0b.reserve(B * L * sizeof(float)))) return fail(st);
-  if ((st = u->xcur.reserve(B * L * sizeof(float)))) return fail(st);
-  if ((st = u->state.reserve(sizeof(StepState)))) return fail(st);
   ce = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM);
   if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
+  ce = cudaEventCreateWithFlags(&u->fork, cudaEventDisableTiming);
+  if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
+  const int n_lanes = max_batch < 8 ? max_batch : 8;
+  if ((st = surfd_unet_set_lanes(u, n_lanes))) return fail(st);
   *out = u;
   return 0;
 }
 
 extern "C" void surfd_unet_destroy(surfd_unet* u) {
   if (!u) return;
-  if (u->graph_exec) cudaGraphExecDestroy(u->graph_exec);
-  u->weights.release(); u->pool.release(); u->emb_all.release(); u->temb.release(); u->e1.release(); u->emb.release();
-  u->t_cur.release(); u->x0a.release(); u->x0b.release(); u->xcur.release(); u->state.release();
+  cudaDeviceSynchronize();
+  for (auto& ln : u->lanes) ln.release();
+  if (u->fork) cudaEventDestroy(u->fork);
+  u->weights.release();
   delete u;
 }
 
-// one model evaluation: x [B][L], t [B] -> x0 [B][L]
-static int unet_run(surfd_unet* u, int B, const float* x, const int64_t* t, const float* ctx, const int64_t* lab, float* x0,
+// one model evaluation on a lane's buffers: x [B][L], t [B] -> x0 [B][L]
+static int unet_run(surfd_unet* u, Lane& ln, int B, const float* x, const int64_t* t, const float* ctx, const int64_t* lab, float* x0,
                     cudaStream_t st) {
   const auto& h = u->hdr;
   // ---- embedding ----
-  temb_kernel<<<(unsigned)cdiv((int64_t)B * (TCH / 2), 128), 128, 0, st>>>(t, B, u->temb.as<float>());
+  temb_kernel<<<(unsigned)cdiv((int64_t)B * (TCH / 2), 128), 128, 0, st>>>(t, B, ln.temb.as<float>());
   SURFD_CHECK_LAUNCH();
   const dim3 g1((unsigned)cdiv(EMB, 8), (unsigned)cdiv(B, 8));
-  linear_rows_kernel<<<g1, 256, 0, st>>>(u->temb.as<float>(), B, TCH, u->w(h[5]), u->w(h[6]), EMB, 0, 1, 0, u->e1.as<float>());
+  linear_rows_kernel<<<g1, 256, 0, st>>>(ln.temb.as<float>(), B, TCH, u->w(h[5]), u->w(h[6]), EMB, 0, 1, 0, ln.e1.as<float>());
   SURFD_CHECK_LAUNCH();
-  linear_rows_kernel<<<g1, 256, 0, st>>>(u->e1.as<float>(), B, EMB, u->w(h[7]), u->w(h[8]), EMB, 0, 0, 0, u->emb.as<float>());
+  linear_rows_kernel<<<g1, 256, 0, st>>>(ln.e1.as<float>(), B, EMB, u->w(h[7]), u->w(h[8]), EMB, 0, 0, 0, ln.emb.as<float>());
   SURFD_CHECK_LAUNCH();
   if (lab) {
     SURFD_REQUIRE(h[11] >= 0, "labels given but the checkpoint has no label_emb");
-    label_add_kernel<<<(unsigned)cdiv((int64_t)B * EMB, 256), 256, 0, st>>>(lab, B, u->w(h[11]), u->emb.as<float>());
+    label_add_kernel<<<(unsigned)cdiv((int64_t)B * EMB, 256), 256, 0, st>>>(lab, B, u->w(h[11]), ln.emb.as<float>());
     SURFD_CHECK_LAUNCH();
   }
   if (ctx) {
-    linear_rows_kernel<<<g1, 256, 0, st>>>(ctx, B, CTX, u->w(h[9]), u->w(h[10]), EMB, 0, 0, 1, u->emb.as<float>());
+    linear_rows_kernel<<<g1, 256, 0, st>>>(ctx, B, CTX, u->w(h[9]), u->w(h[10]), EMB, 0, 0, 1, ln.emb.as<float>());
     SURFD_CHECK_LAUNCH();
   }
   const dim3 g2((unsigned)cdiv(u->emb_cols, 8), (unsigned)cdiv(B, 8));
-  linear_rows_kernel<<<g2, 256, 0, st>>>(u->emb.as<float>(), B, EMB, u->w(h[3]), u->w(h[4]), u->emb_cols, 1, 0, 0, u->emb_all.as<float>());
+  linear_rows_kernel<<<g2, 256, 0, st>>>(ln.emb.as<float>(), B, EMB, u->w(h[3]), u->w(h[4]), u->emb_cols, 1, 0, 0, ln.emb_all.as<float>());
   SURFD_CHECK_LAUNCH();
   // ---- program ----
   for (const auto& r : u->prog) {
     switch (r[0]) {
       case OP_INCONV: {
         const int N = (int)r[2], L = (int)r[3];
-        inconv_kernel<<<(unsigned)cdiv((int64_t)B * L * N, 256), 256, 0, st>>>(x, B, L, N, u->w(r[4]), u->w(r[5]), u->buf(r[1]));
+        inconv_kernel<<<(unsigned)cdiv((int64_t)B * L * N, 256), 256, 0, st>>>(x, B, L, N, u->w(r[4]), u->w(r[5]), ln.buf(r[1]));
         SURFD_CHECK_LAUNCH();
         break;
       }
       case OP_GN: {
         const int C1 = (int)r[2], C2 = (int)r[4], T = (int)r[5];
-        gn_kernel<<<(unsigned)(B * 32), 128, 0, st>>>(u->buf(r[1]), C1, r[3] >= 0 ? u->buf(r[3]) : nullptr, C2, T, u->w(r[9]), u->w(r[10]),
-                                                      (int)r[8], u->buf(r[6]), r[7] >= 0 ? u->buf(r[7]) : nullptr);
+        gn_kernel<<<(unsigned)(B * 32), 128, 0, st>>>(ln.buf(r[1]), C1, r[3] >= 0 ? ln.buf(r[3]) : nullptr, C2, T, u->w(r[9]), u->w(r[10]),
+                                                      (int)r[8], ln.buf(r[6]), r[7] >= 0 ? ln.buf(r[7]) : nullptr);
         SURFD_CHECK_LAUNCH();
         break;
       }
       case OP_CONV: {
         ConvArgs a{};
-        a.out = u->buf(r[1]); a.N = (int)r[2]; a.T_out = (int)r[3]; a.nseg = (int)r[4]; a.B = B;
+        a.out = ln.buf(r[1]); a.N = (int)r[2]; a.T_out = (int)r[3]; a.nseg = (int)r[4]; a.B = B;
         for (int s = 0; s < a.nseg; ++s) {
           const int64_t* q = &r[5 + 7 * s];
-          a.seg[s].A = u->buf(q[0]); a.seg[s].Cin = (int)q[1]; a.seg[s].taps = (int)q[2]; a.seg[s].stride = (int)q[3];
+          a.seg[s].A = ln.buf(q[0]); a.seg[s].Cin = (int)q[1]; a.seg[s].taps = (int)q[2]; a.seg[s].stride = (int)q[3];
           a.seg[s].up = (int)q[4]; a.seg[s].T_in = (int)q[5]; a.seg[s].W = u->w(q[6]);
         }
         a.bias = u->w(r[19]);
-        a.emb = r[20] >= 0 ? u->emb_all.as<float>() + r[20] : nullptr;
+        a.emb = r[20] >= 0 ? ln.emb_all.as<float>() + r[20] : nullptr;
         a.emb_ld = u->emb_cols;
-        a.residual = r[21] >= 0 ? u->buf(r[21]) : nullptr;
+        a.residual = r[21] >= 0 ? ln.buf(r[21]) : nullptr;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(a.N / CT), (unsigned)cdiv((int64_t)B * a.T_out, CT), KSPLIT);
         cfg.blockDim = dim3(256);
@@ -540,13 +586,13 @@ static int unet_run(surfd_unet* u, int B, const float* x, const int64_t* t, cons
         const int ch = C / heads;
         const float scale = (float)(1.0 / sqrt(sqrt((double)ch)));
         const size_t smem = ((size_t)3 * T * ch + (size_t)T * (T + 1)) * sizeof(float);
-        attn_kernel<<<(unsigned)(B * heads), 128, smem, st>>>(u->buf(r[1]), C, T, heads, scale, u->buf(r[4]));
+        attn_kernel<<<(unsigned)(B * heads), 128, smem, st>>>(ln.buf(r[1]), C, T, heads, scale, ln.buf(r[4]));
         SURFD_CHECK_LAUNCH();
         break;
       }
       case OP_OUTCONV: {
         const int C = (int)r[2], T = (int)r[3];
-        outconv_kernel<<<(unsigned)cdiv((int64_t)B * T * 32, 256), 256, 0, st>>>(u->buf(r[1]), B, T, C, u->w(r[4]), u->w(r[5]), x0);
+        outconv_kernel<<<(unsigned)cdiv((int64_t)B * T * 32, 256), 256, 0, st>>>(ln.buf(r[1]), B, T, C, u->w(r[4]), u->w(r[5]), x0);
         SURFD_CHECK_LAUNCH();
         break;
       }
@@ -561,20 +607,20 @@ extern "C" int surfd_unet_forward(surfd_unet* u, int B, const float* x_dev, cons
                                   const int64_t* labels_dev, float* out_dev, void* stream) {
   SURFD_REQUIRE(u && x_dev && t_dev && out_dev, "null argument");
   SURFD_REQUIRE(B >= 1 && B <= u->max_batch, "batch exceeds max_batch");
-  return unet_run(u, B, x_dev, t_dev, context_dev, labels_dev, out_dev, (cudaStream_t)stream);
+  return unet_run(u, u->lanes[0], B, x_dev, t_dev, context_dev, labels_dev, out_dev, (cudaStream_t)stream);
 }
 
-static int record_step(surfd_unet* u, int B, const int64_t* tmap, const float* coef, const float* noise, const float* ctx,
-                       const int64_t* lab, float guidance, cudaStream_t st) {
-  StepState* ss = u->state.as<StepState>();
-  step_begin_kernel<<<(unsigned)cdiv(B, 128), 128, 0, st>>>(ss, tmap, B, u->t_cur.as<int64_t>());
+static int record_step(surfd_unet* u, Lane& ln, int B, const int64_t* tmap, const float* coef, const float* noise, int64_t noise_stride,
+                       const float* ctx, const int64_t* lab, float guidance, cudaStream_t st) {
+  StepState* ss = ln.state.as<StepState>();
+  step_begin_kernel<<<(unsigned)cdiv(B, 128), 128, 0, st>>>(ss, tmap, B, ln.t_cur.as<int64_t>());
   SURFD_CHECK_LAUNCH();
-  SURFD_TRY(unet_run(u, B, u->xcur.as<float>(), u->t_cur.as<int64_t>(), ctx, lab, u->x0a.as<float>(), st));
+  SURFD_TRY(unet_run(u, ln, B, ln.xcur.as<float>(), ln.t_cur.as<int64_t>(), ctx, lab, ln.x0a.as<float>(), st));
   const bool cfg = guidance != 1.0f;
-  if (cfg) SURFD_TRY(unet_run(u, B, u->xcur.as<float>(), u->t_cur.as<int64_t>(), ctx, lab, u->x0b.as<float>(), st));
+  if (cfg) SURFD_TRY(unet_run(u, ln, B, ln.xcur.as<float>(), ln.t_cur.as<int64_t>(), ctx, lab, ln.x0b.as<float>(), st));
   const int n = B * u->L;
-  ddpm_update_kernel<<<(unsigned)cdiv(n, 128), 128, 0, st>>>(ss, coef, u->x0a.as<float>(), cfg ? u->x0b.as<float>() : nullptr, guidance, noise,
-                                                             n, u->xcur.as<float>());
+  ddpm_update_kernel<<<(unsigned)cdiv(n, 128), 128, 0, st>>>(ss, coef, ln.x0a.as<float>(), cfg ? ln.x0b.as<float>() : nullptr, guidance, noise,
+                                                             noise_stride, n, ln.xcur.as<float>());
   SURFD_CHECK_LAUNCH();
   step_advance_kernel<<<1, 1, 0, st>>>(ss);
   SURFD_CHECK_LAUNCH();
@@ -587,39 +633,64 @@ extern "C" int surfd_sample(surfd_unet* u, int B, int n_steps, const int64_t* tm
   SURFD_REQUIRE(B >= 1 && B <= u->max_batch, "batch exceeds max_batch");
   SURFD_REQUIRE(n_steps >= 1, "n_steps must be positive");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t nbytes = (size_t)B * u->L * sizeof(float);
-  SURFD_CUDA(cudaMemcpyAsync(u->xcur.p, noise_dev, nbytes, cudaMemcpyDeviceToDevice, st));   // x_T = noise row 0
-  StepState init{0, n_steps};
-  SURFD_CUDA(cudaMemcpyAsync(u->state.p, &init, sizeof(init), cudaMemcpyHostToDevice, st));
-  const bool reuse = u->graph_exec && u->graph_B == B && u->graph_ctx == context_dev && u->graph_lab == labels_dev &&
-                     u->graph_tmap == tmap_dev && u->graph_coef == coef_dev && u->graph_noise == noise_dev && u->graph_guidance == guidance;
-  if (!reuse) {
-    if (u->graph_exec) { cudaGraphExecDestroy(u->graph_exec); u->graph_exec = nullptr; }
-    // capture on a private stream so the caller's stream (possibly the legacy default) is left alone
-    cudaStream_t cs;
-    SURFD_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
-    int rc = 0;
-    if (ce == cudaSuccess) {
-      const int64_t launches_before = g_launch_count;
-      rc = record_step(u, B, tmap_dev, coef_dev, noise_dev, context_dev, labels_dev, guidance, cs);
-      u->graph_launches = g_launch_count - launches_before;
-      g_launch_count = launches_before;   // capture is not execution; launches are counted per replay below
-      ce = cudaStreamEndCapture(cs, &graph);
+  const int L = u->L;
+  const int n_lanes = (int)u->lanes.size() < B ? (int)u->lanes.size() : B;
+  const int64_t stride = (int64_t)B * L;
+  SURFD_CUDA(cudaEventRecord(u->fork, st));
+  int off = 0;
+  for (int li = 0; li < n_lanes; ++li) {
+    Lane& ln = u->lanes[(size_t)li];
+    const int b = B / n_lanes + (li < B % n_lanes ? 1 : 0);
+    SURFD_REQUIRE(b <= ln.cap, "lane capacity exceeded");
+    const float* noise = noise_dev + (size_t)off * L;
+    const float* ctx = context_dev ? context_dev + (size_t)off * CTX : nullptr;
+    const int64_t* lab = labels_dev ? labels_dev + off : nullptr;
+    SURFD_CUDA(cudaStreamWaitEvent(ln.stream, u->fork, 0));
+    SURFD_CUDA(cudaMemcpyAsync(ln.xcur.p, noise, (size_t)b * L * sizeof(float), cudaMemcpyDeviceToDevice, ln.stream));   // x_T = noise row 0
+    StepState init{0, n_steps};
+    SURFD_CUDA(cudaMemcpyAsync(ln.state.p, &init, sizeof(init), cudaMemcpyHostToDevice, ln.stream));
+    const bool reuse = ln.graph_exec && ln.graph_B == b && ln.graph_ctx == ctx && ln.graph_lab == lab && ln.graph_tmap == tmap_dev &&
+                       ln.graph_coef == coef_dev && ln.graph_noise == noise && ln.graph_stride == stride && ln.graph_guidance == guidance;
+    if (!reuse) {
+      if (ln.graph_exec) { cudaGraphExecDestroy(ln.graph_exec); ln.graph_exec = nullptr; }
+      cudaStream_t cs;
+      SURFD_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      int rc = 0;
+      if (ce == cudaSuccess) {
+        const int64_t launches_before = g_launch_count;
+        rc = record_step(u, ln, b, tmap_dev, coef_dev, noise, stride, ctx, lab, guidance, cs);
+        ln.graph_launches = g_launch_count - launches_before;
+        g_launch_count = launches_before;   // capture is not execution; launches are counted per replay below
+        ce = cudaStreamEndCapture(cs, &graph);
+      }
+      if (ce == cudaSuccess && rc == 0) ce = cudaGraphInstantiate(&ln.graph_exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      cudaStreamDestroy(cs);
+      if (rc) return rc;
+      if (ce != cudaSuccess) { ln.graph_exec = nullptr; return set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__); }
+      ln.graph_B = b; ln.graph_ctx = ctx; ln.graph_lab = lab; ln.graph_tmap = tmap_dev; ln.graph_coef = coef_dev;
+      ln.graph_noise = noise; ln.graph_stride = stride; ln.graph_guidance = guidance;
     }
-    if (ce == cudaSuccess && rc == 0) ce = cudaGraphInstantiate(&u->graph_exec, graph, 0);
-    if (graph) cudaGraphDestroy(graph);
-    cudaStreamDestroy(cs);
-    if (rc) return rc;
-    if (ce != cudaSuccess) { u->graph_exec = nullptr; return set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__); }
-    u->graph_B = B; u->graph_ctx = context_dev; u->graph_lab = labels_dev; u->graph_tmap = tmap_dev; u->graph_coef = coef_dev;
-    u->graph_noise = noise_dev; u->graph_guidance = guidance;
+    off += b;
   }
+  // interleave the lanes' graph launches step by step so they progress together (and share weight lines in L2)
   for (int i = 0; i < n_steps; ++i) {
-    SURFD_CUDA(cudaGraphLaunch(u->graph_exec, st));
-    g_launch_count += u->graph_launches;
+    for (int li = 0; li < n_lanes; ++li) {
+      Lane& ln = u->lanes[(size_t)li];
+      SURFD_CUDA(cudaGraphLaunch(ln.graph_exec, ln.stream));
+      g_launch_count += ln.graph_launches;
+    }
   }
-  SURFD_CUDA(cudaMemcpyAsync(out_dev, u->xcur.p, nbytes, cudaMemcpyDeviceToDevice, st));
+  off = 0;
+  for (int li = 0; li < n_lanes; ++li) {
+    Lane& ln = u->lanes[(size_t)li];
+    const int b = B / n_lanes + (li < B % n_lanes ? 1 : 0);
+    SURFD_CUDA(cudaMemcpyAsync(out_dev + (size_t)off * L, ln.xcur.p, (size_t)b * L * sizeof(float), cudaMemcpyDeviceToDevice, ln.stream));
+    SURFD_CUDA(cudaEventRecord(ln.done, ln.stream));
+    SURFD_CUDA(cudaStreamWaitEvent(st, ln.done, 0));
+    off += b;
+  }
   return 0;
 }

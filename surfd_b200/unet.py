@@ -366,6 +366,10 @@ class UNetSampler:
         except Exception:
             pass
 
+    def set_lanes(self, n):
+        """number of concurrent sampler streams a batch is split over (default min(8, max_batch))"""
+        _lib.check(self.lib.surfd_unet_set_lanes(self._h, int(n)))
+
     def forward(self, x, t, context=None, labels=None):
         """x [B,1,L], t [B] int64 (original-process timesteps) -> model output [B,1,L]  (MDM.forward)"""
         B = x.shape[0]

@@ -70,7 +70,7 @@ def main():
         res[f"sample_100steps_B{B}_ms_per_step"] = t * 10
     res["launches"] = int(_lib.load().surfd_launch_count(0))
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open("gpurun_out/probe.json", "w"), indent=1)
+    json.dump(res, open(os.environ.get("PROBE_OUT", "gpurun_out/probe.json"), "w"), indent=1)
     print(json.dumps(res, indent=1))
 
 
