@@ -113,8 +113,10 @@ int surfd_unet_create(const float* packed, size_t n_floats, const int64_t* progr
                       int max_batch, surfd_unet** out);
 void surfd_unet_destroy(surfd_unet* u);
 /* The denoiser is latency-bound (~170 dependent small kernels per step), so surfd_sample() splits a batch over `n_lanes`
- * concurrent streams (private activations, shared weights).  Default min(8, max_batch).  Results do not depend on it. */
+ * concurrent streams (private activations, shared weights).  Default 1 (measured fastest).  Results do not depend on it. */
 int surfd_unet_set_lanes(surfd_unet* u, int n_lanes);
+/* token-GEMM arithmetic: 0 = fp32 FFMA, 1 = mma.sync 3xTF32 split (fp32-class accuracy, default), 2 = single-pass TF32 */
+int surfd_unet_set_precision(surfd_unet* u, int mode);
 size_t surfd_unet_packed_floats(void);
 /* one model evaluation x0_hat = model(x_t, t, context/labels): teacher-forced parity entry.
  * x_dev [B][L]; t_dev [B] int64 (already mapped through timestep_map); context_dev [B][512] or NULL;

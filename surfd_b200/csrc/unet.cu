@@ -102,6 +102,20 @@ constexpr int KSPLIT = 8;     // CTAs per cluster: the K reduction is split over
 // (M = 32 tokens, K = 5376) put 200+ CTAs on the machine and every weight byte is fetched exactly once.  Partial
 // tiles are reduced first across the warps of a CTA (shared memory) and then across the cluster through distributed
 // shared memory in a fixed order -- deterministic, no atomics, no second kernel.
+// MODE 0: fp32 FFMA.  MODE 1: tensor cores, mma.sync m16n8k8 with the 3xTF32 split (a = hi + lo, products hi*hi + hi*lo +
+// lo*hi accumulate in fp32: ~2^-21 relative, fp32-class results at a tenth of the issue slots).  MODE 2: single TF32 pass.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(256)
 conv_gemm_kernel(ConvArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -119,8 +133,9 @@ conv_gemm_kernel(ConvArgs a) {
   const int rb = m_row / a.T_out, rl = m_row % a.T_out;
   const bool row_ok = m_row < M;
 
-  const int ly = lane >> 3, lx = lane & 7;
-  float acc[8][4];
+  const int ly = lane >> 3, lx = lane & 7;   // FFMA mapping: rows ly + 4i, cols lx + 8j
+  const int fg = lane >> 2, ft = lane & 3;   // MMA fragment mapping: group id / thread in group
+  float acc[8][4];                           // MODE 0: [i][j];  MODE 1/2: [mt*4 + nt][c0..c3]
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -155,20 +170,56 @@ conv_gemm_kernel(ConvArgs a) {
           *reinterpret_cast<float4*>(Ws + lane * CTP + 4 * j) = wv[j];
         }
         __syncwarp();
+        if (MODE == 0) {
 #pragma unroll
-        for (int kk = 0; kk < CT; kk += 4) {
-          float4 wj[4];
+          for (int kk = 0; kk < CT; kk += 4) {
+            float4 wj[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) wj[j] = *reinterpret_cast<const float4*>(Ws + (lx + 8 * j) * CTP + kk);
+            for (int j = 0; j < 4; ++j) wj[j] = *reinterpret_cast<const float4*>(Ws + (lx + 8 * j) * CTP + kk);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 ai = *reinterpret_cast<const float4*>(As + (ly + 4 * i) * CTP + kk);
+            for (int i = 0; i < 8; ++i) {
+              const float4 ai = *reinterpret_cast<const float4*>(As + (ly + 4 * i) * CTP + kk);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc[i][j] = fmaf(ai.x, wj[j].x, acc[i][j]);
-              acc[i][j] = fmaf(ai.y, wj[j].y, acc[i][j]);
-              acc[i][j] = fmaf(ai.z, wj[j].z, acc[i][j]);
-              acc[i][j] = fmaf(ai.w, wj[j].w, acc[i][j]);
+              for (int j = 0; j < 4; ++j) {
+                acc[i][j] = fmaf(ai.x, wj[j].x, acc[i][j]);
+                acc[i][j] = fmaf(ai.y, wj[j].y, acc[i][j]);
+                acc[i][j] = fmaf(ai.z, wj[j].z, acc[i][j]);
+                acc[i][j] = fmaf(ai.w, wj[j].w, acc[i][j]);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k0 = 0; k0 < CT; k0 += 8) {
+            // A fragments (16x8, row-major): a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4)
+            uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              const float* ap = As + (mt * 16 + fg) * CTP + k0 + ft;
+              const float x[4] = {ap[0], ap[8 * CTP], ap[4], ap[8 * CTP + 4]};
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                ahi[mt][r] = to_tf32(x[r]);
+                if (MODE == 1) alo[mt][r] = to_tf32(x[r] - __uint_as_float(ahi[mt][r]));
+              }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              // B fragment (8x8, k x n): b0 (k = t, n = g) b1 (k = t+4, n = g); W tile is [n][k]
+              const float* bp = Ws + (nt * 8 + fg) * CTP + k0 + ft;
+              const float y[2] = {bp[0], bp[4]};
+              uint32_t bhi[2], blo[2];
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                bhi[r] = to_tf32(y[r]);
+                if (MODE == 1) blo[r] = to_tf32(y[r] - __uint_as_float(bhi[r]));
+              }
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                float* c = acc[mt * 4 + nt];
+                if (MODE == 1) { mma_tf32(c, alo[mt], bhi); mma_tf32(c, ahi[mt], blo); }
+                mma_tf32(c, ahi[mt], bhi);
+              }
             }
           }
         }
@@ -179,10 +230,21 @@ conv_gemm_kernel(ConvArgs a) {
   __syncthreads();
   float* red = smem;
   float* part = smem + 8 * CT * 33;   // [32][32] CTA partial, read by the other CTAs of the cluster
+  if (MODE == 0) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) red[(warp * CT + (ly + 4 * i)) * 33 + (lx + 8 * j)] = acc[i][j];
+      for (int j = 0; j < 4; ++j) red[(warp * CT + (ly + 4 * i)) * 33 + (lx + 8 * j)] = acc[i][j];
+  } else {
+    // accumulator fragment: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          red[(warp * CT + (mt * 16 + fg + (r >> 1) * 8)) * 33 + (nt * 8 + 2 * ft + (r & 1))] = acc[mt * 4 + nt][r];
+  }
   __syncthreads();
   {
     const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
@@ -431,6 +493,7 @@ struct Lane {
 
 struct surfd_unet {
   int L = 0, max_batch = 0;
+  int precision = 1;   // token GEMMs: 0 fp32 FFMA, 1 3xTF32 mma.sync (fp32-class accuracy, default), 2 single-pass TF32
   DevBuf weights;
   std::vector<int64_t> hdr, buf_sizes;
   std::vector<std::vector<int64_t>> prog;
@@ -461,6 +524,18 @@ static int lane_init(surfd_unet* u, Lane& ln, int cap) {
   SURFD_TRY(ln.state.reserve(sizeof(StepState)));
   if (!ln.stream) SURFD_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
   if (!ln.done) SURFD_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+  return 0;
+}
+
+extern "C" int surfd_unet_set_precision(surfd_unet* u, int mode) {
+  SURFD_REQUIRE(u != nullptr && mode >= 0 && mode <= 2, "precision mode must be 0 (fp32), 1 (3xTF32) or 2 (TF32)");
+  if (mode != u->precision) {
+    SURFD_CUDA(cudaDeviceSynchronize());
+    for (auto& ln : u->lanes) {   // captured step graphs embed the kernel variant
+      if (ln.graph_exec) { cudaGraphExecDestroy(ln.graph_exec); ln.graph_exec = nullptr; }
+    }
+    u->precision = mode;
+  }
   return 0;
 }
 
@@ -497,12 +572,15 @@ extern "C" int surfd_unet_create(const float* packed, size_t n_floats, const int
   if ((st = u->weights.reserve(n_floats * sizeof(float)))) return fail(st);
   cudaError_t ce = cudaMemcpy(u->weights.p, packed, n_floats * sizeof(float), cudaMemcpyDefault);
   if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
-  ce = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM);
+  ce = cudaFuncSetAttribute(conv_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM);
   if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
   ce = cudaEventCreateWithFlags(&u->fork, cudaEventDisableTiming);
   if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
-  const int n_lanes = max_batch < 8 ? max_batch : 8;
-  if ((st = surfd_unet_set_lanes(u, n_lanes))) return fail(st);
+  // measured on B200 (B=8, L=32): 1 lane 2.6 ms/step, 8 concurrent lanes 5.6 ms/step -- many tiny cluster launches from
+  // several streams contend in the front end, so the default is a single lane; set_lanes() stays for experiments.
+  if ((st = surfd_unet_set_lanes(u, 1))) return fail(st);
   *out = u;
   return 0;
 }
@@ -577,7 +655,9 @@ static int unet_run(surfd_unet* u, Lane& ln, int B, const float* x, const int64_
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = KSPLIT;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        SURFD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel, a));
+        if (u->precision == 0) SURFD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<0>, a));
+        else if (u->precision == 1) SURFD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<1>, a));
+        else SURFD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2>, a));
         SURFD_CHECK_LAUNCH();
         break;
       }

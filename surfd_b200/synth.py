@@ -104,8 +104,14 @@ def poly_logit(d):
     return 2 - 40 * d + (v[None, :] * torch.relu(k[None, :] - d.reshape(-1, 1))).sum(-1).reshape(d.shape)
 
 
+POLY_CLIP = 0.17
+
+
 def synth_ae_poly(latent_dim=32, seed=4321, r0=0.5, amp=0.05):
-    H = 512
+    """All intermediate quantities are kept non-negative and <= 2*POLY_CLIP (plane distances are clipped to
+    [-c, c] and shifted by +c before the max-tournament), so a TF32 rounding of an activation moves it by <= 6e-5:
+    the field is well conditioned for the tensor-core path as well as in fp32."""
+    H, c = 512, POLY_CLIP
     sd = {}
     for key, shp in expected_keys(latent_dim).items():
         if key.endswith("num_batches_tracked"):
@@ -118,42 +124,45 @@ def synth_ae_poly(latent_dim=32, seed=4321, r0=0.5, amp=0.05):
             sd[key] = torch.zeros(shp)
     n = poly_planes(32)
     U = _poly_u(latent_dim, seed, amp)
-    # level-0 channels: plane i -> (2i: +a_i, 2i+1: -a_i),  a_i = n_i.x - r0 ; tau enters through bn_0 beta of block 0
+    # level 0: plane i -> channels (2i: a_i + c, 2i+1: a_i - c), a_i = n_i.x - r0 (+ tau_i(z) through bn_0's beta);
+    # A'_i = relu(a_i + c) - relu(a_i - c) = clip(a_i, -c, c) + c   in [0, 2c]
     Wp, bp = sd["decoder.fc_p.weight"], sd["decoder.fc_p.bias"]
     for i in range(32):
-        Wp[2 * i, 0:3, 0] = n[i]
-        Wp[2 * i + 1, 0:3, 0] = -n[i]
-        bp[2 * i] = -r0
-        bp[2 * i + 1] = r0
-        sd["decoder.blocks.0.bn_0.conv_beta.weight"][2 * i, :, 0] = U[i]
-        sd["decoder.blocks.0.bn_0.conv_beta.weight"][2 * i + 1, :, 0] = -U[i]
+        for j, off in ((2 * i, c), (2 * i + 1, -c)):
+            Wp[j, 0:3, 0] = n[i]
+            bp[j] = -r0 + off
+            sd["decoder.blocks.0.bn_0.conv_beta.weight"][j, :, 0] = U[i]
     k, v = _poly_pl()
     K = k.numel()
-    base = [0, 64, 96, 112, 120]      # first channel of level l's (+,-) pairs; level 4 = A+,A-,B+,B- at 120..123
-    CH_D = 124                        # D = B - A
-    CH_ABS = 125                      # K+1 copies of d = |max(A,B)| from here
+    base = [0, 64, 80, 88]            # first channel of level 0 (pairs), levels 1..3 (single non-negative channels)
+    CH_A, CH_B, CH_D = 92, 93, 94     # level 4: A' = max of the first half, B' of the second, D = B' - A'
+    CH_ABS = 95                       # K+1 copies of d = |max - c| from here
     assert CH_ABS + K + 1 <= H
     for lvl in range(4):              # blocks 0..3: 32 -> 16 -> 8 -> 4 -> 2
         n_in = 32 >> lvl
         W0 = sd[f"decoder.blocks.{lvl}.fc_0.weight"]
         W1 = sd[f"decoder.blocks.{lvl}.fc_1.weight"]
+
+        def val(row, idx, sgn):      # add sgn * X_idx (level `lvl` value) to hidden row `row`
+            if lvl == 0:
+                W0[row, 2 * idx, 0] += sgn; W0[row, 2 * idx + 1, 0] -= sgn
+            else:
+                W0[row, base[lvl] + idx, 0] += sgn
         for p in range(n_in // 2):
-            a_p, a_m = base[lvl] + 4 * p, base[lvl] + 4 * p + 1
-            b_p, b_m = base[lvl] + 4 * p + 2, base[lvl] + 4 * p + 3
-            h = 3 * p                 # hidden channels: relu(a), relu(-a), relu(b-a)
-            W0[h, a_p, 0] = 1; W0[h, a_m, 0] = -1
-            W0[h + 1, a_p, 0] = -1; W0[h + 1, a_m, 0] = 1
-            W0[h + 2, b_p, 0] = 1; W0[h + 2, b_m, 0] = -1; W0[h + 2, a_p, 0] = -1; W0[h + 2, a_m, 0] = 1
-            for c, sgn in ((base[lvl + 1] + 2 * p, 1.0), (base[lvl + 1] + 2 * p + 1, -1.0)):
-                W1[c, h, 0] = sgn; W1[c, h + 1, 0] = -sgn; W1[c, h + 2, 0] = sgn
-            if lvl == 3:
-                # D = B - A = M(pair 1) - M(pair 0), written while the two level-4 values are produced
+            h = 2 * p                 # hidden: X_a (copy, non-negative) and relu(X_b - X_a)
+            val(h, 2 * p, 1.0)
+            val(h + 1, 2 * p + 1, 1.0); val(h + 1, 2 * p, -1.0)
+            if lvl < 3:
+                W1[base[lvl + 1] + p, h, 0] = 1; W1[base[lvl + 1] + p, h + 1, 0] = 1
+            else:
+                dst = CH_A if p == 0 else CH_B
+                W1[dst, h, 0] = 1; W1[dst, h + 1, 0] = 1
                 sgn = -1.0 if p == 0 else 1.0
-                W1[CH_D, h, 0] = sgn; W1[CH_D, h + 1, 0] = -sgn; W1[CH_D, h + 2, 0] = sgn
-    # block 4: relu(A), relu(-A), relu(D) -> h+ = relu(M), h- = relu(-M), M = A + relu(D);  d = h+ + h-
-    W0, W1 = sd["decoder.blocks.4.fc_0.weight"], sd["decoder.blocks.4.fc_1.weight"]
-    W0[0, 120, 0] = 1; W0[0, 121, 0] = -1; W0[0, CH_D, 0] = 1
-    W0[1, 120, 0] = -1; W0[1, 121, 0] = 1; W0[1, CH_D, 0] = -1
+                W1[CH_D, h, 0] = sgn; W1[CH_D, h + 1, 0] = sgn
+    # block 4: relu(A'), relu(D) -> h+ = relu(M' - c), h- = relu(c - M'), M' = A' + relu(D);  d = h+ + h-
+    W0, b0, W1 = sd["decoder.blocks.4.fc_0.weight"], sd["decoder.blocks.4.fc_0.bias"], sd["decoder.blocks.4.fc_1.weight"]
+    W0[0, CH_A, 0] = 1; W0[0, CH_D, 0] = 1; b0[0] = -c
+    W0[1, CH_A, 0] = -1; W0[1, CH_D, 0] = -1; b0[1] = c
     for j in range(K + 1):
         W1[CH_ABS + j, 0, 0] = 1; W1[CH_ABS + j, 1, 0] = 1
     # final CBN: channel CH_ABS: relu(d) (gamma=1, beta=0) with fc_out -40; channels CH_ABS+1+j: relu(k_j - d), fc_out v_j
@@ -169,11 +178,11 @@ def synth_ae_poly(latent_dim=32, seed=4321, r0=0.5, amp=0.05):
 
 def poly_udf(pts, latent, seed=4321, r0=0.5, amp=0.05):
     """the field the 'poly' checkpoint encodes, evaluated directly in float64:
-    0.1*(1 - sigmoid(logit_PL(|m|))), m = max_i(n_i.x - r_i(z));  ~= |m| for |m| <= 0.05"""
+    0.1*(1 - sigmoid(logit_PL(|clip(m, -c, c)|))), m = max_i(n_i.x - r_i(z));  ~= |m| for |m| <= 0.05"""
     n = poly_planes(32).to(torch.float64)
     r = poly_offsets(latent, seed, r0, amp).to(torch.float64)
     m = (pts.to(torch.float64) @ n.T - r).max(-1).values
-    return 0.1 * (1 - torch.sigmoid(poly_logit(m.abs()))), m
+    return 0.1 * (1 - torch.sigmoid(poly_logit(m.clamp(-POLY_CLIP, POLY_CLIP).abs()))), m
 
 
 def synth_mdm(L=32, cond_mode="no_cond", seed=1234, num_actions=9):

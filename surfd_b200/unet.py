@@ -366,6 +366,10 @@ class UNetSampler:
         except Exception:
             pass
 
+    def set_precision(self, mode):
+        """token GEMMs: 0 fp32 FFMA, 1 mma.sync 3xTF32 (default, fp32-class accuracy), 2 single-pass TF32"""
+        _lib.check(self.lib.surfd_unet_set_precision(self._h, int(mode)))
+
     def set_lanes(self, n):
         """number of concurrent sampler streams a batch is split over (default min(8, max_batch))"""
         _lib.check(self.lib.surfd_unet_set_lanes(self._h, int(n)))

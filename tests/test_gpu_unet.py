@@ -35,6 +35,30 @@ def test_forward_and_sample_match_reference_golden(case):
     assert torch.equal(r, r2)
 
 
+@pytest.mark.parametrize("mode,tol", [(0, 1e-4), (1, 1e-4), (2, 5e-3)], ids=["fp32-ffma", "3xtf32-mma", "tf32-mma"])
+def test_token_gemm_precision_modes(mode, tol):
+    """fp32 FFMA and the 3xTF32 tensor-core split both meet the fp32 tolerance; single-pass TF32 meets the 'fast' one"""
+    g = np.load(os.path.join(GOLDEN, "unet.npz"))
+    net = U.UNetSampler(synth.synth_mdm(64, "img"), 64, "img", max_batch=4)
+    net.set_precision(mode)
+    o = net.forward(torch.from_numpy(g["img64_x"]), torch.from_numpy(g["img64_t"]), torch.from_numpy(g["img64_ctx"]))
+    err = float((o.cpu() - torch.from_numpy(g["img64_out"])).abs().max())
+    assert err < tol, (mode, err)
+    if mode == 2:
+        assert err > 1e-6, "single-pass TF32 returned fp32-exact output: the tensor-core variant did not run"
+
+
+def test_lanes_do_not_change_results():
+    L = 32
+    net = U.UNetSampler(synth.synth_mdm(L), L, max_batch=8)
+    S = U.SpacedSchedule(U.cosine_betas(), U.space_timesteps(1000, [5]))
+    noise = torch.randn(6, 7, L, generator=torch.Generator().manual_seed(4))
+    r1 = net.sample(S, noise)
+    net.set_lanes(4)
+    r4 = net.sample(S, noise)
+    assert torch.equal(r1, r4)
+
+
 def test_batch_independence_and_ragged_batches():
     L = 32
     sd = synth.synth_mdm(L)
