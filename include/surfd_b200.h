@@ -54,6 +54,9 @@ int surfd_dec_set_precision(surfd_decoder* d, int mode);
  * layer GEMM over M <= chunk points) timed with CUDA events on `stream`, `iters` back-to-back launches. */
 int surfd_dec_chunk_points(surfd_decoder* d);
 int surfd_dec_time_layer(surfd_decoder* d, int M, int iters, float* ms_per_launch, void* stream);
+/* test hook: one 512x512 layer (fc_0 of block `blk` + CBN/ReLU epilogue) over A_dev [M][512] with kernel `mode`
+ * (0 fp32 FFMA, 1 tcgen05 TF32), both on the TF32-rounded weights; out_dev [M][512] */
+int surfd_dec_debug_layer(surfd_decoder* d, const float* A_dev, int M, int blk, int mode, float* out_dev, void* stream);
 
 /* udf (and optionally -normalize(d udf/dx), meshudf.py:231-251) at explicit points.
  * pts_dev [M][3]; udf_dev [M]; grad_dev [M][3] or NULL.  Replaces udf_func / sample_udf /

@@ -1,0 +1,7 @@
+"""surfd_b200 -- the Surf-D generation hot path on B200."""
+import os
+
+# One main stream plus one stream per in-flight marching-cubes replay: with the default 8 hardware work queues two
+# streams alias and main-stream kernels wait behind a replay's pending result copy (measured: +0.74 s on one lattice).
+# Must be set before the CUDA context is created.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")

@@ -26,6 +26,7 @@ PROTOTYPES = {
     "surfd_dec_set_precision": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "surfd_dec_chunk_points": (ctypes.c_int, [c_vp]),
     "surfd_dec_time_layer": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp]),
+    "surfd_dec_debug_layer": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "surfd_udf_query": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "surfd_udf_lattice": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_vp, c_vp, ctypes.POINTER(c_i64), c_vp]),
     "surfd_mc_create": (ctypes.c_int, [ctypes.POINTER(c_vp)]),

@@ -766,6 +766,19 @@ extern "C" int surfd_dec_time_layer(surfd_decoder* d, int M, int iters, float* m
 
 extern "C" int surfd_dec_chunk_points(surfd_decoder* d) { return d ? d->chunk : 0; }
 
+// Test hook: one 512x512 layer (fc_0 of block `blk`, bias + CBN + ReLU epilogue, TF32-rounded activation output) over the
+// caller's A [M][512] with the kernel selected by `mode` (0 FFMA, 1 tcgen05); out [M][512].  Lets the tests compare the two
+// kernels element by element on arbitrary M (tails, multi-tile persistence).
+extern "C" int surfd_dec_debug_layer(surfd_decoder* d, const float* A_dev, int M, int blk, int mode, float* out_dev, void* stream) {
+  SURFD_REQUIRE(d && d->latent_set && A_dev && out_dev, "null argument / latent not set");
+  SURFD_REQUIRE(M >= 1 && blk >= 0 && blk < NBLK && (mode == 0 || mode == 1), "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Epilogue e{};
+  e.ld = HID; e.bias = d->b0(blk); e.act = out_dev; e.s2 = d->s(2 * blk + 1); e.t2 = d->t(2 * blk + 1); e.round_act = 1;
+  if (mode == 0) return launch_gemm(A_dev, HID, d->W0r(blk), HID, M, HID, HID, e, st);
+  return launch_gemm_tc(A_dev, d->W0r(blk), M, e, d->err.as<int>(), d->num_sms, st);
+}
+
 extern "C" int surfd_face_filter(surfd_decoder* d, const double* verts64_dev, const int32_t* faces_dev, int64_t n_f, int N,
                                  uint8_t* keep_dev, void* stream) {
   SURFD_REQUIRE(d && d->latent_set, "decoder latent not set");

@@ -23,7 +23,8 @@ constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4;               // 16 KB
 constexpr int B_BYTES = BN * BK * 4;               // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;     // 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STG_LD = 36;                         // padded row of the epilogue transpose stage (floats)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * STG_LD * 4 /*epilogue stages*/;
 constexpr int K_TOTAL = 512, KBLOCKS = K_TOTAL / BK;
 constexpr int THREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
@@ -184,47 +185,56 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m0 = (tile >> 1) * BM, n0 = (tile & 1) * BN;
       mbar_wait(&tfull[acc], acc_phase, err, 4);
       tc_fence_after();
-      const int m = m0 + row;
-      const bool ok = m < M;
-      const size_t rbase = (size_t)m * e.ld;
+      // Each thread owns one accumulator row in TMEM, but row-per-lane global accesses are fully divergent (32 lines per
+      // instruction; ncu: epilogue-bound at 18% tensor-pipe activity).  So every 32x32 block is transposed through a padded
+      // shared-memory stage and the global side runs with 8 lanes per row: 128 contiguous bytes per row, 4 rows per access.
+      float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * STG_LD);
+      const int srow = lane >> 3, scol = (lane & 7) * 4;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        if (ok) {
-          const int nb = n0 + c * 32;
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = nb + j;
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            if (e.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n)); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
-            if (e.mask) {
-              const float4 mk = *reinterpret_cast<const float4*>(e.mask + rbase + n);
-              const float4 ms = __ldg(reinterpret_cast<const float4*>(e.mscale + n));
-              v.x = mk.x > 0.f ? v.x * ms.x : 0.f; v.y = mk.y > 0.f ? v.y * ms.y : 0.f;
-              v.z = mk.z > 0.f ? v.z * ms.z : 0.f; v.w = mk.w > 0.f ? v.w * ms.w : 0.f;
-            }
-            if (e.R) { const float4 rr = *reinterpret_cast<const float4*>(e.R + rbase + n); v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
-            if (e.C) {
-              float4 o = v;
-              if (e.round_c) { o.x = round_to_tf32(o.x); o.y = round_to_tf32(o.y); o.z = round_to_tf32(o.z); o.w = round_to_tf32(o.w); }
-              *reinterpret_cast<float4*>(e.C + rbase + n) = o;
-            }
-            if (e.act) {
-              const float4 s2 = __ldg(reinterpret_cast<const float4*>(e.s2 + n));
-              const float4 t2 = __ldg(reinterpret_cast<const float4*>(e.t2 + n));
-              float4 a;
-              a.x = fmaxf(fmaf(s2.x, v.x, t2.x), 0.f); a.y = fmaxf(fmaf(s2.y, v.y, t2.y), 0.f);
-              a.z = fmaxf(fmaf(s2.z, v.z, t2.z), 0.f); a.w = fmaxf(fmaf(s2.w, v.w, t2.w), 0.f);
-              if (e.round_act) { a.x = round_to_tf32(a.x); a.y = round_to_tf32(a.y); a.z = round_to_tf32(a.z); a.w = round_to_tf32(a.w); }
-              *reinterpret_cast<float4*>(e.act + rbase + n) = a;
-            }
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(stage + lane * STG_LD + 4 * q) =
+              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+        __syncwarp();
+        const int n = n0 + c * 32 + scol;
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), ms = bias, s2 = bias, t2 = bias;
+        if (e.bias) bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+        if (e.mask) ms = __ldg(reinterpret_cast<const float4*>(e.mscale + n));
+        if (e.act) { s2 = __ldg(reinterpret_cast<const float4*>(e.s2 + n)); t2 = __ldg(reinterpret_cast<const float4*>(e.t2 + n)); }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + srow;
+          const int m = m0 + quad * 32 + rr;
+          if (m >= M) continue;
+          float4 v = *reinterpret_cast<const float4*>(stage + rr * STG_LD + scol);
+          const size_t off = (size_t)m * e.ld + n;
+          v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+          if (e.mask) {
+            const float4 mk = *reinterpret_cast<const float4*>(e.mask + off);
+            v.x = mk.x > 0.f ? v.x * ms.x : 0.f; v.y = mk.y > 0.f ? v.y * ms.y : 0.f;
+            v.z = mk.z > 0.f ? v.z * ms.z : 0.f; v.w = mk.w > 0.f ? v.w * ms.w : 0.f;
+          }
+          if (e.R) { const float4 q4 = *reinterpret_cast<const float4*>(e.R + off); v.x += q4.x; v.y += q4.y; v.z += q4.z; v.w += q4.w; }
+          if (e.C) {
+            float4 o = v;
+            if (e.round_c) { o.x = round_to_tf32(o.x); o.y = round_to_tf32(o.y); o.z = round_to_tf32(o.z); o.w = round_to_tf32(o.w); }
+            *reinterpret_cast<float4*>(e.C + off) = o;
+          }
+          if (e.act) {
+            float4 a;
+            a.x = fmaxf(fmaf(s2.x, v.x, t2.x), 0.f); a.y = fmaxf(fmaf(s2.y, v.y, t2.y), 0.f);
+            a.z = fmaxf(fmaf(s2.z, v.z, t2.z), 0.f); a.w = fmaxf(fmaf(s2.w, v.w, t2.w), 0.f);
+            if (e.round_act) { a.x = round_to_tf32(a.x); a.y = round_to_tf32(a.y); a.z = round_to_tf32(a.z); a.w = round_to_tf32(a.w); }
+            *reinterpret_cast<float4*>(e.act + off) = a;
           }
         }
       }

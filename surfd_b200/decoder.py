@@ -133,6 +133,13 @@ class UdfDecoder:
         _lib.check(self.lib.surfd_dec_time_layer(self._h, M, int(iters), ctypes.byref(ms), _lib.stream_ptr()))
         return float(ms.value), M
 
+    def debug_layer(self, A, blk=0, mode=0):
+        """one hidden layer over A [M,512] with the FFMA (mode 0) or tcgen05 (mode 1) kernel -- test hook"""
+        A = A.to(self.device, torch.float32).contiguous()
+        out = torch.empty_like(A)
+        _lib.check(self.lib.surfd_dec_debug_layer(self._h, _lib.ptr(A), A.shape[0], int(blk), int(mode), _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
     def face_filter(self, verts64, faces, N):
         """keep mask [F] (uint8) of meshudf.py:356-379."""
         verts64 = verts64.to(self.device, torch.float64).contiguous()
