@@ -16,6 +16,8 @@ Prints ONE JSON line (rank 0).
 import argparse
 import json
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before the CUDA context exists (see surfd_b200/__init__.py)
 import subprocess
 import sys
 import tempfile

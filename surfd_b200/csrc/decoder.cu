@@ -774,7 +774,7 @@ extern "C" int surfd_dec_debug_layer(surfd_decoder* d, const float* A_dev, int M
   SURFD_REQUIRE(M >= 1 && blk >= 0 && blk < NBLK && (mode == 0 || mode == 1), "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   Epilogue e{};
-  e.ld = HID; e.bias = d->b0(blk); e.act = out_dev; e.s2 = d->s(2 * blk + 1); e.t2 = d->t(2 * blk + 1); e.round_act = 1;
+  e.ld = HID; e.bias = d->b0(blk); e.act = out_dev; e.s2 = d->s(2 * blk + 1); e.t2 = d->t(2 * blk + 1); e.round_act = 0;
   if (mode == 0) return launch_gemm(A_dev, HID, d->W0r(blk), HID, M, HID, HID, e, st);
   return launch_gemm_tc(A_dev, d->W0r(blk), M, e, d->err.as<int>(), d->num_sms, st);
 }

@@ -118,6 +118,10 @@ extern "C" int surfd_mc_create(surfd_mc** out) {
   if (e != cudaSuccess) { m->comp.destroy(); delete m; return set_error(-(int)e, cudaGetErrorString(e), __FILE__, __LINE__); }
   st = m->grid_dev.reserve(sizeof(surfd_mccore::Grid));
   if (st) { surfd_mc_destroy(m); return st; }
+  // The replay is a single long-running warp that shares the GPU with the decoder's persistent tcgen05 kernel (one 215 KB
+  // CTA per SM).  An SM can only host both if they agree on the L1/shared split, so ask for the same max-shared carve-out;
+  // otherwise every SM holding a replay is lost to the GEMM and its 148-CTA grid needs a second wave (measured ~2x).
+  cudaFuncSetAttribute(replay_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   *out = m;
   return 0;
 }

@@ -95,7 +95,7 @@ struct ConvArgs {
 
 constexpr int CT = 32;        // tile edge
 constexpr int CTP = CT + 4;   // padded row (floats)
-constexpr int KSPLIT = 8;     // CTAs per cluster: the K reduction is split over a thread-block cluster
+constexpr int KSPLIT = 8;     // max CTAs per cluster: the K reduction is split over a thread-block cluster (1, 2, 4 or 8)
 
 // One output tile (32 tokens x 32 channels) is owned by a cluster of KSPLIT CTAs.  K chunks (32 input channels of one
 // tap of one segment) are dealt round-robin to the 8 x 8 = 64 warps of the cluster, so even the deepest layers
@@ -141,7 +141,8 @@ conv_gemm_kernel(ConvArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  const int my_slot = warp * KSPLIT + crank;   // chunk c belongs to slot c % 64; consecutive chunks go to different CTAs
+  const int ks = (int)cluster.num_blocks();    // K split of this launch: 1, 2, 4 or 8 CTAs per output tile
+  const int my_slot = warp * ks + crank;       // chunk c belongs to slot c % (8*ks); consecutive chunks go to different CTAs
   int chunk = 0;
   for (int s = 0; s < a.nseg; ++s) {
     const Seg sg = a.seg[s];
@@ -155,7 +156,7 @@ conv_gemm_kernel(ConvArgs a) {
       const float* arow = sg.A + ((size_t)rb * sg.T_in + (ok ? st : 0)) * sg.Cin;
       const float* wrow = sg.W + ((size_t)tap * a.N + n0 + lane) * sg.Cin;
       for (int c = 0; c < cpt; ++c, ++chunk) {
-        if ((chunk & (8 * KSPLIT - 1)) != my_slot) continue;
+        if ((chunk & (8 * ks - 1)) != my_slot) continue;
         const int ci0 = c * CT;
         float4 av[8], wv[8];
 #pragma unroll
@@ -256,22 +257,24 @@ conv_gemm_kernel(ConvArgs a) {
       part[r * CT + c0 + j] = sum;
     }
   }
-  // (2) cross-CTA reduction over distributed shared memory: CTA `crank` finishes rows 4*crank .. 4*crank+3
+  // (2) cross-CTA reduction over distributed shared memory: CTA `crank` finishes its 1/ks share of the 32x32 tile
   cluster.sync();
-  if (threadIdx.x < 128) {
-    const int r = 4 * crank + (threadIdx.x >> 5), col = threadIdx.x & 31;
-    float v = 0.f;
-#pragma unroll
-    for (int j = 0; j < KSPLIT; ++j) v += cluster.map_shared_rank(part, j)[r * CT + col];
-    const int m = m0 + r;
-    if (m < M) {
-      const int n = n0 + col;
-      const int b = m / a.T_out;
-      v += a.bias[n];
-      if (a.emb) v += a.emb[(size_t)b * a.emb_ld + n];
-      const size_t o = (size_t)m * a.N + n;
-      if (a.residual) v += a.residual[o];
-      a.out[o] = v;
+  {
+    const int per = CT * CT / ks;
+    for (int idx = crank * per + threadIdx.x; idx < (crank + 1) * per; idx += 256) {
+      const int r = idx >> 5, col = idx & 31;
+      float v = 0.f;
+      for (int j = 0; j < ks; ++j) v += cluster.map_shared_rank(part, j)[idx];
+      const int m = m0 + r;
+      if (m < M) {
+        const int n = n0 + col;
+        const int b = m / a.T_out;
+        v += a.bias[n];
+        if (a.emb) v += a.emb[(size_t)b * a.emb_ld + n];
+        const size_t o = (size_t)m * a.N + n;
+        if (a.residual) v += a.residual[o];
+        a.out[o] = v;
+      }
     }
   }
   cluster.sync();   // keep this CTA's shared memory alive until every peer has read it
@@ -646,14 +649,21 @@ static int unet_run(surfd_unet* u, Lane& ln, int B, const float* x, const int64_
         a.emb = r[20] >= 0 ? ln.emb_all.as<float>() + r[20] : nullptr;
         a.emb_ld = u->emb_cols;
         a.residual = r[21] >= 0 ? ln.buf(r[21]) : nullptr;
+        // K split: enough CTAs to cover the SMs, but at least ~2 chunks of work per warp (8 warps per CTA)
+        int chunks = 0;
+        for (int s = 0; s < a.nseg; ++s) chunks += a.seg[s].taps * (a.seg[s].Cin / CT);
+        // (decided from the per-sample tile count so the fp32 summation order -- and the result -- does not depend on B)
+        const int tiles = (a.N / CT) * (int)cdiv((int64_t)a.T_out, CT);
+        int ksplit = 1;
+        while (ksplit < KSPLIT && tiles * ksplit < 148 && chunks >= 16 * (ksplit * 2)) ksplit *= 2;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(a.N / CT), (unsigned)cdiv((int64_t)B * a.T_out, CT), KSPLIT);
+        cfg.gridDim = dim3((unsigned)(a.N / CT), (unsigned)cdiv((int64_t)B * a.T_out, CT), (unsigned)ksplit);
         cfg.blockDim = dim3(256);
         cfg.dynamicSmemBytes = CONV_SMEM;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = KSPLIT;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)ksplit;
         cfg.attrs = attr; cfg.numAttrs = 1;
         if (u->precision == 0) SURFD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<0>, a));
         else if (u->precision == 1) SURFD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<1>, a));

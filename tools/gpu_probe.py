@@ -2,6 +2,7 @@
 """Stage timings on the GPU box (not the benchmark of record): decoder throughput, lattice, marching cubes, sampler.
 Writes gpurun_out/probe.json."""
 import json, os, sys, time
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import torch
 sys.path.insert(0, ".")
 from surfd_b200 import synth, _lib, unet as U

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Host wall-clock + device-event breakdown of SurfDPipeline.extract() per call site (diagnostics, not a benchmark)."""
 import json, os, sys, time
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import torch
 sys.path.insert(0, ".")
 from surfd_b200 import synth
