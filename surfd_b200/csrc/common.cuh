@@ -78,7 +78,8 @@ struct DevBuf {
 struct Compactor {
   DevBuf block_counts;   // int32 per block (+1)
   int64_t* d_total = nullptr;   // device scalar
-  int64_t* h_total = nullptr;   // pinned host scalar
+  int64_t* h_total = nullptr;   // mapped pinned host scalar (written by the scan kernel)
+  int64_t* h_total_dev = nullptr;   // its device-side alias
   int init();
   void destroy();
   // count(): per-block popcounts + exclusive offsets + total (device scalar d_total).

@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(kThreads) popc_blocks_kernel(const uint32_t* _
 }
 
 // single block: exclusive scan of block_counts[0..nb) in place; total -> *total
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(int32_t* __restrict__ counts, int nb, int64_t* __restrict__ total) {
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(int32_t* __restrict__ counts, int nb, int64_t* __restrict__ total,
+                                                           int64_t* __restrict__ total_host) {
   __shared__ int64_t part[1024];
   const int t = threadIdx.x;
   const int per = (nb + 1023) / 1024;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(int32_t* __restrict__
     counts[i] = (int32_t)run;
     run += c;
   }
-  if (t == 1023) *total = part[1023];
+  if (t == 1023) { *total = part[1023]; *total_host = part[1023]; }
 }
 
 __global__ void __launch_bounds__(kThreads) scatter_bits_kernel(const uint32_t* __restrict__ bits, int64_t n_words,
@@ -97,7 +98,11 @@ __global__ void __launch_bounds__(kThreads) scatter_bits_kernel(const uint32_t* 
 
 int Compactor::init() {
   SURFD_CUDA(cudaMalloc(&d_total, sizeof(int64_t)));
-  SURFD_CUDA(cudaMallocHost(&h_total, sizeof(int64_t)));
+  // The host reads the total from mapped pinned memory the scan kernel writes directly: no device->host copy is queued, so
+  // the read-back cannot sit behind another stream's pending copy in a copy-engine queue.
+  SURFD_CUDA(cudaHostAlloc(&h_total, sizeof(int64_t), cudaHostAllocMapped));
+  SURFD_CUDA(cudaHostGetDevicePointer(&h_total_dev, h_total, 0));
+  *h_total = 0;
   return 0;
 }
 
@@ -114,11 +119,13 @@ int Compactor::count(const uint32_t* bits, int64_t n_words, cudaStream_t st) {
   SURFD_TRY(block_counts.reserve((size_t)(nb + 1) * sizeof(int32_t)));
   if (nb == 0) {
     SURFD_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int64_t), st));
+    SURFD_CUDA(cudaStreamSynchronize(st));
+    *h_total = 0;
     return 0;
   }
   popc_blocks_kernel<<<(unsigned)nb, kThreads, 0, st>>>(bits, n_words, block_counts.as<int32_t>());
   SURFD_CHECK_LAUNCH();
-  scan_blocks_kernel<<<1, 1024, 0, st>>>(block_counts.as<int32_t>(), (int)nb, d_total);
+  scan_blocks_kernel<<<1, 1024, 0, st>>>(block_counts.as<int32_t>(), (int)nb, d_total, h_total_dev);
   SURFD_CHECK_LAUNCH();
   return 0;
 }
@@ -132,9 +139,8 @@ int Compactor::scatter(const uint32_t* bits, int64_t n_words, int32_t* out_list,
 }
 
 int Compactor::read_total(int64_t* total, cudaStream_t st) {
-  SURFD_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   SURFD_CUDA(cudaStreamSynchronize(st));
-  *total = *h_total;
+  *total = *reinterpret_cast<volatile int64_t*>(h_total);
   return 0;
 }
 

@@ -76,7 +76,8 @@ classify_kernel(const float* __restrict__ im, int N, float avg_t, float max_t, u
 // One warp per shape: all 32 lanes run replay_w() on a private copy of the bookkeeping (identical control flow, same-value
 // stores) and split the neighbourhood fetch / edge votes of each visit (mc_core.h, "warp-cooperative variant").
 // n_cand comes from the device-side compaction total, so the host never has to read it before the launch.
-__global__ void __launch_bounds__(32) replay_kernel(surfd_mccore::Grid* gp, const int64_t* __restrict__ n_cand_dev, int64_t cap_cand) {
+__global__ void __launch_bounds__(32) replay_kernel(surfd_mccore::Grid* gp, surfd_mccore::Grid* result_host,
+                                                    const int64_t* __restrict__ n_cand_dev, int64_t cap_cand) {
   __shared__ surfd_mccore::CubeCache cc;
   surfd_mccore::Grid g = *gp;
   const int64_t n = *n_cand_dev;
@@ -89,7 +90,8 @@ __global__ void __launch_bounds__(32) replay_kernel(surfd_mccore::Grid* gp, cons
     if (n > cap_cand) g.status = surfd_mccore::MC_CAPACITY;   // candidate list truncated: caller retries with more room
   }
   __syncwarp();
-  if (threadIdx.x == 0) *gp = g;
+  // results go straight to mapped pinned host memory: no device->host copy has to be queued behind this long kernel
+  if (threadIdx.x == 0) { *gp = g; *result_host = g; }
 }
 
 }  // namespace surfd
@@ -98,7 +100,8 @@ using namespace surfd;
 
 struct surfd_mc {
   DevBuf bits, list, sgn, flg, face_layer, verts, faces, queues, grid_dev;
-  surfd_mccore::Grid* grid_host = nullptr;   // pinned: results land here
+  surfd_mccore::Grid* grid_host = nullptr;   // mapped pinned: the kernel writes the results here
+  surfd_mccore::Grid* grid_host_dev = nullptr;
   surfd_mccore::Grid* grid_stage = nullptr;  // pinned: launch parameters
   Compactor comp;
   int64_t n_v = 0, n_f3 = 0;
@@ -113,7 +116,8 @@ extern "C" int surfd_mc_create(surfd_mc** out) {
   surfd_mc* m = new surfd_mc();
   int st = m->comp.init();
   if (st) { delete m; return st; }
-  cudaError_t e = cudaMallocHost(&m->grid_host, sizeof(surfd_mccore::Grid));
+  cudaError_t e = cudaHostAlloc(&m->grid_host, sizeof(surfd_mccore::Grid), cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer(&m->grid_host_dev, m->grid_host, 0);
   if (e == cudaSuccess) e = cudaMallocHost(&m->grid_stage, sizeof(surfd_mccore::Grid));
   if (e != cudaSuccess) { m->comp.destroy(); delete m; return set_error(-(int)e, cudaGetErrorString(e), __FILE__, __LINE__); }
   st = m->grid_dev.reserve(sizeof(surfd_mccore::Grid));
@@ -210,9 +214,8 @@ extern "C" int surfd_mc_launch(surfd_mc* m, const float* udf_dev, const float* g
   // the launch struct is staged through a second pinned copy so grid_host can receive the results
   memcpy(m->grid_stage, &g, sizeof(g));
   SURFD_CUDA(cudaMemcpyAsync(m->grid_dev.p, m->grid_stage, sizeof(g), cudaMemcpyHostToDevice, st));
-  replay_kernel<<<1, 32, 0, st>>>(m->grid_dev.as<surfd_mccore::Grid>(), m->comp.d_total, cap);
+  replay_kernel<<<1, 32, 0, st>>>(m->grid_dev.as<surfd_mccore::Grid>(), m->grid_host_dev, m->comp.d_total, cap);
   SURFD_CHECK_LAUNCH();
-  SURFD_CUDA(cudaMemcpyAsync(&g, m->grid_dev.p, sizeof(g), cudaMemcpyDeviceToHost, st));
   m->pending_stream = st;
   m->pending = true;
   return 0;
@@ -224,7 +227,8 @@ extern "C" int surfd_mc_finish(surfd_mc* m, int64_t* n_v, int64_t* n_f, int64_t*
   SURFD_REQUIRE(m->pending, "surfd_mc_finish without surfd_mc_launch");
   SURFD_CUDA(cudaStreamSynchronize(m->pending_stream));
   m->pending = false;
-  const surfd_mccore::Grid& g = *m->grid_host;
+  surfd_mccore::Grid g;
+  memcpy(&g, m->grid_host, sizeof(g));   // written by the kernel into mapped pinned memory; the stream sync above orders it
   m->n_v = g.n_v; m->n_f3 = g.n_f3;
   *n_v = g.n_v; *n_f = g.n_f3 / 3;
   if (stats) {
