@@ -26,6 +26,13 @@ namespace cg = cooperative_groups;
 
 namespace surfd {
 
+// Programmatic dependent launch: every kernel of the step first lets its successor start launching (its CTAs become
+// resident and park at their own wait) and then waits for its predecessor to finish and flush.  This hides the
+// kernel-to-kernel launch latency of the ~170-node step graph.  Both instructions are no-ops for ordinary launches.
+#define PDL_PROLOGUE()                                            \
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  asm volatile("griddepcontrol.wait;" ::: "memory")
+
 enum { OP_GN = 1, OP_CONV = 2, OP_ATTN = 3, OP_INCONV = 4, OP_OUTCONV = 5 };
 constexpr int REC = 32;
 constexpr int EMB = 896;
@@ -38,6 +45,7 @@ constexpr int CTX = 512;
 __global__ void __launch_bounds__(128)
 gn_kernel(const float* __restrict__ in1, int C1, const float* __restrict__ in2, int C2, int T, const float* __restrict__ gamma,
           const float* __restrict__ beta, int silu, float* __restrict__ out, float* __restrict__ raw) {
+  PDL_PROLOGUE();
   const int C = C1 + C2;
   const int cg = C / 32;
   const int b = blockIdx.x >> 5, g = blockIdx.x & 31;
@@ -118,6 +126,7 @@ __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, const uint
 template <int MODE>
 __global__ void __launch_bounds__(256)
 conv_gemm_kernel(ConvArgs a) {
+  PDL_PROLOGUE();
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
@@ -305,6 +314,7 @@ conv_gemm_kernel(ConvArgs a) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 attn_kernel(const float* __restrict__ qkv, int C, int T, int heads, float scale, float* __restrict__ out) {
+  PDL_PROLOGUE();
   extern __shared__ __align__(16) float sm[];
   const int ch = C / heads;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -348,6 +358,7 @@ attn_kernel(const float* __restrict__ qkv, int C, int T, int heads, float scale,
 // first conv (1 -> 224, k=3, pad 1) and last conv (224 -> 1)
 __global__ void inconv_kernel(const float* __restrict__ x, int B, int L, int N, const float* __restrict__ W /*[3][N][1]*/,
                               const float* __restrict__ bias, float* __restrict__ out) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * L * N) return;
   const int n = i % N, l = (i / N) % L, b = i / (N * L);
@@ -361,6 +372,7 @@ __global__ void inconv_kernel(const float* __restrict__ x, int B, int L, int N, 
 
 __global__ void outconv_kernel(const float* __restrict__ a, int B, int L, int C, const float* __restrict__ W /*[3][1][C]*/,
                                const float* __restrict__ bias, float* __restrict__ out) {
+  PDL_PROLOGUE();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * L) return;
   const int l = warp % L, b = warp / L;
@@ -380,6 +392,7 @@ __global__ void outconv_kernel(const float* __restrict__ a, int B, int L, int C,
 // ---- embedding path ----------------------------------------------------------------------------
 // timestep_embedding: [cos(t*f_k) | sin(t*f_k)], f_k = exp(-ln(1e4) * k / 112) in fp32 (utils/ldm_utils.py:165-185)
 __global__ void temb_kernel(const int64_t* __restrict__ t, int B, float* __restrict__ out) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * (TCH / 2)) return;
   const int k = i % (TCH / 2), b = i / (TCH / 2);
@@ -394,6 +407,7 @@ __global__ void temb_kernel(const int64_t* __restrict__ t, int B, float* __restr
 __global__ void __launch_bounds__(256)
 linear_rows_kernel(const float* __restrict__ in, int M, int K, const float* __restrict__ W, const float* __restrict__ bias, int N,
                    int in_silu, int out_silu, int accumulate, float* __restrict__ out) {
+  PDL_PROLOGUE();
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int mb = blockIdx.y * 8;
@@ -436,6 +450,7 @@ linear_rows_kernel(const float* __restrict__ in, int M, int K, const float* __re
 }
 
 __global__ void label_add_kernel(const int64_t* __restrict__ y, int B, const float* __restrict__ table, float* __restrict__ emb) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * EMB) return;
   const int b = i / EMB, c = i % EMB;
@@ -449,6 +464,7 @@ struct StepState {
 };
 
 __global__ void step_begin_kernel(const StepState* __restrict__ st, const int64_t* __restrict__ tmap, int B, int64_t* __restrict__ t_cur) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   const int idx = st->n_steps - 1 - st->iter;
@@ -460,6 +476,7 @@ __global__ void step_begin_kernel(const StepState* __restrict__ st, const int64_
 __global__ void ddpm_update_kernel(StepState* __restrict__ st, const float* __restrict__ coef, const float* __restrict__ x0a,
                                    const float* __restrict__ x0b, float scale, const float* __restrict__ noise, int64_t noise_row_stride, int n,
                                    float* __restrict__ x) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int iter = st->iter, ns = st->n_steps;
   const int idx = ns - 1 - iter;
@@ -474,11 +491,35 @@ __global__ void ddpm_update_kernel(StepState* __restrict__ st, const float* __re
   }
 }
 
-__global__ void step_advance_kernel(StepState* st) { st->iter += 1; }
+__global__ void step_advance_kernel(StepState* st) {
+  PDL_PROLOGUE();
+  st->iter += 1;
+}
 
 }  // namespace surfd
 
 using namespace surfd;
+
+// cudaLaunchKernelEx with an optional cluster dimension (z) and the programmatic-dependent-launch attribute
+#define UNET_LAUNCH(pdl, kernel, grid, block, smem, st, cluster_z, ...)                                   \
+  do {                                                                                                    \
+    cudaLaunchConfig_t _cfg{};                                                                            \
+    _cfg.gridDim = (grid); _cfg.blockDim = (block); _cfg.dynamicSmemBytes = (smem); _cfg.stream = (st);   \
+    cudaLaunchAttribute _attr[2];                                                                         \
+    unsigned _na = 0;                                                                                     \
+    if ((cluster_z) > 0) {                                                                                \
+      _attr[_na].id = cudaLaunchAttributeClusterDimension;                                                \
+      _attr[_na].val.clusterDim.x = 1; _attr[_na].val.clusterDim.y = 1;                                   \
+      _attr[_na].val.clusterDim.z = (unsigned)(cluster_z); ++_na;                                         \
+    }                                                                                                     \
+    if (pdl) {                                                                                            \
+      _attr[_na].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                 \
+      _attr[_na].val.programmaticStreamSerializationAllowed = 1; ++_na;                                   \
+    }                                                                                                     \
+    _cfg.attrs = _attr; _cfg.numAttrs = _na;                                                              \
+    SURFD_CUDA(cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__));                                           \
+    SURFD_CHECK_LAUNCH();                                                                                 \
+  } while (0)
 
 // per-warp A/W staging (8 warps x 2 x 32 x 36 floats) is reused for the 8 x 32 x 33 warp partials; + the 32x32 CTA partial
 static constexpr int CONV_SMEM = (8 * 2 * CT * CTP + CT * CT) * (int)sizeof(float);
@@ -516,6 +557,7 @@ struct Lane {
 
 struct surfd_unet {
   int L = 0, max_batch = 0;
+  bool pdl = true;     // programmatic dependent launch between the step's kernels (falls back to false if capture rejects it)
   int precision = 1;   // token GEMMs: 0 fp32 FFMA, 1 3xTF32 mma.sync (fp32-class accuracy, default), 2 single-pass TF32
   DevBuf weights;
   std::vector<int64_t> hdr, buf_sizes;
@@ -622,39 +664,31 @@ static int unet_run(surfd_unet* u, Lane& ln, int B, const float* x, const int64_
                     cudaStream_t st) {
   const auto& h = u->hdr;
   // ---- embedding ----
-  temb_kernel<<<(unsigned)cdiv((int64_t)B * (TCH / 2), 128), 128, 0, st>>>(t, B, ln.temb.as<float>());
-  SURFD_CHECK_LAUNCH();
+  UNET_LAUNCH(u->pdl, temb_kernel, dim3((unsigned)cdiv((int64_t)B * (TCH / 2), 128)), dim3(128), 0, st, 0, t, B, ln.temb.as<float>());
   const dim3 g1((unsigned)cdiv(EMB, 8), (unsigned)cdiv(B, 8));
-  linear_rows_kernel<<<g1, 256, 0, st>>>(ln.temb.as<float>(), B, TCH, u->w(h[5]), u->w(h[6]), EMB, 0, 1, 0, ln.e1.as<float>());
-  SURFD_CHECK_LAUNCH();
-  linear_rows_kernel<<<g1, 256, 0, st>>>(ln.e1.as<float>(), B, EMB, u->w(h[7]), u->w(h[8]), EMB, 0, 0, 0, ln.emb.as<float>());
-  SURFD_CHECK_LAUNCH();
+  UNET_LAUNCH(u->pdl, linear_rows_kernel, dim3(g1), dim3(256), 0, st, 0, ln.temb.as<float>(), B, TCH, u->w(h[5]), u->w(h[6]), EMB, 0, 1, 0, ln.e1.as<float>());
+  UNET_LAUNCH(u->pdl, linear_rows_kernel, dim3(g1), dim3(256), 0, st, 0, ln.e1.as<float>(), B, EMB, u->w(h[7]), u->w(h[8]), EMB, 0, 0, 0, ln.emb.as<float>());
   if (lab) {
     SURFD_REQUIRE(h[11] >= 0, "labels given but the checkpoint has no label_emb");
-    label_add_kernel<<<(unsigned)cdiv((int64_t)B * EMB, 256), 256, 0, st>>>(lab, B, u->w(h[11]), ln.emb.as<float>());
-    SURFD_CHECK_LAUNCH();
+    UNET_LAUNCH(u->pdl, label_add_kernel, dim3((unsigned)cdiv((int64_t)B * EMB, 256)), dim3(256), 0, st, 0, lab, B, u->w(h[11]), ln.emb.as<float>());
   }
   if (ctx) {
-    linear_rows_kernel<<<g1, 256, 0, st>>>(ctx, B, CTX, u->w(h[9]), u->w(h[10]), EMB, 0, 0, 1, ln.emb.as<float>());
-    SURFD_CHECK_LAUNCH();
+    UNET_LAUNCH(u->pdl, linear_rows_kernel, dim3(g1), dim3(256), 0, st, 0, ctx, B, CTX, u->w(h[9]), u->w(h[10]), EMB, 0, 0, 1, ln.emb.as<float>());
   }
   const dim3 g2((unsigned)cdiv(u->emb_cols, 8), (unsigned)cdiv(B, 8));
-  linear_rows_kernel<<<g2, 256, 0, st>>>(ln.emb.as<float>(), B, EMB, u->w(h[3]), u->w(h[4]), u->emb_cols, 1, 0, 0, ln.emb_all.as<float>());
-  SURFD_CHECK_LAUNCH();
+  UNET_LAUNCH(u->pdl, linear_rows_kernel, dim3(g2), dim3(256), 0, st, 0, ln.emb.as<float>(), B, EMB, u->w(h[3]), u->w(h[4]), u->emb_cols, 1, 0, 0, ln.emb_all.as<float>());
   // ---- program ----
   for (const auto& r : u->prog) {
     switch (r[0]) {
       case OP_INCONV: {
         const int N = (int)r[2], L = (int)r[3];
-        inconv_kernel<<<(unsigned)cdiv((int64_t)B * L * N, 256), 256, 0, st>>>(x, B, L, N, u->w(r[4]), u->w(r[5]), ln.buf(r[1]));
-        SURFD_CHECK_LAUNCH();
+        UNET_LAUNCH(u->pdl, inconv_kernel, dim3((unsigned)cdiv((int64_t)B * L * N, 256)), dim3(256), 0, st, 0, x, B, L, N, u->w(r[4]), u->w(r[5]), ln.buf(r[1]));
         break;
       }
       case OP_GN: {
         const int C1 = (int)r[2], C2 = (int)r[4], T = (int)r[5];
-        gn_kernel<<<(unsigned)(B * 32), 128, 0, st>>>(ln.buf(r[1]), C1, r[3] >= 0 ? ln.buf(r[3]) : nullptr, C2, T, u->w(r[9]), u->w(r[10]),
+        UNET_LAUNCH(u->pdl, gn_kernel, dim3((unsigned)(B * 32)), dim3(128), 0, st, 0, ln.buf(r[1]), C1, r[3] >= 0 ? ln.buf(r[3]) : nullptr, C2, T, u->w(r[9]), u->w(r[10]),
                                                       (int)r[8], ln.buf(r[6]), r[7] >= 0 ? ln.buf(r[7]) : nullptr);
-        SURFD_CHECK_LAUNCH();
         break;
       }
       case OP_CONV: {
@@ -676,19 +710,10 @@ static int unet_run(surfd_unet* u, Lane& ln, int B, const float* x, const int64_
         const int tiles = (a.N / CT) * (int)cdiv((int64_t)a.T_out, CT);
         int ksplit = 1;
         while (ksplit < KSPLIT && tiles * ksplit < 148 && chunks >= 16 * (ksplit * 2)) ksplit *= 2;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(a.N / CT), (unsigned)cdiv((int64_t)B * a.T_out, CT), (unsigned)ksplit);
-        cfg.blockDim = dim3(256);
-        cfg.dynamicSmemBytes = CONV_SMEM;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)ksplit;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        if (u->precision == 0) SURFD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<0>, a));
-        else if (u->precision == 1) SURFD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<1>, a));
-        else SURFD_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<2>, a));
-        SURFD_CHECK_LAUNCH();
+        const dim3 cgrid((unsigned)(a.N / CT), (unsigned)cdiv((int64_t)B * a.T_out, CT), (unsigned)ksplit);
+        if (u->precision == 0) UNET_LAUNCH(u->pdl, conv_gemm_kernel<0>, cgrid, dim3(256), CONV_SMEM, st, ksplit, a);
+        else if (u->precision == 1) UNET_LAUNCH(u->pdl, conv_gemm_kernel<1>, cgrid, dim3(256), CONV_SMEM, st, ksplit, a);
+        else UNET_LAUNCH(u->pdl, conv_gemm_kernel<2>, cgrid, dim3(256), CONV_SMEM, st, ksplit, a);
         break;
       }
       case OP_ATTN: {
@@ -696,14 +721,12 @@ static int unet_run(surfd_unet* u, Lane& ln, int B, const float* x, const int64_
         const int ch = C / heads;
         const float scale = (float)(1.0 / sqrt(sqrt((double)ch)));
         const size_t smem = ((size_t)3 * T * ch + (size_t)T * (T + 1)) * sizeof(float);
-        attn_kernel<<<(unsigned)(B * heads), 128, smem, st>>>(ln.buf(r[1]), C, T, heads, scale, ln.buf(r[4]));
-        SURFD_CHECK_LAUNCH();
+        UNET_LAUNCH(u->pdl, attn_kernel, dim3((unsigned)(B * heads)), dim3(128), smem, st, 0, ln.buf(r[1]), C, T, heads, scale, ln.buf(r[4]));
         break;
       }
       case OP_OUTCONV: {
         const int C = (int)r[2], T = (int)r[3];
-        outconv_kernel<<<(unsigned)cdiv((int64_t)B * T * 32, 256), 256, 0, st>>>(ln.buf(r[1]), B, T, C, u->w(r[4]), u->w(r[5]), x0);
-        SURFD_CHECK_LAUNCH();
+        UNET_LAUNCH(u->pdl, outconv_kernel, dim3((unsigned)cdiv((int64_t)B * T * 32, 256)), dim3(256), 0, st, 0, ln.buf(r[1]), B, T, C, u->w(r[4]), u->w(r[5]), x0);
         break;
       }
       default:
@@ -723,17 +746,14 @@ extern "C" int surfd_unet_forward(surfd_unet* u, int B, const float* x_dev, cons
 static int record_step(surfd_unet* u, Lane& ln, int B, const int64_t* tmap, const float* coef, const float* noise, int64_t noise_stride,
                        const float* ctx, const int64_t* lab, float guidance, cudaStream_t st) {
   StepState* ss = ln.state.as<StepState>();
-  step_begin_kernel<<<(unsigned)cdiv(B, 128), 128, 0, st>>>(ss, tmap, B, ln.t_cur.as<int64_t>());
-  SURFD_CHECK_LAUNCH();
+  UNET_LAUNCH(u->pdl, step_begin_kernel, dim3((unsigned)cdiv(B, 128)), dim3(128), 0, st, 0, ss, tmap, B, ln.t_cur.as<int64_t>());
   SURFD_TRY(unet_run(u, ln, B, ln.xcur.as<float>(), ln.t_cur.as<int64_t>(), ctx, lab, ln.x0a.as<float>(), st));
   const bool cfg = guidance != 1.0f;
   if (cfg) SURFD_TRY(unet_run(u, ln, B, ln.xcur.as<float>(), ln.t_cur.as<int64_t>(), ctx, lab, ln.x0b.as<float>(), st));
   const int n = B * u->L;
-  ddpm_update_kernel<<<(unsigned)cdiv(n, 128), 128, 0, st>>>(ss, coef, ln.x0a.as<float>(), cfg ? ln.x0b.as<float>() : nullptr, guidance, noise,
+  UNET_LAUNCH(u->pdl, ddpm_update_kernel, dim3((unsigned)cdiv(n, 128)), dim3(128), 0, st, 0, ss, coef, ln.x0a.as<float>(), cfg ? ln.x0b.as<float>() : nullptr, guidance, noise,
                                                              noise_stride, n, ln.xcur.as<float>());
-  SURFD_CHECK_LAUNCH();
-  step_advance_kernel<<<1, 1, 0, st>>>(ss);
-  SURFD_CHECK_LAUNCH();
+  UNET_LAUNCH(u->pdl, step_advance_kernel, dim3(1), dim3(1), 0, st, 0, ss);
   return 0;
 }
 
@@ -763,23 +783,30 @@ extern "C" int surfd_sample(surfd_unet* u, int B, int n_steps, const int64_t* tm
                        ln.graph_coef == coef_dev && ln.graph_noise == noise && ln.graph_stride == stride && ln.graph_guidance == guidance;
     if (!reuse) {
       if (ln.graph_exec) { cudaGraphExecDestroy(ln.graph_exec); ln.graph_exec = nullptr; }
-      cudaStream_t cs;
-      SURFD_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      cudaGraph_t graph = nullptr;
-      cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
-      int rc = 0;
-      if (ce == cudaSuccess) {
-        const int64_t launches_before = g_launch_count;
-        rc = record_step(u, ln, b, tmap_dev, coef_dev, noise, stride, ctx, lab, guidance, cs);
-        ln.graph_launches = g_launch_count - launches_before;
-        g_launch_count = launches_before;   // capture is not execution; launches are counted per replay below
-        ce = cudaStreamEndCapture(cs, &graph);
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        cudaStream_t cs;
+        SURFD_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        int rc = 0;
+        if (ce == cudaSuccess) {
+          const int64_t launches_before = g_launch_count;
+          rc = record_step(u, ln, b, tmap_dev, coef_dev, noise, stride, ctx, lab, guidance, cs);
+          ln.graph_launches = g_launch_count - launches_before;
+          g_launch_count = launches_before;   // capture is not execution; launches are counted per replay below
+          cudaError_t ce2 = cudaStreamEndCapture(cs, &graph);
+          if (ce == cudaSuccess) ce = ce2;
+        }
+        if (ce == cudaSuccess && rc == 0) ce = cudaGraphInstantiate(&ln.graph_exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(cs);
+        if (ce == cudaSuccess && rc == 0) break;
+        ln.graph_exec = nullptr;
+        cudaGetLastError();   // clear
+        if (u->pdl && attempt == 0) { u->pdl = false; continue; }   // programmatic edges rejected: capture again without them
+        if (rc) return rc;
+        return set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__);
       }
-      if (ce == cudaSuccess && rc == 0) ce = cudaGraphInstantiate(&ln.graph_exec, graph, 0);
-      if (graph) cudaGraphDestroy(graph);
-      cudaStreamDestroy(cs);
-      if (rc) return rc;
-      if (ce != cudaSuccess) { ln.graph_exec = nullptr; return set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__); }
       ln.graph_B = b; ln.graph_ctx = ctx; ln.graph_lab = lab; ln.graph_tmap = tmap_dev; ln.graph_coef = coef_dev;
       ln.graph_noise = noise; ln.graph_stride = stride; ln.graph_guidance = guidance;
     }
