@@ -51,3 +51,21 @@ for it in range(2):
     run(False, "no-mc  iter%d" % it)
 for it in range(3):
     run(True, "with-mc iter%d" % it)
+
+# --- does a running replay slow an unrelated GEMM? -------------------------------------------------------------
+dec.set_latent(lats[0])
+udf, grads, counts = dec.lattice(N, True)
+udf.clamp_(min=0)
+torch.cuda.synchronize()
+for prec_mode in (1, 0):
+    dec.set_precision(prec_mode)
+    ms_idle, m = dec.time_layer(50)
+    for nmc in (1, 8):
+        for k in range(nmc):
+            mcs[k].launch(udf, grads, streams[k])
+        time.sleep(0.05)
+        ms_busy, _ = dec.time_layer(50)
+        for k in range(nmc):
+            mcs[k].finish()
+        print("precision %d: layer GEMM %.4f ms idle, %.4f ms with %d replays running" % (prec_mode, ms_idle, ms_busy, nmc))
+dec.set_precision(prec)
