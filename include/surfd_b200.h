@@ -49,6 +49,9 @@ int surfd_dec_set_latent(surfd_decoder* d, const float* lat_dev, void* stream);
 
 /* precision: 0 = fp32 FFMA (parity mode), 1 = TF32 tcgen05 tensor cores (fast mode) */
 int surfd_dec_set_precision(surfd_decoder* d, int mode);
+/* grid size of the persistent tcgen05 GEMM (0 = every SM): leave SMs to concurrently running marching-cubes replays */
+int surfd_dec_set_sm_budget(surfd_decoder* d, int n_sms);
+int surfd_dec_num_sms(surfd_decoder* d);
 
 /* measurement hooks (bench.py): points per internal chunk; average duration of the dominant kernel (one 512x512
  * layer GEMM over M <= chunk points) timed with CUDA events on `stream`, `iters` back-to-back launches. */

@@ -24,6 +24,8 @@ PROTOTYPES = {
     "surfd_dec_packed_floats": (ctypes.c_size_t, [ctypes.c_int]),
     "surfd_dec_set_latent": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "surfd_dec_set_precision": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "surfd_dec_set_sm_budget": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "surfd_dec_num_sms": (ctypes.c_int, [c_vp]),
     "surfd_dec_chunk_points": (ctypes.c_int, [c_vp]),
     "surfd_dec_time_layer": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp]),
     "surfd_dec_debug_layer": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),

@@ -408,6 +408,7 @@ struct surfd_decoder {
   DevBuf wR;         // TF32-rounded (rna) copies for the tensor-core path: 5x{W0, W1}, then 5x{W0T, W1T}
   DevBuf err;        // int error flag written by the tcgen05 kernel's bounded waits
   int num_sms = 148;
+  int sm_budget = 0;     // persistent-kernel grid size (0 = all SMs); lower it while other long-running kernels hold SMs
   DevBuf fold;       // s[11][512], t[11][512]
   DevBuf acts;       // 11 x [chunk][512]
   DevBuf net, dnet, dh, enc, de, pts, dudf, udf_tmp;
@@ -546,8 +547,20 @@ extern "C" int surfd_dec_set_precision(surfd_decoder* d, int mode) {
 
 static int gemm512(surfd_decoder* d, const float* A, const float* W, const float* Wr, int M, Epilogue e, cudaStream_t st) {
   if (d->precision == 0) return launch_gemm(A, HID, W, HID, M, HID, HID, e, st);
-  return launch_gemm_tc(A, Wr, M, e, d->err.as<int>(), d->num_sms, st);
+  const int sms = d->sm_budget > 0 && d->sm_budget < d->num_sms ? d->sm_budget : d->num_sms;
+  return launch_gemm_tc(A, Wr, M, e, d->err.as<int>(), sms, st);
 }
+
+// The tcgen05 layer GEMM is persistent: one 215 KB CTA per SM.  An SM that already hosts another long-running kernel (a
+// marching-cubes replay) cannot take such a CTA, and with a static tile schedule one late CTA doubles the kernel time
+// (measured: 0.049 -> 0.086 ms with a single replay resident).  The pipeline therefore budgets the GEMM to
+// num_sms - (#replay streams) CTAs and sizes the point chunk to a whole number of tiles per CTA.
+extern "C" int surfd_dec_set_sm_budget(surfd_decoder* d, int n_sms) {
+  SURFD_REQUIRE(d != nullptr && n_sms >= 0, "bad argument");
+  d->sm_budget = n_sms;
+  return 0;
+}
+extern "C" int surfd_dec_num_sms(surfd_decoder* d) { return d ? d->num_sms : 0; }
 
 extern "C" int surfd_dec_set_latent(surfd_decoder* d, const float* lat_dev, void* stream) {
   SURFD_REQUIRE(d != nullptr && lat_dev != nullptr, "null argument");
@@ -776,7 +789,7 @@ extern "C" int surfd_dec_debug_layer(surfd_decoder* d, const float* A_dev, int M
   Epilogue e{};
   e.ld = HID; e.bias = d->b0(blk); e.act = out_dev; e.s2 = d->s(2 * blk + 1); e.t2 = d->t(2 * blk + 1); e.round_act = 0;
   if (mode == 0) return launch_gemm(A_dev, HID, d->W0r(blk), HID, M, HID, HID, e, st);
-  return launch_gemm_tc(A_dev, d->W0r(blk), M, e, d->err.as<int>(), d->num_sms, st);
+  return launch_gemm_tc(A_dev, d->W0r(blk), M, e, d->err.as<int>(), d->sm_budget > 0 && d->sm_budget < d->num_sms ? d->sm_budget : d->num_sms, st);
 }
 
 extern "C" int surfd_face_filter(surfd_decoder* d, const double* verts64_dev, const int32_t* faces_dev, int64_t n_f, int N,

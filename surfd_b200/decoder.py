@@ -102,6 +102,14 @@ class UdfDecoder:
     def set_precision(self, mode):
         _lib.check(self.lib.surfd_dec_set_precision(self._h, int(mode)))
 
+    def set_sm_budget(self, n_sms):
+        """CTAs of the persistent tensor-core GEMM (0 = all SMs); see surfd_dec_set_sm_budget"""
+        _lib.check(self.lib.surfd_dec_set_sm_budget(self._h, int(n_sms)))
+
+    @property
+    def num_sms(self):
+        return int(self.lib.surfd_dec_num_sms(self._h))
+
     def set_latent(self, lat):
         lat = lat.detach().reshape(-1).to(self.device, torch.float32).contiguous()
         assert lat.numel() == self.latent_dim

@@ -21,7 +21,12 @@ class SurfDPipeline:
         self.L = latent_dim
         self.sampler = U.UNetSampler(mdm_state, latent_dim, cond_mode, num_actions, device=device, max_batch=max_batch,
                                      packed=packed_unet)
-        self.decoder = UdfDecoder(ae_state, latent_dim, device=device, packed=packed_decoder)
+        # leave one SM per concurrent marching-cubes replay to the persistent decoder GEMM's budget and size the point chunk
+        # to whole tiles per CTA: (148 - 8) CTAs x 2 x 128 rows
+        n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        budget = max(1, n_sms - mc_parallel)
+        self.decoder = UdfDecoder(ae_state, latent_dim, device=device, packed=packed_decoder, max_chunk_points=budget * 256)
+        self.decoder.set_sm_budget(budget)
         self.mcs = [MarchingCubes(device) for _ in range(mc_parallel)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(mc_parallel)]
         self.schedule_cache = {}

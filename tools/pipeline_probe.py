@@ -10,8 +10,9 @@ from surfd_b200.meshudf import MarchingCubes, finish_mesh
 
 L, N, B = 32, int(sys.argv[1]) if len(sys.argv) > 1 else 256, 8
 prec = int(os.environ.get("PREC", "1"))
-dec = UdfDecoder(synth.synth_ae_poly(L)["decoder"], L)
+dec = UdfDecoder(synth.synth_ae_poly(L)["decoder"], L, max_chunk_points=(148 - 8) * 256)
 dec.set_precision(prec)
+dec.set_sm_budget(int(os.environ.get("BUDGET", "140")))
 gen = torch.Generator().manual_seed(0)
 lats = torch.randn(B, L, generator=gen).cuda() * 0.7
 mcs = [MarchingCubes() for _ in range(B)]
