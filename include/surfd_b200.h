@@ -93,6 +93,9 @@ int surfd_mc_udf(surfd_mc* m, const float* udf_dev, const float* grad_dev, int N
  * returns counts/status.  SURFD_CAPACITY from _finish means the per-handle buffers were grown: launch again. */
 int surfd_mc_launch(surfd_mc* m, const float* udf_dev, const float* grad_dev, int N, void* stream);
 int surfd_mc_finish(surfd_mc* m, int64_t* n_v, int64_t* n_f, int64_t* stats_host);
+/* Diagnostics: cycle counters of the last finished replay (all zero unless the library was built with -DMC_PROFILE):
+ * total, fetch, sign propagation, tiling selection, emission, visits, window refills, 0. */
+int surfd_mc_profile(surfd_mc* m, int64_t* prof_host /* [8] */);
 int surfd_mc_fetch(surfd_mc* m, float* verts_dev /* [n_v][3] */, int32_t* faces_dev /* [n_f][3] */, void* stream);
 /* classification pass alone (HBM-bound scan, pyx:1157-1158,1215-1218): candidate bitmask words
  * [ceil(N^3/32)] and count; used by the benchmarks / tests. */

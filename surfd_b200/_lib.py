@@ -35,6 +35,7 @@ PROTOTYPES = {
     "surfd_mc_destroy": (None, [c_vp]),
     "surfd_mc_udf": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_vp]),
     "surfd_mc_launch": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, c_vp]),
+    "surfd_mc_profile": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
     "surfd_mc_finish": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "surfd_mc_fetch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "surfd_mc_classify": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, ctypes.POINTER(c_i64), c_vp]),

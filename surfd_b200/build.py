@@ -15,7 +15,8 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
           "-DSURFD_BUILDING", "--expt-relaxed-constexpr"]
 # per-file extra flags
 EXTRA = {
-    "mc.cu": ["-fmad=false"],   # the replay must match the reference's unfused IEEE arithmetic
+    # the replay must match the reference's unfused IEEE arithmetic; SURFD_MC_FLAGS=-DMC_PROFILE adds cycle counters
+    "mc.cu": ["-fmad=false"] + os.environ.get("SURFD_MC_FLAGS", "").split(),
 }
 
 

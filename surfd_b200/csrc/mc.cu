@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(32) replay_kernel(surfd_mccore::Grid* gp, surf
   if (n == 0) {
     g.n_v = 0; g.n_f3 = 0; g.status = surfd_mccore::MC_EMPTY;
   } else {
-    surfd_mccore::replay_w(g, cc);
+    surfd_mccore::replay_w(g, cc, gp);
     if (n > cap_cand) g.status = surfd_mccore::MC_CAPACITY;   // candidate list truncated: caller retries with more room
   }
   __syncwarp();
@@ -244,6 +244,13 @@ extern "C" int surfd_mc_finish(surfd_mc* m, int64_t* n_v, int64_t* n_f, int64_t*
     return set_error(SURFD_CAPACITY, "marching cubes capacity exceeded; call again (buffers were grown)", __FILE__, __LINE__);
   }
   if (g.status == surfd_mccore::MC_QUEUE_OVERFLOW) return set_error(SURFD_QUEUE_OVERFLOW, "marching cubes BFS queue overflow", __FILE__, __LINE__);
+  return 0;
+}
+
+extern "C" int surfd_mc_profile(surfd_mc* m, int64_t* prof) {
+  SURFD_REQUIRE(m && prof, "null argument");
+  SURFD_REQUIRE(!m->pending, "surfd_mc_profile while a launch is pending");
+  for (int i = 0; i < 8; ++i) prof[i] = m->grid_host->prof[i];
   return 0;
 }
 

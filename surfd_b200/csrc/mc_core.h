@@ -103,6 +103,9 @@ struct Grid {
   int status;
   // statistics (diagnostics only)
   int64_t n_seed, n_accept, n_unsure_push, n_nontrivial_push;
+  // cycle counters, filled only by builds with -DMC_PROFILE (device): 0 total, 1 neighbourhood fetch + edge votes,
+  // 2 sign propagation, 3 case/tiling selection, 4 vertices + faces + pushes, 5 number of visits, 6 window refills
+  int64_t prof[8];
 };
 
 struct Cell {
@@ -651,6 +654,11 @@ MC_HD_NOINLINE void replay(Grid& g) {
 //   fall back to visit_cube().  On the host (logic tests) the lane loops run sequentially.
 // =====================================================================================================
 #if defined(__CUDA_ARCH__)
+#define MC_UNROLL _Pragma("unroll")
+#else
+#define MC_UNROLL
+#endif
+#if defined(__CUDA_ARCH__)
 #define MC_LANE_LOOP(l) for (int l = (int)(threadIdx.x & 31), _mc_once = 1; _mc_once; _mc_once = 0)
 #define MC_WARP_SYNC() __syncwarp()
 #else
@@ -666,7 +674,30 @@ struct CubeCache {
   int8_t sgn[64];
   uint8_t flg[64];
   uint8_t vstat[48];   // 0: skipped by the bounds rule, 1: usable, 2: neighbour udf == 0 (needs the extension rule)
+  // look-ahead windows: the next <= 32 entries of the BFS queue / of the raster candidate list, one per lane, with
+  // bit0 = "visited flag already set" (kept coherent by note_done()), bit1 = "is a candidate cube"
+  int32_t qw_cur[32];
+  int32_t sw_cur[32];
+  uint8_t qw_f[32];
+  uint8_t sw_f[32];
+  uint8_t tedge[36];   // edge ids of the selected tiling
 };
+
+#if defined(__CUDA_ARCH__) && defined(MC_PROFILE)
+#define MC_PROF_T(var) const long long var = clock64()
+#define MC_PROF_ADD(slot, t0, t1) g.prof[slot] += (t1) - (t0)
+#define MC_PROF_INC(slot) g.prof[slot] += 1
+#else
+#define MC_PROF_T(var)
+#define MC_PROF_ADD(slot, t0, t1)
+#define MC_PROF_INC(slot)
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define MC_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#else
+#define MC_PREFETCH(p) ((void)(p))
+#endif
 
 MC_HD int64_t facelayer_index_xyz(int64_t nx, int x, int y, int z, int vi) {
   int64_t i = nx * nx * z + nx * y + x;
@@ -690,15 +721,15 @@ MC_HD int64_t facelayer_index_xyz(int64_t nx, int x, int y, int z, int vi) {
 
 #define MC_BLK(bz, by, bx) (((bz) << 4) | ((by) << 2) | (bx))
 
+// check_tiling() on the cached slots.  A vertex index lives in exactly one face_layer slot, and the 13 edge ids of a
+// cube map to 13 distinct slots, so "distinct existing vertex indices" == "distinct edge ids whose slot is filled".
 MC_HD int check_tiling_c(const CubeCache& cc, const Tiling& t, int config) {
-  int seen[36];
-  int n = 0, result = 0;
+  uint32_t seen = 0;
+  int result = 0;
   for (int k = 0; k < t.nt * 3; ++k) {
-    const int fl = cc.fl[tiling_edge(t, config, k)];
-    bool found = false;
-    for (int m = 0; m < n; ++m) found = found || (seen[m] == fl);
-    if (!found && fl >= 0) ++result;
-    seen[n++] = fl;
+    const int e = tiling_edge(t, config, k);
+    if (!((seen >> e) & 1u) && cc.fl[e] >= 0) ++result;
+    seen |= 1u << e;
   }
   return result;
 }
@@ -742,9 +773,42 @@ MC_HD void add_face_from_edge_c(Grid& g, CubeCache& cc, Cell& c, int vi) {
   ++g.n_f3;
 }
 
-MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, int mode) {
+// The mutable part of a Grid, passed by value to the generic path: the warp path's own `Grid` never has its address
+// taken, so the compiler keeps it in registers instead of local memory.
+struct GridState {
+  uint32_t qh, qt, uh, ut, nh, nt;
+  int status;
+  int64_t n_v, n_f3, n_seed, n_accept, n_unsure_push, n_nontrivial_push;
+};
+MC_HD GridState grid_state_get(const Grid& g) {
+  GridState s;
+  s.qh = g.q.head; s.qt = g.q.tail; s.uh = g.q_unsure.head; s.ut = g.q_unsure.tail;
+  s.nh = g.q_nontrivial.head; s.nt = g.q_nontrivial.tail; s.status = g.status;
+  s.n_v = g.n_v; s.n_f3 = g.n_f3; s.n_seed = g.n_seed; s.n_accept = g.n_accept;
+  s.n_unsure_push = g.n_unsure_push; s.n_nontrivial_push = g.n_nontrivial_push;
+  return s;
+}
+MC_HD void grid_state_put(Grid& g, const GridState& s) {
+  g.q.head = s.qh; g.q.tail = s.qt; g.q_unsure.head = s.uh; g.q_unsure.tail = s.ut;
+  g.q_nontrivial.head = s.nh; g.q_nontrivial.tail = s.nt; g.status = s.status;
+  g.n_v = s.n_v; g.n_f3 = s.n_f3; g.n_seed = s.n_seed; g.n_accept = s.n_accept;
+  g.n_unsure_push = s.n_unsure_push; g.n_nontrivial_push = s.n_nontrivial_push;
+}
+// `home` holds the constant fields (sizes, pointers, queue buffers); the state travels in `gs`.
+MC_HD_NOINLINE bool visit_cube_generic(const Grid* home, GridState& gs, int z, int y, int x, int mode) {
+  Grid tmp = *home;
+  grid_state_put(tmp, gs);
+  const bool r = visit_cube(tmp, z, y, x, mode);
+  gs = grid_state_get(tmp);
+  return r;
+}
+
+MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, int x, int mode, bool& done_set) {
   const int N = g.N;
+  done_set = false;
   const int nb = N - 2;
+  MC_PROF_T(t_begin);
+  MC_PROF_INC(5);
   // ---- phase 1: cooperative fetch of the 4x4x4 neighbourhood (origin z-1,y-1,x-1) and the 13 vertex slots ----
   MC_WARP_SYNC();
   MC_LANE_LOOP(l) {
@@ -781,28 +845,35 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, int mode) {
     }
   }
   MC_WARP_SYNC();
+  MC_PROF_T(t_fetched);
+  MC_PROF_ADD(1, t_begin, t_fetched);
   // ---- uniform part ----
   int cb[8];
   float cim[8];
   int64_t ci[8];
+  MC_UNROLL
   for (int i = 0; i < 8; ++i) {
     cb[i] = MC_BLK(1 + MC_CZ(i), 1 + MC_CY(i), 1 + MC_CX(i));
     cim[i] = cc.im[cb[i]];
     ci[i] = lin(g, z + MC_CZ(i), y + MC_CY(i), x + MC_CX(i));
   }
   // the "exact zero neighbour" extension (pyx:1287-1292) reaches outside the cached block: generic path
+  MC_UNROLL
   for (int i = 0; i < 8; ++i) {
     if ((cc.flg[cb[i]] & 1) || cim[i] == 0.0f) continue;
+    MC_UNROLL
     for (int d = 0; d < 6; ++d)
       if (cc.vstat[i * 6 + d] == 2) {
-        Grid tmp = g;            // the generic path takes the struct by address; keep `g` itself register-promotable
-        const bool r = visit_cube(tmp, z, y, x, mode);
-        g = tmp;
+        GridState gs = grid_state_get(g);
+        const bool r = visit_cube_generic(home, gs, z, y, x, mode);
+        grid_state_put(g, gs);
+        done_set = (g.flg[lin(g, z, y, x)] & 2) != 0;
         return r;
       }
   }
   int visited_vs[8];
   float sign_vs[8];
+  MC_UNROLL
   for (int vtx = 0; vtx < 8; ++vtx) {
     visited_vs[vtx] = 0;
     sign_vs[vtx] = 0.0f;
@@ -817,6 +888,7 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, int mode) {
       continue;
     }
     const int bz = 1 + MC_CZ(vtx), by = 1 + MC_CY(vtx), bx = 1 + MC_CX(vtx);
+    MC_UNROLL
     for (int d = 0; d < 6; ++d) {
       if (cc.vstat[vtx * 6 + d] != 1) continue;
       const int dz = (d == 0) - (d == 1), dy = (d == 2) - (d == 3), dx = (d == 4) - (d == 5);
@@ -842,13 +914,16 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, int mode) {
   }
 
   bool all_voted = true;
+  MC_UNROLL
   for (int i = 0; i < 8; ++i) all_voted = all_voted && (visited_vs[i] >= 1);
   if (!all_voted) {
     const int order[8] = {0, 1, 3, 2, 4, 5, 7, 6};
     float base[3] = {0.f, 0.f, 0.f};
     float anchor_sign = 1.f;
     bool found = false;
-    for (int k = 0; k < 8 && !found; ++k) {
+    MC_UNROLL
+    for (int k = 0; k < 8; ++k) {
+      if (found) continue;
       const int b0 = cb[order[k]];
       if ((cc.flg[b0] & 1) && non_zero_norm(cc.gr + 3 * b0)) {
         anchor_sign = my_sign((float)cc.sgn[b0]);
@@ -856,7 +931,9 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, int mode) {
         found = true;
       }
     }
-    for (int k = 0; k < 8 && !found; ++k) {
+    MC_UNROLL
+    for (int k = 0; k < 8; ++k) {
+      if (found) continue;
       const int b0 = cb[order[k]];
       if (non_zero_norm(cc.gr + 3 * b0)) {
         base[0] = cc.gr[3 * b0]; base[1] = cc.gr[3 * b0 + 1]; base[2] = cc.gr[3 * b0 + 2];
@@ -865,6 +942,7 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, int mode) {
     }
     base[0] = anchor_sign * base[0]; base[1] = anchor_sign * base[1]; base[2] = anchor_sign * base[2];
     const bool check_unsure = (mode == 1) && !g.q.empty();
+    MC_UNROLL
     for (int i = 0; i < 8; ++i) {
       if (visited_vs[i] != 0) continue;
       const float s = dot3(base, cc.gr + 3 * cb[i]);
@@ -882,15 +960,19 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, int mode) {
     }
   }
 
+  MC_PROF_T(t_signed);
+  MC_PROF_ADD(2, t_fetched, t_signed);
   if (mode == 2) return false;
 
   double v[8];
+  MC_UNROLL
   for (int i = 0; i < 8; ++i) {
     float p = (float)cc.sgn[cb[i]] * cim[i];
     v[i] = (double)p;
   }
   Cell c;
   cell_set(c, x, y, z, v);
+  MC_UNROLL
   for (int i = 0; i < 8; ++i) g.flg[ci[i]] = (uint8_t)(cc.flg[cb[i]] | 1);
 
   const int kase = LUT2(CASES, c.index, 0);
@@ -906,30 +988,111 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, int z, int y, int x, int mode) {
     }
     const int config = LUT2(CASES, c.index, 1);
     const Tiling t = select_tiling(c, kase, config);
+    // the tiling's edge list (<= 36 table entries): one cooperative load, then both passes below read shared memory
+    MC_WARP_SYNC();
+    MC_LANE_LOOP(l) {
+      for (int k = l; k < t.nt * 3; k += 32) cc.tedge[k] = (uint8_t)tiling_edge(t, config, k);
+    }
+    MC_WARP_SYNC();
     if (mode == 1) {
-      if (check_tiling_c(cc, t, config) < 2) return false;
+      uint32_t seen = 0;
+      int existing = 0;   // check_tiling(): distinct edge ids whose vertex slot is already filled (see check_tiling_c)
+      for (int k = 0; k < t.nt * 3; ++k) {
+        const int e = cc.tedge[k];
+        if (!((seen >> e) & 1u) && cc.fl[e] >= 0) ++existing;
+        seen |= 1u << e;
+      }
+      if (existing < 2) return false;
     }
     g.flg[me] = (uint8_t)(cc.flg[cb[0]] | 1 | 2);
-    for (int k = 0; k < t.nt * 3; ++k) add_face_from_edge_c(g, cc, c, tiling_edge(t, config, k));
+    done_set = true;
+    MC_PROF_T(t_tiled);
+    MC_PROF_ADD(3, t_signed, t_tiled);
+    for (int k = 0; k < t.nt * 3; ++k) add_face_from_edge_c(g, cc, c, cc.tedge[k]);
     push_neighbours(g, z, y, x);
     ++g.n_accept;
+    MC_PROF_T(t_emitted);
+    MC_PROF_ADD(4, t_tiled, t_emitted);
     return true;
   }
   g.flg[me] = (uint8_t)(cc.flg[cb[0]] | 1 | 2);
+  done_set = true;
   return false;
 }
 
-// replay() with visit_cube_w(); `g` is the caller's private (per-lane) copy of the bookkeeping.
-MC_HD void replay_w(Grid& g, CubeCache& cc) {
+// linear index -> (z, y, x); `sh` = log2(N) when N is a power of two (shifts instead of three integer divisions), else -1
+MC_HD void decode_index(int32_t c, int N, int sh, int& z, int& y, int& x) {
+  if (sh >= 0) { x = c & (N - 1); y = (c >> sh) & (N - 1); z = c >> (2 * sh); }
+  else { x = c % N; y = (c / N) % N; z = c / (N * N); }
+}
+
+// Pull the lattice neighbourhood of cube `c` towards L2 ahead of its visit (hint only; no effect on results).
+MC_HD void prefetch_cube(const Grid& g, int32_t c, int sh) {
   const int N = g.N;
+  int x, y, z;
+  decode_index(c, N, sh, z, y, x);
+  const int x0 = x > 0 ? x - 1 : 0;
+  for (int r = 0; r < 16; ++r) {
+    int cz = z - 1 + (r >> 2), cy = y - 1 + (r & 3);
+    cz = cz < 0 ? 0 : (cz >= N ? N - 1 : cz);
+    cy = cy < 0 ? 0 : (cy >= N ? N - 1 : cy);
+    const int64_t i = lin(g, cz, cy, x0);
+    MC_PREFETCH(g.im + i);
+    MC_PREFETCH(g.grads + 3 * i);
+    MC_PREFETCH(g.grads + 3 * i + 8);
+    MC_PREFETCH(g.sgn + i);
+    MC_PREFETCH(g.flg + i);
+  }
+  for (int r = 0; r < 4; ++r) MC_PREFETCH(g.face_layer + 4 * lin(g, z + (r >> 1), y + (r & 1), x));
+}
+
+// A visit set the "visited" flag of cube `me`: keep the look-ahead windows coherent.
+MC_HD void note_done(CubeCache& cc, int32_t me) {
+  MC_LANE_LOOP(l) {
+    if (cc.qw_cur[l] == me) cc.qw_f[l] |= 1;
+    if (cc.sw_cur[l] == me) cc.sw_f[l] |= 1;
+  }
+  MC_WARP_SYNC();
+}
+
+// replay() with visit_cube_w(); `g` is the caller's private (per-lane) copy of the bookkeeping.
+// Queue pops and raster seeds are served from 32-entry look-ahead windows: one cooperative load fetches the next 32
+// entries, their visited flags and candidate bits (instead of two dependent global loads per pop), and note_done()
+// replays this warp's own flag updates into the windows, so the decisions are exactly those of replay().
+MC_HD void replay_w(Grid& g, CubeCache& cc, const Grid* home) {
+  const int N = g.N;
+  int sh = -1;
+  if ((N & (N - 1)) == 0) { sh = 0; while ((1 << sh) < N) ++sh; }
   g.n_v = 0; g.n_f3 = 0; g.status = MC_OK;
   g.n_seed = g.n_accept = g.n_unsure_push = g.n_nontrivial_push = 0;
+  for (int i = 0; i < 8; ++i) g.prof[i] = 0;
+  MC_PROF_T(t_replay0);
+  MC_WARP_SYNC();
+  MC_LANE_LOOP(l) { cc.qw_cur[l] = -1; cc.sw_cur[l] = -1; cc.qw_f[l] = 0; cc.sw_f[l] = 0; }
+  MC_WARP_SYNC();
+  uint32_t qw_base = 0, qw_n = 0;
+  int64_t sw_base = 0, sw_n = 0;
+  bool done_set = false;
   for (int64_t k = 0; k < g.n_cand; ++k) {
-    const int32_t cidx = g.cand_list[k];
-    if (g.flg[cidx] & 2) continue;
-    int x = cidx % N, y = (cidx / N) % N, z = cidx / (N * N);
+    if (k - sw_base >= sw_n) {
+      sw_base = k;
+      sw_n = g.n_cand - k < 32 ? g.n_cand - k : 32;
+      MC_WARP_SYNC();
+      MC_LANE_LOOP(l) {
+        int32_t c = -1; uint8_t f = 0;
+        if (l < sw_n) { c = g.cand_list[sw_base + l]; f = (g.flg[c] & 2) ? 1 : 0; }
+        cc.sw_cur[l] = c; cc.sw_f[l] = f;
+      }
+      MC_WARP_SYNC();
+    }
+    const int32_t cidx = cc.sw_cur[k - sw_base];
+    if (cc.sw_f[k - sw_base] & 1) continue;
+    int x, y, z;
+    decode_index(cidx, N, sh, z, y, x);
     ++g.n_seed;
-    if (!visit_cube_w(g, cc, z, y, x, 0)) continue;
+    const bool accepted = visit_cube_w(g, cc, home, z, y, x, 0, done_set);
+    if (done_set) note_done(cc, cidx);
+    if (!accepted) continue;
     bool visit_neighbours = true;
     while (!g.q.empty() || !g.q_unsure.empty() || !g.q_nontrivial.empty()) {
       if (g.status == MC_QUEUE_OVERFLOW) return;
@@ -941,7 +1104,9 @@ MC_HD void replay_w(Grid& g, CubeCache& cc) {
           cur = g.q_unsure.front();
           if (visit_neighbours) {
             if (g.flg[cur] & 2) { g.q_unsure.pop(); continue; }
-            push_neighbours(g, cur / (N * N), (cur / N) % N, cur % N);
+            int ux, uy, uz;
+            decode_index(cur, N, sh, uz, uy, ux);
+            push_neighbours(g, uz, uy, ux);
             visit_neighbours = false;
             continue;
           } else {
@@ -949,14 +1114,40 @@ MC_HD void replay_w(Grid& g, CubeCache& cc) {
             visit_neighbours = true;
           }
         }
+        if (g.flg[cur] & 2) continue;
+        if (!is_candidate(g, cur)) continue;
       } else {
-        cur = g.q.front(); g.q.pop();
+        if (g.q.head - qw_base >= qw_n) {
+          qw_base = g.q.head;
+          const uint32_t avail = g.q.tail - g.q.head;
+          qw_n = avail < 32u ? avail : 32u;
+          MC_PROF_INC(6);
+          MC_WARP_SYNC();
+          MC_LANE_LOOP(l) {
+            int32_t c = -1; uint8_t f = 0;
+            if ((uint32_t)l < qw_n) {
+              c = g.q.buf[(qw_base + (uint32_t)l) & g.q.mask];
+              f = (uint8_t)(((g.flg[c] & 2) ? 1 : 0) | (is_candidate(g, c) ? 2 : 0));
+              if (f == 2) prefetch_cube(g, c, sh);
+            }
+            cc.qw_cur[l] = c; cc.qw_f[l] = f;
+          }
+          MC_WARP_SYNC();
+        }
+        const uint32_t w = g.q.head - qw_base;
+        cur = cc.qw_cur[w];
+        const uint8_t wf = cc.qw_f[w];
+        g.q.pop();
+        if (wf != 2) continue;   // already visited, or not a candidate cube
       }
-      if (g.flg[cur] & 2) continue;
-      if (!is_candidate(g, cur)) continue;
-      visit_cube_w(g, cc, cur / (N * N), (cur / N) % N, cur % N, visit_neighbours ? 1 : 2);
+      int vx, vy, vz;
+      decode_index(cur, N, sh, vz, vy, vx);
+      visit_cube_w(g, cc, home, vz, vy, vx, visit_neighbours ? 1 : 2, done_set);
+      if (done_set) note_done(cc, cur);
     }
   }
+  MC_PROF_T(t_replay1);
+  MC_PROF_ADD(0, t_replay0, t_replay1);
   if (g.status == MC_OK && g.n_v == 0) g.status = MC_EMPTY;
 }
 

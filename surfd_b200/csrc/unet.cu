@@ -123,18 +123,12 @@ __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, const uint
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// K slice `crank` of `ks` of output tile (n0, m0): every warp accumulates its chunks into register fragments.
 template <int MODE>
-__global__ void __launch_bounds__(256)
-conv_gemm_kernel(ConvArgs a) {
-  PDL_PROLOGUE();
-  extern __shared__ __align__(16) float smem[];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int crank = (int)cluster.block_rank();
+__device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m0, int ks, int crank, float* smem, float (&acc)[8][4]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* As = smem + warp * (2 * CT * CTP);
   float* Ws = As + CT * CTP;
-  const int n0 = blockIdx.x * CT;
-  const int m0 = blockIdx.y * CT;
   const int M = a.B * a.T_out;
 
   // this lane's token row for loading
@@ -144,13 +138,12 @@ conv_gemm_kernel(ConvArgs a) {
 
   const int ly = lane >> 3, lx = lane & 7;   // FFMA mapping: rows ly + 4i, cols lx + 8j
   const int fg = lane >> 2, ft = lane & 3;   // MMA fragment mapping: group id / thread in group
-  float acc[8][4];                           // MODE 0: [i][j];  MODE 1/2: [mt*4 + nt][c0..c3]
+  // acc: MODE 0: [i][j];  MODE 1/2: [mt*4 + nt][c0..c3]
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  const int ks = (int)cluster.num_blocks();    // K split of this launch: 1, 2, 4 or 8 CTAs per output tile
   const int my_slot = warp * ks + crank;       // chunk c belongs to slot c % (8*ks); consecutive chunks go to different CTAs
   // This warp owns the flattened chunks f = my_slot, my_slot + 8*ks, ...  (f enumerates segment, tap, 32-channel block).
   // The weight rows of the NEXT chunk are prefetched into registers while the current one is multiplied: weights come
@@ -256,7 +249,15 @@ conv_gemm_kernel(ConvArgs a) {
       }
     }
   }
-  // (1) cross-warp reduction inside the CTA: red[warp][row][col] (rows padded to 33) -> part[row][col]
+}
+
+// (1) cross-warp reduction inside the CTA: red[warp][row][col] (rows padded to 33) -> part[row][col]; returns `part`
+// (not yet synchronised: the caller's next barrier publishes it)
+template <int MODE>
+__device__ __forceinline__ float* conv_cta_partial(float (&acc)[8][4], float* smem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ly = lane >> 3, lx = lane & 7;
+  const int fg = lane >> 2, ft = lane & 3;
   __syncthreads();
   float* red = smem;
   float* part = smem + 8 * CT * 33;   // [32][32] CTA partial, read by the other CTAs of the cluster
@@ -286,24 +287,45 @@ conv_gemm_kernel(ConvArgs a) {
       part[r * CT + c0 + j] = sum;
     }
   }
+  return part;
+}
+
+// epilogue of one output element: + bias (+ per-sample embedding column) (+ residual)
+__device__ __forceinline__ void conv_store(const ConvArgs& a, int m0, int n0, int idx, float v) {
+  const int r = idx >> 5, col = idx & 31;
+  const int m = m0 + r;
+  if (m < a.B * a.T_out) {
+    const int n = n0 + col;
+    const int b = m / a.T_out;
+    v += a.bias[n];
+    if (a.emb) v += a.emb[(size_t)b * a.emb_ld + n];
+    const size_t o = (size_t)m * a.N + n;
+    if (a.residual) v += a.residual[o];
+    a.out[o] = v;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+conv_gemm_kernel(ConvArgs a) {
+  PDL_PROLOGUE();
+  extern __shared__ __align__(16) float smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int ks = (int)cluster.num_blocks();    // K split of this launch: 1, 2, 4 or 8 CTAs per output tile
+  const int n0 = blockIdx.x * CT;
+  const int m0 = blockIdx.y * CT;
+  float acc[8][4];
+  conv_accumulate<MODE>(a, n0, m0, ks, crank, smem, acc);
+  float* part = conv_cta_partial<MODE>(acc, smem);
   // (2) cross-CTA reduction over distributed shared memory: CTA `crank` finishes its 1/ks share of the 32x32 tile
   cluster.sync();
   {
     const int per = CT * CT / ks;
     for (int idx = crank * per + threadIdx.x; idx < (crank + 1) * per; idx += 256) {
-      const int r = idx >> 5, col = idx & 31;
       float v = 0.f;
       for (int j = 0; j < ks; ++j) v += cluster.map_shared_rank(part, j)[idx];
-      const int m = m0 + r;
-      if (m < M) {
-        const int n = n0 + col;
-        const int b = m / a.T_out;
-        v += a.bias[n];
-        if (a.emb) v += a.emb[(size_t)b * a.emb_ld + n];
-        const size_t o = (size_t)m * a.N + n;
-        if (a.residual) v += a.residual[o];
-        a.out[o] = v;
-      }
+      conv_store(a, m0, n0, idx, v);
     }
   }
   cluster.sync();   // keep this CTA's shared memory alive until every peer has read it

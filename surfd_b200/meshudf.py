@@ -84,6 +84,12 @@ class MarchingCubes:
         _lib.check(self.lib.surfd_mc_launch(self._h, _lib.ptr(volume), _lib.ptr(grads), N, sp))
         self._stream = stream
 
+    def profile(self):
+        """cycle counters of the last replay (zeros unless built with -DMC_PROFILE) -- diagnostics"""
+        prof = (ctypes.c_int64 * 8)()
+        _lib.check(self.lib.surfd_mc_profile(self._h, prof))
+        return dict(zip(("total", "fetch", "sign", "tiling", "emit", "visits", "refills"), list(prof)[:7]))
+
     def finish(self):
         """wait for launch(); returns (verts float32 [V,3], faces int32 [F,3]) or None when the buffers had to grow
         (call launch() again).  Raises RuntimeError('No surface found...') like the reference."""

@@ -51,7 +51,7 @@ static int run_impl(const float* im, const float* grads, int N, float* verts, in
   std::vector<int32_t> b0(cap), b1(cap), b2(cap);
   g.q.buf = b0.data(); g.q_unsure.buf = b1.data(); g.q_nontrivial.buf = b2.data();
   g.q.mask = g.q_unsure.mask = g.q_nontrivial.mask = cap - 1;
-  if (warp_variant) { CubeCache cc; replay_w(g, cc); } else replay(g);
+  if (warp_variant) { CubeCache cc; const Grid home = g; replay_w(g, cc, &home); } else replay(g);
   *n_v = g.n_v; *n_f3 = g.n_f3;
   if (stats) { stats[0] = g.n_cand; stats[1] = g.n_seed; stats[2] = g.n_accept; stats[3] = g.n_unsure_push; stats[4] = g.n_nontrivial_push; }
   return g.status;
