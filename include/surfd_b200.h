@@ -22,6 +22,7 @@ extern "C" {
 #define SURFD_CAPACITY 2        /* output buffers too small; *n_v / *n_f hold the required sizes */
 #define SURFD_QUEUE_OVERFLOW 3  /* internal BFS queue bound exceeded (pathological field) */
 #define SURFD_BAD_ARGUMENT 4    /* reference: ValueError on bad shapes _marching_cubes_lewiner.py:102-105 */
+#define SURFD_ABORTED 5         /* the persistent sampler kernel gave up at a grid barrier (never expected) */
 
 int surfd_version(void);
 /* last CUDA / argument error text of the calling thread (static buffer) */
@@ -124,6 +125,18 @@ void surfd_unet_destroy(surfd_unet* u);
 /* The denoiser is latency-bound (~170 dependent small kernels per step), so surfd_sample() splits a batch over `n_lanes`
  * concurrent streams (private activations, shared weights).  Default 1 (measured fastest).  Results do not depend on it. */
 int surfd_unet_set_lanes(surfd_unet* u, int n_lanes);
+/* surfd_sample engine.  mode 1 (default): one persistent cooperative kernel runs the whole reverse-diffusion loop on
+ * `n_sms` CTAs (0 = one per SM; leave SMs free for work that should overlap it), token GEMMs split over K so that every
+ * op is a single round of the resident CTAs.  mode 2: the same kernel with the graph path's K split -- samples are
+ * bit-identical to mode 0 and independent of n_sms.  mode 0: CUDA-graph replay of the per-step kernel sequence.
+ * All modes compute in the precision selected by surfd_unet_set_precision and agree to fp32 rounding. */
+int surfd_unet_set_sampler(surfd_unet* u, int mode, int n_sms);
+/* Diagnostics: out == NULL switches the persistent kernel's per-op-type cycle counters on/off; out != NULL reads the
+ * last run's counters: out[(h * 8 + op) * 3 + {body cycles, barrier cycles, count}], h = 0 first CTA / 1 last CTA,
+ * op = 1 emb1, 2 linear, 3 in-conv, 4 group norm, 5 token GEMM, 6 attention, 7 out-conv + DDPM update. */
+int surfd_unet_profile(surfd_unet* u, int on, int64_t* out /* [48] or NULL */);
+/* SURFD_ABORTED if the last persistent run reported a barrier time-out (valid after its stream was synchronised). */
+int surfd_unet_status(surfd_unet* u);
 /* token-GEMM arithmetic: 0 = fp32 FFMA, 1 = mma.sync 3xTF32 split (fp32-class accuracy, default), 2 = single-pass TF32 */
 int surfd_unet_set_precision(surfd_unet* u, int mode);
 size_t surfd_unet_packed_floats(void);

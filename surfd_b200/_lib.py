@@ -43,6 +43,9 @@ PROTOTYPES = {
     "surfd_unet_create": (ctypes.c_int, [c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "surfd_unet_destroy": (None, [c_vp]),
     "surfd_unet_set_lanes": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "surfd_unet_set_sampler": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
+    "surfd_unet_status": (ctypes.c_int, [c_vp]),
+    "surfd_unet_profile": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_i64)]),
     "surfd_unet_set_precision": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "surfd_unet_packed_floats": (ctypes.c_size_t, []),
     "surfd_unet_forward": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

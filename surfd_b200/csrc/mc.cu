@@ -79,6 +79,7 @@ classify_kernel(const float* __restrict__ im, int N, float avg_t, float max_t, u
 __global__ void __launch_bounds__(32) replay_kernel(surfd_mccore::Grid* gp, surfd_mccore::Grid* result_host,
                                                     const int64_t* __restrict__ n_cand_dev, int64_t cap_cand) {
   __shared__ surfd_mccore::CubeCache cc;
+  surfd_mccore::mc_lut_load();
   surfd_mccore::Grid g = *gp;
   const int64_t n = *n_cand_dev;
   g.n_cand = n < cap_cand ? n : cap_cand;

@@ -34,8 +34,22 @@ namespace surfd_mccore {
 
 #include "mc_luts.inc"
 
+#if defined(__CUDACC__)
+// Device: the 13 KB table blob is copied into shared memory once per kernel (mc_lut_load) -- every lookup on the
+// order-dependent chain is then a ~25-cycle shared load instead of a global load that competes with the lattice traffic
+// for L1.  (A function-scope __shared__ array is one object per kernel, whichever inlined copy names it.)
+__device__ __forceinline__ signed char* mc_lut_smem() {
+  __shared__ signed char lut[sizeof(MC_LUT_BLOB)];
+  return lut;
+}
+__device__ __forceinline__ void mc_lut_load() {   // whole thread block
+  signed char* d = mc_lut_smem();
+  for (int i = threadIdx.x; i < (int)sizeof(MC_LUT_BLOB); i += blockDim.x) d[i] = MC_LUT_BLOB[i];
+  __syncthreads();
+}
+#endif
 #if defined(__CUDACC__) && defined(__CUDA_ARCH__)
-#define MC_LUTV(i) MC_LUT_BLOB[i]
+#define MC_LUTV(i) (mc_lut_smem()[i])
 #define MC_LUTOFF(id) MC_LUT_OFF[id]
 #define MC_LUTL1(id) MC_LUT_L1[id]
 #define MC_LUTL2(id) MC_LUT_L2[id]
@@ -153,6 +167,14 @@ MC_HD float edge_vote(const float* g1, const float* g2, int dz, int dy, int dx) 
 MC_HD float vote_accumulate(float acc, float sgn, float vote) {
   float prod = sgn * vote;
   return (float)((double)acc + (double)prod);
+}
+
+// The same in one float addition: the sum of two floats rounded to double (53 bits >= 2*24 + 2) and then to float equals
+// the correctly rounded float sum (double rounding is innocuous for + - * / sqrt at that width), so the warp path skips
+// the two conversions and the FP64 add.
+MC_HD float vote_accumulate_f32(float acc, float sgn, float vote) {
+  float prod = sgn * vote;
+  return acc + prod;
 }
 
 #define MC_FLT_EPS 2.220446049250313e-16  /* np.spacing(1.0), pyx:35 */
@@ -750,9 +772,14 @@ MC_HD void add_face_from_edge_c(Grid& g, CubeCache& cc, Cell& c, int vi) {
       double fx = 0.0, fy = 0.0, fz = 0.0, ff = 0.0;
       fx += (double)dx1 * w1; fy += (double)dy1 * w1; fz += (double)dz1 * w1; ff += w1;
       fx += (double)dx2 * w2; fy += (double)dy2 * w2; fz += (double)dz2 * w2; ff += w2;
-      px = (double)c.x + 1.0 * fx / ff;
-      py = (double)c.y + 1.0 * fy / ff;
-      pz = (double)c.z + 1.0 * fz / ff;
+      // the two end points of an edge differ along one axis only: along the other two the numerator is 0 or is the very
+      // same sum as ff, so those quotients are exactly 0 or 1 and only one FP64 division is needed
+      const double qx = fx == 0.0 ? 0.0 : (fx == ff ? 1.0 : 1.0 * fx / ff);
+      const double qy = fy == 0.0 ? 0.0 : (fy == ff ? 1.0 : 1.0 * fy / ff);
+      const double qz = fz == 0.0 ? 0.0 : (fz == ff ? 1.0 : 1.0 * fz / ff);
+      px = (double)c.x + qx;
+      py = (double)c.y + qy;
+      pz = (double)c.z + qz;
     }
     idx = (int)g.n_v;
     if (g.n_v < g.cap_v) {
@@ -812,20 +839,31 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, 
   // ---- phase 1: cooperative fetch of the 4x4x4 neighbourhood (origin z-1,y-1,x-1) and the 13 vertex slots ----
   MC_WARP_SYNC();
   MC_LANE_LOOP(l) {
-    for (int v = l; v < 64; v += 32) {
+    // two lattice vertices per lane (v = l, l + 32).  Indices are clamped into the lattice so that all 12 loads (+ the
+    // vertex slot) can be issued back to back -- one memory latency per visit -- and out-of-lattice entries are zeroed
+    // afterwards.
+    int64_t li[2];
+    bool inside[2];
+    MC_UNROLL
+    for (int j = 0; j < 2; ++j) {
+      const int v = l + 32 * j;
       const int cz = z - 1 + (v >> 4), cy = y - 1 + ((v >> 2) & 3), cx = x - 1 + (v & 3);
-      const bool inside = cz >= 0 && cz < N && cy >= 0 && cy < N && cx >= 0 && cx < N;
-      float im = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
-      int8_t sg = 0; uint8_t fg = 0;
-      if (inside) {
-        const int64_t i = lin(g, cz, cy, cx);
-        im = g.im[i]; sg = g.sgn[i]; fg = g.flg[i];
-        g0 = g.grads[3 * i]; g1 = g.grads[3 * i + 1]; g2 = g.grads[3 * i + 2];
-      }
-      cc.im[v] = im; cc.sgn[v] = sg; cc.flg[v] = fg;
-      cc.gr[3 * v] = g0; cc.gr[3 * v + 1] = g1; cc.gr[3 * v + 2] = g2;
+      inside[j] = cz >= 0 && cz < N && cy >= 0 && cy < N && cx >= 0 && cx < N;
+      const int qz = cz < 0 ? 0 : (cz >= N ? N - 1 : cz), qy = cy < 0 ? 0 : (cy >= N ? N - 1 : cy), qx = cx < 0 ? 0 : (cx >= N ? N - 1 : cx);
+      li[j] = lin(g, qz, qy, qx);
     }
-    if (l < 13) cc.fl[l] = g.face_layer[facelayer_index_xyz(N, x, y, z, l)];
+    const float im0 = g.im[li[0]], im1 = g.im[li[1]];
+    const int8_t sg0 = g.sgn[li[0]], sg1 = g.sgn[li[1]];
+    const uint8_t fg0 = g.flg[li[0]], fg1 = g.flg[li[1]];
+    const float a0 = g.grads[3 * li[0]], a1 = g.grads[3 * li[0] + 1], a2 = g.grads[3 * li[0] + 2];
+    const float b0 = g.grads[3 * li[1]], b1 = g.grads[3 * li[1] + 1], b2 = g.grads[3 * li[1] + 2];
+    const int32_t slot = g.face_layer[facelayer_index_xyz(N, x, y, z, l < 13 ? l : 0)];
+    cc.im[l] = inside[0] ? im0 : 0.f; cc.sgn[l] = inside[0] ? sg0 : (int8_t)0; cc.flg[l] = inside[0] ? fg0 : (uint8_t)0;
+    cc.gr[3 * l] = inside[0] ? a0 : 0.f; cc.gr[3 * l + 1] = inside[0] ? a1 : 0.f; cc.gr[3 * l + 2] = inside[0] ? a2 : 0.f;
+    const int l1 = l + 32;
+    cc.im[l1] = inside[1] ? im1 : 0.f; cc.sgn[l1] = inside[1] ? sg1 : (int8_t)0; cc.flg[l1] = inside[1] ? fg1 : (uint8_t)0;
+    cc.gr[3 * l1] = inside[1] ? b0 : 0.f; cc.gr[3 * l1 + 1] = inside[1] ? b1 : 0.f; cc.gr[3 * l1 + 2] = inside[1] ? b2 : 0.f;
+    if (l < 13) cc.fl[l] = slot;
   }
   MC_WARP_SYNC();
   // ---- phase 2: one (corner, direction) edge vote per lane ----
@@ -895,7 +933,7 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, 
       const int8_t sn = cc.sgn[MC_BLK(bz + dz, by + dy, bx + dx)];
       if (sn == 0) continue;
       visited_vs[vtx] += 1;
-      sign_vs[vtx] = vote_accumulate(sign_vs[vtx], (float)sn, cc.vote[vtx * 6 + d]);
+      sign_vs[vtx] = vote_accumulate_f32(sign_vs[vtx], (float)sn, cc.vote[vtx * 6 + d]);
     }
     if (mode != 0) {
       if (visited_vs[vtx] >= 1 &&

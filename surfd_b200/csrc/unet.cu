@@ -104,6 +104,7 @@ struct ConvArgs {
 constexpr int CT = 32;        // tile edge
 constexpr int CTP = CT + 4;   // padded row (floats)
 constexpr int KSPLIT = 8;     // max CTAs per cluster: the K reduction is split over a thread-block cluster (1, 2, 4 or 8)
+constexpr int CONV_STAGES = 2; // per-warp cp.async stages of the chunk stream
 
 // One output tile (32 tokens x 32 channels) is owned by a cluster of KSPLIT CTAs.  K chunks (32 input channels of one
 // tap of one segment) are dealt round-robin to the 8 x 8 = 64 warps of the cluster, so even the deepest layers
@@ -127,8 +128,7 @@ __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, const uint
 template <int MODE>
 __device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m0, int ks, int crank, float* smem, float (&acc)[8][4]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* As = smem + warp * (2 * CT * CTP);
-  float* Ws = As + CT * CTP;
+  float* stage0 = smem + warp * (CONV_STAGES * 2 * CT * CTP);   // per warp: CONV_STAGES x (A tile | W tile)
   const int M = a.B * a.T_out;
 
   // this lane's token row for loading
@@ -146,12 +146,13 @@ __device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m
 
   const int my_slot = warp * ks + crank;       // chunk c belongs to slot c % (8*ks); consecutive chunks go to different CTAs
   // This warp owns the flattened chunks f = my_slot, my_slot + 8*ks, ...  (f enumerates segment, tap, 32-channel block).
-  // The weight rows of the NEXT chunk are prefetched into registers while the current one is multiplied: weights come
-  // from HBM (553 MB per step >> L2) and are the long pole of the per-warp chain; the activation rows are L2-resident.
+  // Chunks stream through a per-warp cp.async double buffer: while chunk f is multiplied, the 32 token rows and 32
+  // weight rows (128 B each) of chunk f + 8*ks are already in flight (weights from HBM: 553 MB per step >> L2; the
+  // activation rows are L2-resident).  Copies bypass L1 (.cg), so the persistent kernel never sees stale activations.
   const int n_chunks0 = a.seg[0].taps * (a.seg[0].Cin / CT);
   const int n_chunks = n_chunks0 + (a.nseg > 1 ? a.seg[1].taps * (a.seg[1].Cin / CT) : 0);
   const int stride_f = 8 * ks;
-  auto locate = [&](int f, const float*& arow, const float*& wrow, bool& ok) {
+  auto issue = [&](int f, float* As_, float* Ws_) {
     const int s = f < n_chunks0 ? 0 : 1;
     const Seg& sg = a.seg[s];
     const int g = s ? f - n_chunks0 : f;
@@ -159,37 +160,32 @@ __device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m
     const int tap = g / cpt, c = g - tap * cpt;
     const int T_eff = sg.up ? 2 * sg.T_in : sg.T_in;
     const int src = rl * sg.stride + tap - (sg.taps >> 1);
-    ok = row_ok && src >= 0 && src < T_eff;
+    const bool ok = row_ok && src >= 0 && src < T_eff;
     const int st = sg.up ? (src >> 1) : src;
-    arow = sg.A + ((size_t)rb * sg.T_in + (ok ? st : 0)) * sg.Cin + c * CT;
-    wrow = sg.W + ((size_t)tap * a.N + n0 + lane) * sg.Cin + c * CT;
-  };
-  float4 wv[8], wn[8];
-  const float* arow = nullptr; const float* wrow = nullptr; bool ok = false;
-  int f = my_slot;
-  if (f < n_chunks) {
-    locate(f, arow, wrow, ok);
+    const float* arow = sg.A + ((size_t)rb * sg.T_in + (ok ? st : 0)) * sg.Cin + c * CT;
+    const float* wrow = sg.W + ((size_t)tap * a.N + n0 + lane) * sg.Cin + c * CT;
+    const uint32_t da = (uint32_t)__cvta_generic_to_shared(As_ + lane * CTP);
+    const uint32_t dw = (uint32_t)__cvta_generic_to_shared(Ws_ + lane * CTP);
+    const int asz = ok ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled (padding rows / taps outside the sequence)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) wv[j] = *reinterpret_cast<const float4*>(wrow + 4 * j);
-  }
+    for (int j = 0; j < 8; ++j) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da + 16 * j), "l"(arow + 4 * j), "r"(asz) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dw + 16 * j), "l"(wrow + 4 * j) : "memory");
+    }
+  };
+  int f = my_slot;
+  int stg = 0;
+  if (f < n_chunks) issue(f, stage0, stage0 + CT * CTP);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (; f < n_chunks; f += stride_f) {
     {
       {
-        float4 av[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) av[j] = ok ? *reinterpret_cast<const float4*>(arow + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float* As = stage0 + stg * (2 * CT * CTP);
+        float* Ws = As + CT * CTP;
         const int fn = f + stride_f;
-        if (fn < n_chunks) {
-          locate(fn, arow, wrow, ok);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) wn[j] = *reinterpret_cast<const float4*>(wrow + 4 * j);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          *reinterpret_cast<float4*>(As + lane * CTP + 4 * j) = av[j];
-          *reinterpret_cast<float4*>(Ws + lane * CTP + 4 * j) = wv[j];
-        }
+        if (fn < n_chunks) issue(fn, stage0 + (stg ^ 1) * (2 * CT * CTP), stage0 + (stg ^ 1) * (2 * CT * CTP) + CT * CTP);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         if (MODE == 0) {
 #pragma unroll
@@ -244,11 +240,12 @@ __device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m
             }
           }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) wv[j] = wn[j];
+        __syncwarp();   // every lane is done reading this stage before the copy issued two chunks later overwrites it
+        stg ^= 1;
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // (1) cross-warp reduction inside the CTA: red[warp][row][col] (rows padded to 33) -> part[row][col]; returns `part`
@@ -323,8 +320,13 @@ conv_gemm_kernel(ConvArgs a) {
   {
     const int per = CT * CT / ks;
     for (int idx = crank * per + threadIdx.x; idx < (crank + 1) * per; idx += 256) {
+      float pv[KSPLIT];
+#pragma unroll
+      for (int j = 0; j < KSPLIT; ++j) pv[j] = j < ks ? cluster.map_shared_rank(part, j)[idx] : 0.f;   // remote loads in flight together
       float v = 0.f;
-      for (int j = 0; j < ks; ++j) v += cluster.map_shared_rank(part, j)[idx];
+#pragma unroll
+      for (int j = 0; j < KSPLIT; ++j)
+        if (j < ks) v += pv[j];
       conv_store(a, m0, n0, idx, v);
     }
   }
@@ -332,49 +334,69 @@ conv_gemm_kernel(ConvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// QKVAttentionLegacy: one CTA per (batch, head).  qkv [B][T][3C] with per-head [q|k|v] channel interleave.
+// QKVAttentionLegacy: one (batch, head) unit per thread group.  qkv [B][T][3C] with per-head [q|k|v] channel interleave.
+// `nthr` threads (a multiple of 32) with ids `tid` cooperate; `sync()` is their barrier.  Every output element is produced
+// by one thread (or one warp for a softmax row) in a fixed order, so the result does not depend on nthr.
+// Shared memory: q, k [T][ch+1] (padded: lanes walk k rows), v [T][ch], w [T][T+1].
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-attn_kernel(const float* __restrict__ qkv, int C, int T, int heads, float scale, float* __restrict__ out) {
-  PDL_PROLOGUE();
-  extern __shared__ __align__(16) float sm[];
+__host__ __device__ inline int attn_smem_floats(int T, int ch) { return 2 * T * (ch + 1) + T * ch + T * (T + 1); }
+
+template <typename Sync>
+__device__ __forceinline__ void attn_unit(const float* qkv, int C, int T, int heads, float scale, float* out, int b, int h, float* sm,
+                                          int tid, int nthr, Sync sync) {
   const int ch = C / heads;
-  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
-  float* q = sm;               // [T][ch] (scaled)
-  float* k = q + T * ch;       // [T][ch] (scaled)
-  float* v = k + T * ch;       // [T][ch]
+  const int chp = ch + 1;
+  float* q = sm;               // [T][chp] (scaled)
+  float* k = q + T * chp;      // [T][chp] (scaled)
+  float* v = k + T * chp;      // [T][ch]
   float* w = v + T * ch;       // [T][T+1]
   const float* base = qkv + (size_t)b * T * 3 * C + (size_t)h * 3 * ch;
-  for (int i = threadIdx.x; i < T * ch; i += 128) {
+  for (int i = tid; i < T * ch; i += nthr) {
     const int t = i / ch, c = i % ch;
     const float* p = base + (size_t)t * 3 * C + c;
-    q[i] = p[0] * scale;
-    k[i] = p[ch] * scale;
+    q[t * chp + c] = p[0] * scale;
+    k[t * chp + c] = p[ch] * scale;
     v[i] = p[2 * ch];
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * T; i += 128) {
+  sync();
+  for (int i = tid; i < T * T; i += nthr) {
     const int t = i / T, s = i % T;
     float acc = 0.f;
-    for (int c = 0; c < ch; ++c) acc = fmaf(q[t * ch + c], k[s * ch + c], acc);
+    for (int c = 0; c < ch; ++c) acc = fmaf(q[t * chp + c], k[s * chp + c], acc);
     w[t * (T + 1) + s] = acc;
   }
-  __syncthreads();
-  for (int t = threadIdx.x; t < T; t += 128) {
+  sync();
+  // softmax: one warp per row, lanes over the keys
+  const int lane = tid & 31;
+  for (int t = tid >> 5; t < T; t += nthr >> 5) {
+    float* wr = w + t * (T + 1);
     float mx = -INFINITY;
-    for (int s = 0; s < T; ++s) mx = fmaxf(mx, w[t * (T + 1) + s]);
+    for (int s = lane; s < T; s += 32) mx = fmaxf(mx, wr[s]);
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, of));
     float sum = 0.f;
-    for (int s = 0; s < T; ++s) { const float e = expf(w[t * (T + 1) + s] - mx); w[t * (T + 1) + s] = e; sum += e; }
+    for (int s = lane; s < T; s += 32) { const float e = expf(wr[s] - mx); wr[s] = e; sum += e; }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
     const float inv = 1.0f / sum;
-    for (int s = 0; s < T; ++s) w[t * (T + 1) + s] *= inv;
+    for (int s = lane; s < T; s += 32) wr[s] *= inv;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * ch; i += 128) {
+  sync();
+  for (int i = tid; i < T * ch; i += nthr) {
     const int t = i / ch, c = i % ch;
     float acc = 0.f;
     for (int s = 0; s < T; ++s) acc = fmaf(w[t * (T + 1) + s], v[s * ch + c], acc);
     out[((size_t)b * T + t) * C + h * ch + c] = acc;
   }
+  sync();   // the buffers may be reused for the next unit
+}
+
+__global__ void __launch_bounds__(128)
+attn_kernel(const float* __restrict__ qkv, int C, int T, int heads, float scale, float* __restrict__ out) {
+  PDL_PROLOGUE();
+  extern __shared__ __align__(16) float sm[];
+  attn_unit(qkv, C, T, heads, scale, out, (int)blockIdx.x / heads, (int)blockIdx.x % heads, sm, (int)threadIdx.x, 128,
+            [] { __syncthreads(); });
 }
 
 // first conv (1 -> 224, k=3, pad 1) and last conv (224 -> 1)
@@ -518,6 +540,456 @@ __global__ void step_advance_kernel(StepState* st) {
   st->iter += 1;
 }
 
+
+// =================================================================================================================
+// Persistent sampler: the whole reverse-diffusion loop (n_steps x ~170 ops) in ONE cooperative kernel.
+//
+// The step is latency-bound: ~170 dependent small ops on <= 256 tokens, 553 MB of weights streamed per step.  As a
+// graph of kernels every op pays a launch + ramp + drain (~13 us per node at batch 8).  Here one CTA per SM stays
+// resident, interprets the same op list, and separates ops by a grid barrier (one atomic + a spin, ~1.5 us); while a
+// CTA waits at the barrier the weight lines of its NEXT op's units are already on their way to L2.
+//   * token GEMM: same chunk -> (warp, K slice) mapping and the same summation order as conv_gemm_kernel; the K
+//     slices of a tile meet through an L2 scratch tile + a per-tile semaphore (last arriver reduces in slice order and
+//     runs the epilogue), so results are bit-identical to the cluster/DSMEM kernel and independent of the grid size.
+//   * GroupNorm / attention: two 128-thread halves per CTA work on different (batch, group|head) units (named barriers),
+//     arithmetic identical to gn_kernel / attn_kernel.
+//   * embedding linears: input rows staged in shared memory (SiLU applied once), two weight rows in flight per warp.
+//   * the DDPM update is the epilogue of the last op (each output element needs only its own x0).
+// Activations are read with plain loads after the barrier's fence (weights are immutable and may use the read-only path).
+// =================================================================================================================
+constexpr int P_MAX_KS = 16;   // most K slices per output tile in the persistent kernel
+enum { P_EMB1 = 1, P_LIN = 2, P_INCONV = 3, P_GN = 4, P_CONV = 5, P_ATTN = 6, P_OUTCONV = 7 };
+
+struct POp {
+  int type;
+  int ks, tiles_n, tiles_m;   // P_CONV: K split, tile grid
+  ConvArgs conv;
+  const float* in0;           // activations
+  const float* in1;
+  const float* w0;            // weights / bias / tables (immutable)
+  const float* w1;
+  const float* w2;
+  const int64_t* lab;
+  float* out0;
+  float* out1;
+  int i0, i1, i2, i3, i4, i5;
+  float f0;
+  int pad;
+};
+
+struct PersistArgs {
+  const POp* ops;
+  int n_emb, n_prog;          // per step: ops[0, n_emb) once, then ops[n_emb, n_emb + n_prog) once per pass
+  int n_steps, B, L, n_pass;
+  const int64_t* tmap;
+  const float* coef;
+  const float* noise;
+  long long noise_stride;
+  float guidance;
+  float* x;                   // [B][L] current sample, updated in place
+  float* x0a;                 // [B][L] first-pass prediction when n_pass == 2
+  float* partials;            // [tile][slice][32*32] K-slice partial tiles
+  unsigned* sems;             // per-tile arrival counters (zero between ops)
+  unsigned* sync;             // [0] barrier counter, [1] abort flag
+  long long* prof;            // diagnostics (may be null): [cta 0 | cta G-1][op type][body cycles, barrier cycles, count]
+};
+
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// all CTAs of the (co-resident) grid; returns false when the run was aborted (a CTA waited > ~1 s: never expected)
+__device__ __forceinline__ bool grid_barrier(unsigned* sync, unsigned& target, unsigned G, int* s_ok) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += G;
+    __threadfence();
+    atomicAdd(sync, 1u);
+    int ok = 1;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    for (;;) {
+      const unsigned v = *(volatile unsigned*)sync;
+      if ((int)(v - target) >= 0) break;
+      if ((++spins & 1023u) == 0u) {
+        if (*(volatile unsigned*)(sync + 1) != 0u || clock64() - t0 > 2000000000LL) {
+          atomicExch(sync + 1, 1u);
+          ok = 0;
+          break;
+        }
+      }
+    }
+    __threadfence();
+    *s_ok = ok;
+  }
+  __syncthreads();
+  return *s_ok != 0;
+}
+
+// ---- token GEMM units ------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void p_conv(const POp& o, float* smem, float* partials, unsigned* sems, int* s_last, int cta, int G, long long* prof) {
+  const bool pf = prof != nullptr && cta == 0 && threadIdx.x == 0;   // diagnostics: phase split of the first CTA's units
+  const ConvArgs& a = o.conv;
+  const int ks = o.ks;
+  const int n_units = o.tiles_n * o.tiles_m * ks;
+  for (int u = cta; u < n_units; u += G) {
+    const int crank = u % ks, tile = u / ks;
+    const int tn = tile % o.tiles_n, tm = tile / o.tiles_n;
+    const int n0 = tn * CT, m0 = tm * CT;
+    float acc[8][4];
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    if (pf) t0 = clock64();
+    conv_accumulate<MODE>(a, n0, m0, ks, crank, smem, acc);
+    if (pf) t1 = clock64();
+    float* part = conv_cta_partial<MODE>(acc, smem);
+    __syncthreads();
+    if (pf) t2 = clock64();
+    if (ks == 1) {
+      for (int idx = threadIdx.x; idx < CT * CT; idx += 256) {
+        float v = 0.f;
+        v += part[idx];
+        conv_store(a, m0, n0, idx, v);
+      }
+    } else {
+      float* mine = partials + ((size_t)tile * ks + crank) * (CT * CT);
+      for (int idx = threadIdx.x; idx < CT * CT; idx += 256) __stcg(mine + idx, part[idx]);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();   // release: cumulative over the CTA's stores ordered before it by the barrier above
+        const unsigned old = atomicAdd(sems + tile, 1u);
+        const int last = old == (unsigned)(ks - 1);
+        if (last) sems[tile] = 0u;   // every slice has arrived; the next use is at least one grid barrier away
+        *s_last = last;
+      }
+      __syncthreads();
+      if (pf) t3 = clock64();
+      if (*s_last) {
+        __threadfence();
+        // all K-slice partials of this thread's 4 elements are fetched first (independent L2 loads in flight together),
+        // then summed in slice order -- the order that makes the result independent of which CTA arrives last
+        const float* base = partials + (size_t)tile * ks * (CT * CT) + threadIdx.x;
+        float pv[4][P_MAX_KS];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < P_MAX_KS; ++j) pv[i][j] = j < ks ? __ldcg(base + (size_t)j * (CT * CT) + 256 * i) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v = 0.f;
+#pragma unroll
+          for (int j = 0; j < P_MAX_KS; ++j)
+            if (j < ks) v += pv[i][j];
+          conv_store(a, m0, n0, (int)threadIdx.x + 256 * i, v);
+        }
+      }
+    }
+    __syncthreads();   // the staging buffers are reused by the next unit
+    if (pf) {
+      const long long t4 = clock64();
+      prof[0] += t1 - t0;                       // chunk stream (loads + MMA)
+      prof[1] += t2 - t1;                       // warp partials -> CTA partial
+      prof[2] += ks == 1 ? 0 : t3 - t2;         // partial tile to L2 + semaphore
+      prof[24] += ks == 1 ? t4 - t2 : t4 - t3;  // slice reduction + epilogue (only when this CTA arrived last)
+      prof[25] += 1;
+    }
+  }
+}
+
+// weight lines of this CTA's units of a token-GEMM op -> L2 (hint; issued before the barrier in front of that op)
+__device__ __forceinline__ void p_conv_prefetch(const POp& o, int cta, int G) {
+  const ConvArgs& a = o.conv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ks = o.ks;
+  const int n_units = o.tiles_n * o.tiles_m * ks;
+  const int n_chunks0 = a.seg[0].taps * (a.seg[0].Cin / CT);
+  const int n_chunks = n_chunks0 + (a.nseg > 1 ? a.seg[1].taps * (a.seg[1].Cin / CT) : 0);
+  for (int u = cta; u < n_units; u += G) {
+    const int crank = u % ks, tile = u / ks;
+    const int n0 = (tile % o.tiles_n) * CT;
+    for (int f = warp * ks + crank; f < n_chunks; f += 8 * ks) {
+      const int s = f < n_chunks0 ? 0 : 1;
+      const Seg& sg = a.seg[s];
+      const int g = s ? f - n_chunks0 : f;
+      const int cpt = sg.Cin / CT;
+      const int tap = g / cpt, c = g - tap * cpt;
+      const float* wrow = sg.W + ((size_t)tap * a.N + n0 + lane) * sg.Cin + c * CT;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(wrow + CT - 1));
+    }
+  }
+}
+
+// ---- GroupNorm unit (128 threads = one half of the CTA), arithmetic of gn_kernel -------------------------------
+__device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, float* red) {
+  const int tid = threadIdx.x & 127;
+  const float* in1 = o.in0;
+  const float* in2 = o.in1;
+  const int C1 = o.i0, C2 = o.i1, T = o.i2, silu = o.i3;
+  const float* gamma = o.w0;
+  const float* beta = o.w1;
+  float* out = o.out0;
+  float* raw = o.out1;
+  const int C = C1 + C2;
+  const int cg = C / 32;
+  const int n = T * cg;
+  auto load = [&](int idx) -> float {
+    const int t = idx / cg, c = g * cg + idx % cg;
+    return c < C1 ? in1[((size_t)b * T + t) * C1 + c] : in2[((size_t)b * T + t) * C2 + (c - C1)];
+  };
+  auto block_sum = [&](float v) -> float {
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) v += __shfl_xor_sync(0xffffffffu, v, of);
+    named_bar(1 + half, 128);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    named_bar(1 + half, 128);
+    return red[0] + red[1] + red[2] + red[3];
+  };
+  float s = 0.f;
+  for (int i = tid; i < n; i += 128) s += load(i);
+  const float mean = block_sum(s) / (float)n;
+  float q = 0.f;
+  for (int i = tid; i < n; i += 128) { const float d = load(i) - mean; q += d * d; }
+  const float var = block_sum(q) / (float)n;
+  const float rstd = 1.0f / sqrtf(var + 1e-5f);
+  for (int i = tid; i < n; i += 128) {
+    const int t = i / cg, c = g * cg + i % cg;
+    const float x = load(i);
+    float y = (x - mean) * rstd * gamma[c] + beta[c];
+    if (silu) y = y / (1.0f + expf(-y));
+    const size_t oo = ((size_t)b * T + t) * C + c;
+    out[oo] = y;
+    if (raw) raw[oo] = x;
+  }
+}
+
+// ---- small-M linears: rows [mb, mb+8) staged in shared memory (xs, row stride K), two output columns per warp pass ----
+// Same per-lane k order and the same shuffle tree as linear_rows_kernel.  K <= 896 (7 float4 per lane).
+__device__ __forceinline__ void p_lin_cols(const POp& o, const float* xs, int mb, int rows, int cta, int G) {
+  const int K = o.i1, N = o.i2, out_silu = o.i4;
+  const float* W = o.w0;
+  const float* bias = o.w1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_stride = G * 8;
+  for (int nA = cta * 8 + warp; nA < N; nA += 2 * n_stride) {
+    const int nB = nA + n_stride;
+    const bool hasB = nB < N;
+    float4 wa[7], wb[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const int k = lane * 4 + 128 * i;
+      wa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      wb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K) {
+        wa[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)nA * K + k));
+        if (hasB) wb[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)nB * K + k));
+      }
+    }
+    float accA[8], accB[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { accA[r] = 0.f; accB[r] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const int k = lane * 4 + 128 * i;
+      if (k < K) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (r < rows) {
+            const float4 x = *reinterpret_cast<const float4*>(xs + r * K + k);
+            accA[r] = fmaf(x.x, wa[i].x, accA[r]); accA[r] = fmaf(x.y, wa[i].y, accA[r]);
+            accA[r] = fmaf(x.z, wa[i].z, accA[r]); accA[r] = fmaf(x.w, wa[i].w, accA[r]);
+            accB[r] = fmaf(x.x, wb[i].x, accB[r]); accB[r] = fmaf(x.y, wb[i].y, accB[r]);
+            accB[r] = fmaf(x.z, wb[i].z, accB[r]); accB[r] = fmaf(x.w, wb[i].w, accB[r]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int of = 16; of > 0; of >>= 1) {
+        accA[r] += __shfl_xor_sync(0xffffffffu, accA[r], of);
+        accB[r] += __shfl_xor_sync(0xffffffffu, accB[r], of);
+      }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int n = c ? nB : nA;
+        if (c && !hasB) break;
+        const float bv = bias[n];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (r < rows) {
+            float v = (c ? accB[r] : accA[r]) + bv;
+            if (out_silu) v = v / (1.0f + expf(-v));
+            const int row = mb + r;
+            if (o.lab) v = v + o.w2[(size_t)o.lab[row] * EMB + n];    // label_emb row (label_add_kernel)
+            if (o.in1) v = v + o.in1[(size_t)row * N + n];            // projected context (accumulating linear)
+            o.out0[(size_t)row * N + n] = v;
+            if (o.out1) o.out1[(size_t)row * N + n] = v / (1.0f + expf(-v));   // SiLU once, for the consumer
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ POp sop[2];
+  __shared__ float gn_red[2][4];
+  __shared__ int s_ok, s_last;
+  const int G = (int)gridDim.x, cta = (int)blockIdx.x, tid = (int)threadIdx.x;
+  const int half = tid >> 7;
+  const int n_ops = pa.n_emb + pa.n_prog;
+  unsigned target = 0;
+  auto fetch_op = [&](int slot, int oi) {
+    const int* src = reinterpret_cast<const int*>(pa.ops + oi);
+    int* dst = reinterpret_cast<int*>(&sop[slot]);
+    for (int i = tid; i < (int)(sizeof(POp) / sizeof(int)); i += 256) dst[i] = src[i];
+  };
+  static_assert(sizeof(POp) <= 256 * sizeof(int), "descriptor must fit one word per thread");
+  fetch_op(0, 0);
+  __syncthreads();
+  int slot = 0;
+  for (int iter = 0; iter < pa.n_steps; ++iter) {
+    const int sidx = pa.n_steps - 1 - iter;
+    for (int pass = 0; pass < pa.n_pass; ++pass) {
+      for (int oi = pass == 0 ? 0 : pa.n_emb; oi < n_ops; ++oi) {
+        // descriptor of the op after this one (same order as this loop nest)
+        int next = oi + 1;
+        bool has_next = true;
+        if (next == n_ops) {
+          if (pass + 1 < pa.n_pass) next = pa.n_emb;
+          else if (iter + 1 < pa.n_steps) next = 0;
+          else has_next = false;
+        }
+        // the next descriptor travels through a register while this op runs (its load latency stays off the critical path)
+        int next_word = 0;
+        if (has_next && tid < (int)(sizeof(POp) / sizeof(int))) next_word = reinterpret_cast<const int*>(pa.ops + next)[tid];
+        const POp& o = sop[slot];
+        const bool profiled = pa.prof != nullptr && tid == 0 && (cta == 0 || cta == G - 1);
+        long long t_op0 = 0;
+        if (profiled) t_op0 = clock64();
+        switch (o.type) {
+          case P_EMB1: {   // timestep embedding (temb_kernel) + first time_embed linear with SiLU
+            const int B = pa.B;
+            const float tf = (float)pa.tmap[sidx];
+            for (int mb = 0; mb < B; mb += 8) {
+              const int rows = B - mb < 8 ? B - mb : 8;
+              __syncthreads();
+              for (int i = tid; i < rows * (TCH / 2); i += 256) {
+                const int k = i % (TCH / 2), r = i / (TCH / 2);
+                const float c = -9.210340371976184f;
+                const float f = expf(__fdiv_rn(__fmul_rn(c, (float)k), 112.0f));
+                const float arg = __fmul_rn(tf, f);
+                smem[r * TCH + k] = cosf(arg);
+                smem[r * TCH + TCH / 2 + k] = sinf(arg);
+              }
+              __syncthreads();
+              p_lin_cols(o, smem, mb, rows, cta, G);
+            }
+            break;
+          }
+          case P_LIN: {
+            const int M = o.i0, K = o.i1, in_silu = o.i3;
+            for (int mb = 0; mb < M; mb += 8) {
+              const int rows = M - mb < 8 ? M - mb : 8;
+              __syncthreads();
+              for (int i = tid; i < rows * K; i += 256) {
+                float x = o.in0[(size_t)mb * K + i];
+                if (in_silu) x = x / (1.0f + expf(-x));
+                smem[i] = x;
+              }
+              __syncthreads();
+              p_lin_cols(o, smem, mb, rows, cta, G);
+            }
+            break;
+          }
+          case P_INCONV: {
+            const int L = o.i0, N = o.i1;
+            const int total = pa.B * L * N;
+            for (int i = cta * 256 + tid; i < total; i += G * 256) {
+              const int n = i % N, l = (i / N) % L, b = i / (N * L);
+              const float* xr = o.in0 + (size_t)b * L;
+              float acc = 0.f;
+              if (l > 0) acc = fmaf(o.w0[n], xr[l - 1], acc);
+              acc = fmaf(o.w0[N + n], xr[l], acc);
+              if (l < L - 1) acc = fmaf(o.w0[2 * N + n], xr[l + 1], acc);
+              o.out0[i] = acc + o.w1[n];
+            }
+            break;
+          }
+          case P_GN: {
+            const int n_units = pa.B * 32;
+            for (int u = cta * 2 + half; u < n_units; u += 2 * G) p_gn_unit(o, u >> 5, u & 31, half, gn_red[half]);
+            break;
+          }
+          case P_CONV:
+            p_conv<MODE>(o, smem, pa.partials, pa.sems, &s_last, cta, G, pa.prof);
+            break;
+          case P_ATTN: {   // one (batch, head) unit per CTA pass, same arithmetic as attn_kernel
+            const int heads = o.i2;
+            const int n_units = pa.B * heads;
+            for (int u = cta; u < n_units; u += G)
+              attn_unit(o.in0, o.i0, o.i1, heads, o.f0, o.out0, u / heads, u % heads, smem, tid, 256, [] { __syncthreads(); });
+            break;
+          }
+          case P_OUTCONV: {   // last conv (224 -> 1) + the DDPM update of the element it produces
+            const int C = o.i0, L = o.i1;
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int wi = cta * 8 + warp; wi < pa.B * L; wi += G * 8) {
+              const int l = wi % L, b = wi / L;
+              float acc = 0.f;
+              for (int tap = 0; tap < 3; ++tap) {
+                const int src = l + tap - 1;
+                if (src < 0 || src >= L) continue;
+                const float* ar = o.in0 + ((size_t)b * L + src) * C;
+                const float* wr = o.w0 + (size_t)tap * C;
+                for (int c = lane; c < C; c += 32) acc = fmaf(ar[c], wr[c], acc);
+              }
+#pragma unroll
+              for (int of = 16; of > 0; of >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, of);
+              if (lane == 0) {
+                float x0 = acc + o.w1[0];
+                if (pass + 1 < pa.n_pass) {
+                  pa.x0a[wi] = x0;
+                } else {
+                  if (pa.n_pass == 2) {   // classifier-free guidance replay: x0 = x0b + scale * (x0a - x0b)
+                    const float x0a = pa.x0a[wi];
+                    x0 = __fadd_rn(x0, __fmul_rn(pa.guidance, __fsub_rn(x0a, x0)));
+                  }
+                  const int ns = pa.n_steps;
+                  const float c1 = pa.coef[sidx], c2 = pa.coef[ns + sidx], sd = pa.coef[2 * ns + sidx];
+                  const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, pa.x[wi]));
+                  const float mask = sidx != 0 ? 1.0f : 0.0f;
+                  const float nz = pa.noise[(size_t)(1 + iter) * pa.noise_stride + wi];
+                  pa.x[wi] = __fadd_rn(mean, __fmul_rn(__fmul_rn(mask, sd), nz));
+                }
+              }
+            }
+            break;
+          }
+          default:
+            break;
+        }
+        if (has_next && tid < (int)(sizeof(POp) / sizeof(int))) reinterpret_cast<int*>(&sop[slot ^ 1])[tid] = next_word;
+        __syncthreads();
+        if (has_next && sop[slot ^ 1].type == P_CONV) p_conv_prefetch(sop[slot ^ 1], cta, G);
+        long long t_op1 = 0;
+        if (profiled) t_op1 = clock64();
+        if (!grid_barrier(pa.sync, target, (unsigned)G, &s_ok)) return;
+        if (profiled) {
+          long long* pr = pa.prof + ((cta == 0 ? 0 : 8) + sop[slot].type) * 3;
+          pr[0] += t_op1 - t_op0;
+          pr[1] += clock64() - t_op1;
+          pr[2] += 1;
+        }
+        slot ^= 1;
+      }
+    }
+  }
+}
+
 }  // namespace surfd
 
 using namespace surfd;
@@ -543,14 +1015,21 @@ using namespace surfd;
     SURFD_CHECK_LAUNCH();                                                                                 \
   } while (0)
 
-// per-warp A/W staging (8 warps x 2 x 32 x 36 floats) is reused for the 8 x 32 x 33 warp partials; + the 32x32 CTA partial
-static constexpr int CONV_SMEM = (8 * 2 * CT * CTP + CT * CT) * (int)sizeof(float);
+// per-warp A/W staging (8 warps x CONV_STAGES x 2 x 32 x 36 floats); its first part is reused for the 8 x 32 x 33 warp
+// partials, followed (at 8*32*33 floats) by the 32x32 CTA partial
+static constexpr int CONV_SMEM = (8 * CONV_STAGES * 2 * CT * CTP) * (int)sizeof(float);
+static_assert(8 * CONV_STAGES * 2 * CT * CTP >= 8 * CT * 33 + CT * CT, "reduction scratch must fit in the staging area");
 
 // One lane = private activation pool + step state + captured step graph + stream.  The denoiser is latency-bound (about 170
 // dependent small kernels per step on <= 256 tokens), so a batch is split over lanes that run concurrently on their own
 // streams; the weights are shared.
 struct Lane {
   DevBuf pool, emb_all, temb, e1, emb, t_cur, x0a, x0b, xcur, state;
+  // persistent sampler: op descriptors, K-slice scratch, semaphores, barrier word + abort flag
+  DevBuf emb_silu, ctxv, p_ops, p_partials, p_sems, p_sync, p_prof;
+  int p_B = -1, p_n_emb = 0, p_n_prog = 0, p_smem = 0, p_grid = 0, p_split = -1;
+  const float* p_ctx = nullptr;
+  const int64_t* p_lab = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   int cap = 0;   // batch capacity of the buffers
@@ -571,6 +1050,8 @@ struct Lane {
     graph_exec = nullptr;
     pool.release(); emb_all.release(); temb.release(); e1.release(); emb.release(); t_cur.release(); x0a.release(); x0b.release();
     xcur.release(); state.release();
+    emb_silu.release(); ctxv.release(); p_ops.release(); p_partials.release(); p_sems.release(); p_sync.release(); p_prof.release();
+    p_B = -1;
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
     stream = nullptr; done = nullptr;
@@ -580,6 +1061,14 @@ struct Lane {
 struct surfd_unet {
   int L = 0, max_batch = 0;
   bool pdl = true;     // programmatic dependent launch between the step's kernels (falls back to false if capture rejects it)
+  int sampler = 1;     // surfd_sample: 1 = persistent cooperative kernel (default), 0 = CUDA-graph replay of the step
+  int sampler_sms = 0; // CTAs of the persistent kernel (0 = one per SM)
+  bool profile = false; // persistent kernel: per-op-type cycle counters (diagnostics)
+  int persist_split = 1; // token-GEMM K split of the persistent kernel: 0 = the graph path's rule (bit-identical samples),
+                         // 1 = as many slices as fit in ONE round of the resident CTAs (faster; same fp32-class accuracy)
+  int num_sms = 0;
+  bool coop = false;
+  unsigned* h_abort = nullptr;   // pinned: abort flag of the last persistent run
   int precision = 1;   // token GEMMs: 0 fp32 FFMA, 1 3xTF32 mma.sync (fp32-class accuracy, default), 2 single-pass TF32
   DevBuf weights;
   std::vector<int64_t> hdr, buf_sizes;
@@ -609,6 +1098,9 @@ static int lane_init(surfd_unet* u, Lane& ln, int cap) {
   SURFD_TRY(ln.x0b.reserve(B * u->L * sizeof(float)));
   SURFD_TRY(ln.xcur.reserve(B * u->L * sizeof(float)));
   SURFD_TRY(ln.state.reserve(sizeof(StepState)));
+  SURFD_TRY(ln.emb_silu.reserve(B * EMB * sizeof(float)));
+  SURFD_TRY(ln.ctxv.reserve(B * EMB * sizeof(float)));
+  ln.p_B = -1;
   if (!ln.stream) SURFD_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
   if (!ln.done) SURFD_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
   return 0;
@@ -665,6 +1157,15 @@ extern "C" int surfd_unet_create(const float* packed, size_t n_floats, const int
   if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
   ce = cudaEventCreateWithFlags(&u->fork, cudaEventDisableTiming);
   if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
+  {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) u->num_sms = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess) u->coop = v != 0;
+    ce = cudaHostAlloc(&u->h_abort, sizeof(unsigned), cudaHostAllocDefault);
+    if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
+    *u->h_abort = 0u;
+  }
   // measured on B200 (B=8, L=32): 1 lane 2.6 ms/step, 8 concurrent lanes 5.6 ms/step -- many tiny cluster launches from
   // several streams contend in the front end, so the default is a single lane; set_lanes() stays for experiments.
   if ((st = surfd_unet_set_lanes(u, 1))) return fail(st);
@@ -677,6 +1178,7 @@ extern "C" void surfd_unet_destroy(surfd_unet* u) {
   cudaDeviceSynchronize();
   for (auto& ln : u->lanes) ln.release();
   if (u->fork) cudaEventDestroy(u->fork);
+  if (u->h_abort) cudaFreeHost(u->h_abort);
   u->weights.release();
   delete u;
 }
@@ -742,7 +1244,7 @@ static int unet_run(surfd_unet* u, Lane& ln, int B, const float* x, const int64_
         const int C = (int)r[2], T = (int)r[3], heads = (int)r[5];
         const int ch = C / heads;
         const float scale = (float)(1.0 / sqrt(sqrt((double)ch)));
-        const size_t smem = ((size_t)3 * T * ch + (size_t)T * (T + 1)) * sizeof(float);
+        const size_t smem = (size_t)attn_smem_floats(T, ch) * sizeof(float);
         UNET_LAUNCH(u->pdl, attn_kernel, dim3((unsigned)(B * heads)), dim3(128), smem, st, 0, ln.buf(r[1]), C, T, heads, scale, ln.buf(r[4]));
         break;
       }
@@ -779,12 +1281,218 @@ static int record_step(surfd_unet* u, Lane& ln, int B, const int64_t* tmap, cons
   return 0;
 }
 
+// ---- persistent sampler (host side) ---------------------------------------------------------------------------------
+extern "C" int surfd_unet_set_sampler(surfd_unet* u, int mode, int n_sms) {
+  SURFD_REQUIRE(u != nullptr && mode >= 0 && mode <= 2, "sampler mode must be 0 (graph replay), 1 (persistent kernel) or 2 (persistent, graph-identical K split)");
+  SURFD_REQUIRE(n_sms >= 0, "n_sms must be >= 0 (0 = one CTA per SM)");
+  u->sampler = mode ? 1 : 0;
+  u->persist_split = mode == 2 ? 0 : 1;
+  u->sampler_sms = n_sms;
+  return 0;
+}
+
+// Diagnostics: enable (out == NULL, on != 0) / disable per-op-type cycle counters of the persistent sampler, or read the
+// counters of the last run (out != NULL): out[(half * 8 + op type) * 3 + {0 body cycles, 1 barrier cycles, 2 count}],
+// half 0 = first CTA, half 1 = last CTA.  Synchronises the device when reading.
+extern "C" int surfd_unet_profile(surfd_unet* u, int on, int64_t* out) {
+  SURFD_REQUIRE(u != nullptr, "null argument");
+  if (!out) { u->profile = on != 0; return 0; }
+  SURFD_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < 48; ++i) out[i] = 0;
+  if (u->lanes[0].p_prof.p) SURFD_CUDA(cudaMemcpy(out, u->lanes[0].p_prof.p, 48 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int surfd_unet_status(surfd_unet* u) {
+  SURFD_REQUIRE(u != nullptr, "null argument");
+  if (u->h_abort && *u->h_abort != 0u)
+    return set_error(SURFD_ABORTED, "persistent sampler aborted: a grid barrier timed out", __FILE__, __LINE__);
+  return 0;
+}
+
+template <int MODE>
+static int persist_launch(const PersistArgs& pa, int grid, int smem, cudaStream_t st) {
+  SURFD_CUDA(cudaFuncSetAttribute(unet_persistent_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  PersistArgs args = pa;
+  void* kargs[] = {&args};
+  SURFD_CUDA(cudaLaunchCooperativeKernel((void*)unet_persistent_kernel<MODE>, dim3((unsigned)grid), dim3(256), kargs, (size_t)smem, st));
+  g_launch_count += 1;
+  return 0;
+}
+
+template <int MODE>
+static int persist_max_grid(int smem, int num_sms, int* out) {
+  SURFD_CUDA(cudaFuncSetAttribute(unet_persistent_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int per_sm = 0;
+  SURFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, unet_persistent_kernel<MODE>, 256, (size_t)smem));
+  *out = per_sm * num_sms;
+  return 0;
+}
+
+// op descriptors for batch B on lane `ln` (cached per (B, ctx, lab))
+static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const int64_t* lab, int grid) {
+  if (ln.p_B == B && ln.p_ctx == ctx && ln.p_lab == lab && ln.p_grid == grid && ln.p_split == u->persist_split) return 0;
+  const auto& h = u->hdr;
+  std::vector<POp> ops;
+  auto blank = [](int type) { POp o; memset(&o, 0, sizeof(o)); o.type = type; return o; };
+  {
+    POp o = blank(P_EMB1);   // e1 = SiLU(W1 temb(t) + b1)
+    o.w0 = u->w(h[5]); o.w1 = u->w(h[6]); o.i0 = B; o.i1 = TCH; o.i2 = EMB; o.i4 = 1; o.out0 = ln.e1.as<float>();
+    ops.push_back(o);
+  }
+  {
+    POp o = blank(P_LIN);    // emb = W2 e1 + b2 (+ label row) (+ projected context); also SiLU(emb) for the next op
+    o.in0 = ln.e1.as<float>(); o.i0 = B; o.i1 = EMB; o.i2 = EMB; o.w0 = u->w(h[7]); o.w1 = u->w(h[8]);
+    if (lab) {
+      SURFD_REQUIRE(h[11] >= 0, "labels given but the checkpoint has no label_emb");
+      o.lab = lab; o.w2 = u->w(h[11]);
+    }
+    if (ctx) o.in1 = ln.ctxv.as<float>();
+    o.out0 = ln.emb.as<float>(); o.out1 = ln.emb_silu.as<float>();
+    ops.push_back(o);
+  }
+  {
+    POp o = blank(P_LIN);    // all 22 emb_layers at once
+    o.in0 = ln.emb_silu.as<float>(); o.i0 = B; o.i1 = EMB; o.i2 = u->emb_cols; o.w0 = u->w(h[3]); o.w1 = u->w(h[4]);
+    o.out0 = ln.emb_all.as<float>();
+    ops.push_back(o);
+  }
+  const int n_emb = (int)ops.size();
+  size_t max_partial_tiles = 0, max_tiles = 1;
+  int smem_floats = CONV_SMEM / (int)sizeof(float);
+  if (smem_floats < 8 * EMB) smem_floats = 8 * EMB;
+  for (const auto& r : u->prog) {
+    switch (r[0]) {
+      case OP_INCONV: {
+        POp o = blank(P_INCONV);
+        o.in0 = ln.xcur.as<float>(); o.i0 = (int)r[3]; o.i1 = (int)r[2]; o.w0 = u->w(r[4]); o.w1 = u->w(r[5]); o.out0 = ln.buf(r[1]);
+        ops.push_back(o);
+        break;
+      }
+      case OP_GN: {
+        POp o = blank(P_GN);
+        o.in0 = ln.buf(r[1]); o.i0 = (int)r[2]; o.in1 = r[3] >= 0 ? ln.buf(r[3]) : nullptr; o.i1 = (int)r[4]; o.i2 = (int)r[5];
+        o.i3 = (int)r[8]; o.w0 = u->w(r[9]); o.w1 = u->w(r[10]); o.out0 = ln.buf(r[6]); o.out1 = r[7] >= 0 ? ln.buf(r[7]) : nullptr;
+        ops.push_back(o);
+        break;
+      }
+      case OP_CONV: {
+        POp o = blank(P_CONV);
+        ConvArgs& a = o.conv;
+        a.out = ln.buf(r[1]); a.N = (int)r[2]; a.T_out = (int)r[3]; a.nseg = (int)r[4]; a.B = B;
+        int chunks = 0;
+        for (int s = 0; s < a.nseg; ++s) {
+          const int64_t* q = &r[5 + 7 * s];
+          a.seg[s].A = ln.buf(q[0]); a.seg[s].Cin = (int)q[1]; a.seg[s].taps = (int)q[2]; a.seg[s].stride = (int)q[3];
+          a.seg[s].up = (int)q[4]; a.seg[s].T_in = (int)q[5]; a.seg[s].W = u->w(q[6]);
+          chunks += a.seg[s].taps * (a.seg[s].Cin / CT);
+        }
+        a.bias = u->w(r[19]);
+        a.emb = r[20] >= 0 ? ln.emb_all.as<float>() + r[20] : nullptr;
+        a.emb_ld = u->emb_cols;
+        a.residual = r[21] >= 0 ? ln.buf(r[21]) : nullptr;
+        // same K-split rule as the graph path (decided per sample, so results do not depend on B)
+        const int tiles = (a.N / CT) * (int)cdiv((int64_t)a.T_out, CT);
+        int ksplit = 1;
+        o.tiles_n = a.N / CT; o.tiles_m = (int)cdiv((int64_t)B * a.T_out, CT);
+        const size_t nt = (size_t)o.tiles_n * o.tiles_m;
+        if (u->persist_split == 0) {
+          while (ksplit < KSPLIT && tiles * ksplit < 148 && chunks >= 16 * (ksplit * 2)) ksplit *= 2;
+        } else {
+          // one round: every (tile, slice) unit gets its own CTA (any slice count, not only powers of two); a slice
+          // keeps at least one chunk per warp
+          ksplit = (int)((int64_t)grid / (int64_t)nt);
+          if (ksplit > chunks / 8) ksplit = chunks / 8;
+          if (ksplit > P_MAX_KS) ksplit = P_MAX_KS;
+          if (ksplit < 1) ksplit = 1;
+        }
+        o.ks = ksplit;
+        if (nt > max_tiles) max_tiles = nt;
+        if (ksplit > 1 && nt * ksplit > max_partial_tiles) max_partial_tiles = nt * ksplit;
+        ops.push_back(o);
+        break;
+      }
+      case OP_ATTN: {
+        POp o = blank(P_ATTN);
+        const int C = (int)r[2], T = (int)r[3], heads = (int)r[5];
+        const int ch = C / heads;
+        o.in0 = ln.buf(r[1]); o.i0 = C; o.i1 = T; o.i2 = heads; o.i3 = attn_smem_floats(T, ch);
+        o.f0 = (float)(1.0 / sqrt(sqrt((double)ch)));
+        o.out0 = ln.buf(r[4]);
+        if (o.i3 > smem_floats) smem_floats = o.i3;
+        ops.push_back(o);
+        break;
+      }
+      case OP_OUTCONV: {
+        POp o = blank(P_OUTCONV);
+        o.in0 = ln.buf(r[1]); o.i0 = (int)r[2]; o.i1 = (int)r[3]; o.w0 = u->w(r[4]); o.w1 = u->w(r[5]);
+        ops.push_back(o);
+        break;
+      }
+      default:
+        return set_error(SURFD_BAD_ARGUMENT, "unknown op in program", __FILE__, __LINE__);
+    }
+  }
+  SURFD_TRY(ln.p_ops.reserve(ops.size() * sizeof(POp)));
+  SURFD_CUDA(cudaMemcpy(ln.p_ops.p, ops.data(), ops.size() * sizeof(POp), cudaMemcpyHostToDevice));
+  SURFD_TRY(ln.p_partials.reserve((max_partial_tiles ? max_partial_tiles : 1) * CT * CT * sizeof(float)));
+  SURFD_TRY(ln.p_sems.reserve(max_tiles * sizeof(unsigned)));
+  SURFD_TRY(ln.p_sync.reserve(2 * sizeof(unsigned)));
+  SURFD_TRY(ln.p_prof.reserve(48 * sizeof(long long)));
+  SURFD_CUDA(cudaMemset(ln.p_sems.p, 0, max_tiles * sizeof(unsigned)));
+  ln.p_n_emb = n_emb; ln.p_n_prog = (int)ops.size() - n_emb; ln.p_smem = smem_floats * (int)sizeof(float);
+  ln.p_B = B; ln.p_ctx = ctx; ln.p_lab = lab; ln.p_grid = grid; ln.p_split = u->persist_split;
+  return 0;
+}
+
+static int sample_persistent(surfd_unet* u, int B, int n_steps, const int64_t* tmap_dev, const float* coef_dev, const float* noise_dev,
+                             const float* ctx, const int64_t* lab, float guidance, float* out_dev, cudaStream_t st) {
+  Lane& ln = u->lanes[0];
+  SURFD_REQUIRE(B <= ln.cap, "lane capacity exceeded");
+  SURFD_TRY(surfd_unet_status(u));
+  const int L = u->L;
+  int grid = u->sampler_sms > 0 ? u->sampler_sms : u->num_sms;
+  if (grid > u->num_sms) grid = u->num_sms;     // one CTA per SM (234 registers x 256 threads)
+  SURFD_TRY(persist_build(u, ln, B, ctx, lab, grid));
+  int max_grid = 0;
+  if (u->precision == 0) SURFD_TRY(persist_max_grid<0>(ln.p_smem, u->num_sms, &max_grid));
+  else if (u->precision == 1) SURFD_TRY(persist_max_grid<1>(ln.p_smem, u->num_sms, &max_grid));
+  else SURFD_TRY(persist_max_grid<2>(ln.p_smem, u->num_sms, &max_grid));
+  SURFD_REQUIRE(max_grid >= grid, "persistent sampler kernel: the requested CTAs cannot all be resident");
+  SURFD_CUDA(cudaMemcpyAsync(ln.xcur.p, noise_dev, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, st));   // x_T = noise row 0
+  SURFD_CUDA(cudaMemsetAsync(ln.p_sync.p, 0, 2 * sizeof(unsigned), st));
+  if (ctx) {   // projected context: constant over the loop, computed once (the graph path accumulates it every step)
+    const dim3 g1((unsigned)cdiv(EMB, 8), (unsigned)cdiv(B, 8));
+    const auto& h = u->hdr;
+    UNET_LAUNCH(false, linear_rows_kernel, dim3(g1), dim3(256), 0, st, 0, ctx, B, CTX, u->w(h[9]), u->w(h[10]), EMB, 0, 0, 0, ln.ctxv.as<float>());
+  }
+  PersistArgs pa{};
+  pa.ops = ln.p_ops.as<POp>(); pa.n_emb = ln.p_n_emb; pa.n_prog = ln.p_n_prog;
+  pa.n_steps = n_steps; pa.B = B; pa.L = L; pa.n_pass = guidance != 1.0f ? 2 : 1;
+  pa.tmap = tmap_dev; pa.coef = coef_dev; pa.noise = noise_dev; pa.noise_stride = (long long)B * L; pa.guidance = guidance;
+  pa.x = ln.xcur.as<float>(); pa.x0a = ln.x0a.as<float>();
+  pa.partials = ln.p_partials.as<float>(); pa.sems = ln.p_sems.as<unsigned>(); pa.sync = ln.p_sync.as<unsigned>();
+  pa.prof = nullptr;
+  if (u->profile) {
+    SURFD_CUDA(cudaMemsetAsync(ln.p_prof.p, 0, 48 * sizeof(long long), st));
+    pa.prof = ln.p_prof.as<long long>();
+  }
+  if (u->precision == 0) SURFD_TRY(persist_launch<0>(pa, grid, ln.p_smem, st));
+  else if (u->precision == 1) SURFD_TRY(persist_launch<1>(pa, grid, ln.p_smem, st));
+  else SURFD_TRY(persist_launch<2>(pa, grid, ln.p_smem, st));
+  SURFD_CUDA(cudaMemcpyAsync(u->h_abort, ln.p_sync.as<unsigned>() + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  SURFD_CUDA(cudaMemcpyAsync(out_dev, ln.xcur.p, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 extern "C" int surfd_sample(surfd_unet* u, int B, int n_steps, const int64_t* tmap_dev, const float* coef_dev, const float* noise_dev,
                             const float* context_dev, const int64_t* labels_dev, float guidance, float* out_dev, void* stream) {
   SURFD_REQUIRE(u && tmap_dev && coef_dev && noise_dev && out_dev, "null argument");
   SURFD_REQUIRE(B >= 1 && B <= u->max_batch, "batch exceeds max_batch");
   SURFD_REQUIRE(n_steps >= 1, "n_steps must be positive");
   cudaStream_t st = (cudaStream_t)stream;
+  if (u->sampler == 1 && u->coop)
+    return sample_persistent(u, B, n_steps, tmap_dev, coef_dev, noise_dev, context_dev, labels_dev, guidance, out_dev, st);
   const int L = u->L;
   const int n_lanes = (int)u->lanes.size() < B ? (int)u->lanes.size() : B;
   const int64_t stride = (int64_t)B * L;

@@ -27,6 +27,7 @@ class SurfDPipeline:
         budget = max(1, n_sms - mc_parallel)
         self.decoder = UdfDecoder(ae_state, latent_dim, device=device, packed=packed_decoder, max_chunk_points=budget * 256)
         self.decoder.set_sm_budget(budget)
+        self.sampler.set_sampler(1, budget)   # the persistent sampler kernel also leaves the replays' SMs alone (generate_many)
         self.mcs = [MarchingCubes(device) for _ in range(mc_parallel)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(mc_parallel)]
         self.schedule_cache = {}
@@ -41,61 +42,122 @@ class SurfDPipeline:
     def sample_latents(self, noise, context=None, labels=None, guidance=1.0, n_steps=1000, noise_schedule="cosine"):
         return self.sampler.sample(self.schedule(n_steps, noise_schedule), noise, context, labels, guidance)
 
+    def _launch_fields(self, wave, latents, N, use_fast_grid_filler, max_dist, marks):
+        """lattice of every shape of `wave` on the current stream; each shape's marching cubes starts on its side stream
+        as soon as its lattice is complete"""
+        dec = self.decoder
+        main = torch.cuda.current_stream(self.device)
+        fields = {}
+        for j, k in enumerate(wave):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(main)
+            dec.set_latent(latents[k])
+            udf, grads, counts = dec.lattice(N, use_fast_grid_filler=use_fast_grid_filler, max_dist=max_dist)
+            udf.clamp_(min=0)                                    # udf[udf < 0] = 0  (meshudf.py:342)
+            e1.record(main)
+            marks.append((e0, e1))
+            fields[k] = (udf, grads, counts)
+            self.streams[j].wait_event(e1)
+            self.mcs[j].launch(udf, grads, self.streams[j])
+        return fields
+
+    def _finish_fields(self, wave, latents, N, fields, meshes, stats, marks):
+        """wait for each shape's replay, then mesh assembly + UDF face filter on the current stream"""
+        dec = self.decoder
+        main = torch.cuda.current_stream(self.device)
+        for j, k in enumerate(wave):
+            udf, grads, counts = fields[k]
+            res = self.mcs[j].finish()
+            while res is None:                                   # buffers were grown: run this shape again
+                self.mcs[j].launch(udf, grads, self.streams[j])
+                res = self.mcs[j].finish()
+            verts_raw, faces_raw = res
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(main)
+            vertices, faces = finish_mesh(verts_raw, faces_raw, N)
+            dec.set_latent(latents[k])
+            keep = dec.face_filter(vertices, faces, N)
+            faces_kept = faces[keep.bool()]
+            e1.record(main)
+            marks.append((e0, e1, "f"))
+            meshes[k] = (vertices.to(torch.float32), faces_kept.to(torch.int64))
+            stats[k] = dict(n_udf=counts[0], n_grad=counts[1], n_verts=int(vertices.shape[0]), n_faces_mc=int(faces.shape[0]),
+                            n_faces=int(faces_kept.shape[0]), **self.mcs[j].last_stats)
+            del fields[k]
+
+    def _account(self, marks, timings):
+        if timings is None:
+            return
+        torch.cuda.synchronize(self.device)
+        for m in marks:
+            key = "filter_s" if len(m) == 3 else "lattice_s"
+            timings[key] = timings.get(key, 0.0) + m[0].elapsed_time(m[1]) / 1e3
+
     def extract(self, latents, N, use_fast_grid_filler=True, max_dist=0.1, timings=None):
         """latents [B,1,L] (device) -> list of (verts float32 [V,3], faces int64 [F,3]) + per-shape stats"""
         B = latents.shape[0]
-        dec = self.decoder
         P = len(self.mcs)
         meshes, stats = [None] * B, [None] * B
-        main = torch.cuda.current_stream(self.device)
-        ev = lambda: torch.cuda.Event(enable_timing=True)
-        t_lat = t_filter = 0.0
+        marks = []
         for w0 in range(0, B, P):
             wave = list(range(w0, min(B, w0 + P)))
-            fields = {}
-            marks = []
-            for j, k in enumerate(wave):
-                e0, e1 = ev(), ev()
-                e0.record(main)
-                dec.set_latent(latents[k])
-                udf, grads, counts = dec.lattice(N, use_fast_grid_filler=use_fast_grid_filler, max_dist=max_dist)
-                udf.clamp_(min=0)                                    # udf[udf < 0] = 0  (meshudf.py:342)
-                e1.record(main)
-                marks.append((e0, e1))
-                fields[k] = (udf, grads, counts)
-                self.streams[j].wait_event(e1)
-                self.mcs[j].launch(udf, grads, self.streams[j])
-            for j, k in enumerate(wave):
-                udf, grads, counts = fields[k]
-                res = self.mcs[j].finish()
-                while res is None:                                   # buffers were grown: run this shape again
-                    self.mcs[j].launch(udf, grads, self.streams[j])
-                    res = self.mcs[j].finish()
-                verts_raw, faces_raw = res
-                e0, e1 = ev(), ev()
-                e0.record(main)
-                vertices, faces = finish_mesh(verts_raw, faces_raw, N)
-                dec.set_latent(latents[k])
-                keep = dec.face_filter(vertices, faces, N)
-                faces_kept = faces[keep.bool()]
-                e1.record(main)
-                marks.append((e0, e1, "f"))
-                meshes[k] = (vertices.to(torch.float32), faces_kept.to(torch.int64))
-                stats[k] = dict(n_udf=counts[0], n_grad=counts[1], n_verts=int(vertices.shape[0]), n_faces_mc=int(faces.shape[0]),
-                                n_faces=int(faces_kept.shape[0]), **self.mcs[j].last_stats)
-                del fields[k]
-            if timings is not None:
-                torch.cuda.synchronize(self.device)
-                for m in marks:
-                    dt = m[0].elapsed_time(m[1]) / 1e3
-                    if len(m) == 3:
-                        t_filter += dt
-                    else:
-                        t_lat += dt
-        if timings is not None:
-            timings["lattice_s"] = timings.get("lattice_s", 0.0) + t_lat
-            timings["filter_s"] = timings.get("filter_s", 0.0) + t_filter
+            fields = self._launch_fields(wave, latents, N, use_fast_grid_filler, max_dist, marks)
+            self._finish_fields(wave, latents, N, fields, meshes, stats, marks)
+        self._account(marks, timings)
         return meshes, stats
+
+    def generate_many(self, noises, N, contexts=None, labels=None, guidance=1.0, n_steps=1000, use_fast_grid_filler=True,
+                      noise_schedule="cosine", timings=None, to_host=False, io=None):
+        """Several independent batches, software-pipelined on one GPU: while batch i's marching-cubes replays (one warp
+        each, latency-bound) run on their side streams, the sampler of batch i+1 already runs on the main stream; batch
+        i's face filters follow it.  Each batch must fit one wave (B <= mc_parallel).
+        noises: list of [n_steps+1, B, L] tensors, on the device or in (pinned) host memory -- host tensors are copied
+        inside the loop, just before their sampler is launched.  to_host=True also copies every batch's latents/meshes
+        to host memory as soon as they are complete.  `io` (dict) accumulates h2d/d2h byte counts.
+        Returns a list of (latents, meshes, stats)."""
+        K = len(noises)
+        P = len(self.mcs)
+        get = lambda seq, i: None if seq is None else seq[i]
+        io = io if io is not None else {}
+
+        def dev(t):
+            if t is None or t.is_cuda:
+                return t
+            io["h2d"] = io.get("h2d", 0) + t.numel() * t.element_size()
+            return t.to(self.device, non_blocking=True)
+
+        def host(lat, meshes):
+            outm = []
+            for v, f in meshes:
+                vc, fc = v.cpu(), f.cpu()
+                io["d2h"] = io.get("d2h", 0) + vc.numel() * vc.element_size() + fc.numel() * fc.element_size()
+                outm.append((vc, fc))
+            latc = lat.cpu()
+            io["d2h"] = io.get("d2h", 0) + latc.numel() * latc.element_size()
+            return latc, outm
+
+        def sample(i):
+            return self.sample_latents(dev(noises[i]), dev(get(contexts, i)), dev(get(labels, i)), guidance, n_steps, noise_schedule)
+
+        out, marks = [], []
+        if any(n.shape[1] > P for n in noises):            # more shapes than replay slots: one batch after the other
+            for i in range(K):
+                lat = sample(i)
+                meshes, stats = self.extract(lat, N, use_fast_grid_filler, timings=timings)
+                out.append(host(lat, meshes) + (stats,) if to_host else (lat, meshes, stats))
+            return out
+        lat = sample(0)
+        for i in range(K):
+            B = lat.shape[0]
+            wave = list(range(B))
+            fields = self._launch_fields(wave, lat, N, use_fast_grid_filler, 0.1, marks)
+            lat_next = sample(i + 1) if i + 1 < K else None
+            meshes, stats = [None] * B, [None] * B
+            self._finish_fields(wave, lat, N, fields, meshes, stats, marks)
+            out.append(host(lat, meshes) + (stats,) if to_host else (lat, meshes, stats))
+            lat = lat_next
+        self._account(marks, timings)
+        return out
 
     def generate(self, noise, N, context=None, labels=None, guidance=1.0, n_steps=1000, use_fast_grid_filler=True,
                  noise_schedule="cosine", timings=None):

@@ -374,6 +374,27 @@ class UNetSampler:
         """number of concurrent sampler streams a batch is split over (default min(8, max_batch))"""
         _lib.check(self.lib.surfd_unet_set_lanes(self._h, int(n)))
 
+    def set_sampler(self, mode, n_sms=0):
+        """sample() engine: 1 = persistent cooperative kernel (default; `n_sms` CTAs, 0 = one per SM), 2 = the same with the
+        graph path's K split (bit-identical to mode 0), 0 = CUDA-graph replay of the step kernels"""
+        _lib.check(self.lib.surfd_unet_set_sampler(self._h, int(mode), int(n_sms)))
+
+    def profile(self, on=None):
+        """on=True/False: switch the persistent kernel's cycle counters; on=None: read the last run's counters as
+        {cta: {op: (body_cycles, barrier_cycles, count)}} -- diagnostics"""
+        if on is not None:
+            _lib.check(self.lib.surfd_unet_profile(self._h, int(bool(on)), None))
+            return None
+        buf = (ctypes.c_int64 * 48)()
+        _lib.check(self.lib.surfd_unet_profile(self._h, 0, buf))
+        self.last_gemm_phases = dict(chunk_stream=buf[0], cta_partial=buf[1], publish=buf[2], reduce_epilogue=buf[24], units=buf[25])
+        names = {1: "emb1", 2: "linear", 3: "inconv", 4: "groupnorm", 5: "token_gemm", 6: "attention", 7: "outconv+update"}
+        return {("first_cta", "last_cta")[h]: {names[o]: tuple(buf[(h * 8 + o) * 3 + i] for i in range(3)) for o in names} for h in range(2)}
+
+    def status(self):
+        """raises if the last persistent sample() aborted (call after synchronising its stream)"""
+        _lib.check(self.lib.surfd_unet_status(self._h))
+
     def forward(self, x, t, context=None, labels=None):
         """x [B,1,L], t [B] int64 (original-process timesteps) -> model output [B,1,L]  (MDM.forward)"""
         B = x.shape[0]

@@ -89,3 +89,48 @@ def test_hundred_step_trajectory_stays_close_to_oracle():
         ref = UO.p_sample_loop(sd, S, noise)
     assert torch.isfinite(r).all()
     assert float((r.cpu() - ref).abs().max()) < 1e-2
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
+def test_persistent_sampler_is_bit_identical_to_graph_replay(case):
+    """surfd_sample's two engines (one cooperative persistent kernel / CUDA-graph replay of the step kernels) share the
+    chunk -> warp mapping and every summation order, so they must agree bit for bit -- for every conditioning mode, with
+    the CFG double pass, for ragged batches, and for any number of resident CTAs."""
+    tag, L, cond = case
+    gen = torch.Generator().manual_seed(11)
+    net = U.UNetSampler(synth.synth_mdm(L, cond), L, cond, max_batch=8)
+    S = U.SpacedSchedule(U.cosine_betas(), U.space_timesteps(1000, [6]))
+    for B, guidance in ((8, 1.0), (3, 2.5 if cond == "img" else 1.0), (1, 1.0)):
+        noise = torch.randn(7, B, L, generator=gen)
+        ctx = torch.randn(B, 512, generator=gen) if cond == "img" else None
+        lab = torch.randint(0, 9, (B,), generator=gen) if cond == "category" else None
+        net.set_sampler(0)
+        ref = net.sample(S, noise, ctx, lab, guidance)
+        net.set_sampler(2)
+        out = net.sample(S, noise, ctx, lab, guidance)
+        torch.cuda.synchronize(); net.status()
+        assert torch.isfinite(out).all()
+        assert torch.equal(out, ref), (tag, B, float((out - ref).abs().max()))
+        net.set_sampler(2, 61)          # fewer (and an odd number of) CTAs: same bits
+        out2 = net.sample(S, noise, ctx, lab, guidance)
+        torch.cuda.synchronize(); net.status()
+        assert torch.equal(out2, ref), (tag, B, "61 CTAs", float((out2 - ref).abs().max()))
+        for n_sms in (0, 140):          # default engine: one-round K split, fp32-rounding-level differences only
+            net.set_sampler(1, n_sms)
+            out3 = net.sample(S, noise, ctx, lab, guidance)
+            torch.cuda.synchronize(); net.status()
+            assert float((out3 - ref).abs().max()) < 2e-4, (tag, B, n_sms, float((out3 - ref).abs().max()))
+        net.set_sampler(1, 0)
+
+
+@pytest.mark.parametrize("mode", [0, 2], ids=["fp32-ffma", "tf32-mma"])
+def test_persistent_sampler_precision_modes(mode):
+    L = 32
+    net = U.UNetSampler(synth.synth_mdm(L), L, max_batch=8)
+    net.set_precision(mode)
+    S = U.SpacedSchedule(U.cosine_betas(), U.space_timesteps(1000, [4]))
+    noise = torch.randn(5, 8, L, generator=torch.Generator().manual_seed(5))
+    net.set_sampler(0); ref = net.sample(S, noise)
+    net.set_sampler(2); out = net.sample(S, noise)
+    torch.cuda.synchronize(); net.status()
+    assert torch.equal(out, ref), float((out - ref).abs().max())
