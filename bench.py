@@ -189,11 +189,16 @@ def bench_gpu(args):
     pipe.generate(noise_dev, RES, n_steps=STEPS_DDPM, timings=tm)
     stats = last["stats"]
 
-    # ---- roofline of the dominant kernel: the decoder's 512x512 layer GEMM, timed live in isolation ----
+    # ---- roofline of the decoder's 512x512 layer GEMM (the kernel SURVEY.md 8(d) names), measured live INSIDE the real
+    # layer chain: one more extraction of a full batch with a CUDA event pair around every launch of that kernel ----
     pk = peaks()
-    ms_layer, m_layer = pipe.decoder.time_layer(iters=20)
-    flops_layer = 2.0 * m_layer * 512 * 512
-    achieved = flops_layer / (ms_layer * 1e-3) / 1e12
+    lat_last = pipe.sample_latents(noise_dev, n_steps=10)          # any latents do; the extraction is what is measured
+    pipe.decoder.profile(True)
+    pipe.extract(lat_last, RES)
+    n_launch, n_rows, ms_total = pipe.decoder.profile(False)
+    flops_total = 2.0 * n_rows * 512 * 512
+    achieved = flops_total / (ms_total * 1e-3) / 1e12
+    ms_iso, m_iso = pipe.decoder.time_layer(iters=20)              # the same kernel alone, operands L2-warm, no residual
     # the FFMA path computes in fp32; the tensor-pipe peak it is held against is TF32 = 1/2 of the measured bf16 burst figure
     peak = pk["bf16_tflops"] / 2.0
     traffic = None
@@ -201,10 +206,18 @@ def bench_gpu(args):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     kname = "tc_gemm_kernel (tcgen05 kind::tf32" if args.precision == "tf32" else "sgemm_nt_kernel (fp32 FFMA"
-    roofline = {"bound": "tensor", "kernel": kname + ", decoder 512x512 layer, fused bias+CBN+ReLU epilogue)",
+    roofline = {"bound": "tensor", "kernel": kname + ", decoder 512x512 layer, fused bias+residual+CBN+ReLU epilogue)",
                 "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": pk["source"] + " bf16 burst / 2 (TF32-class contraction held to the tensor pipe)",
-                "flops_per_launch": flops_layer, "ms_per_launch": round(ms_layer, 4), "points_per_launch": m_layer}
+                "launches": n_launch, "flops_per_launch": round(flops_total / max(1, n_launch)), "ms_per_launch": round(ms_total / max(1, n_launch), 4),
+                "measured": "event pair around every launch of one batch's lattice + face-filter chains (activations of consecutive layers "
+                            "exceed L2, residual/mask operands come from HBM)",
+                "isolated": {"ms_per_launch": round(ms_iso, 4), "points_per_launch": m_iso,
+                             "tflops": round(2.0 * m_iso * 512 * 512 / (ms_iso * 1e-3) / 1e12, 1)}}
+    # the sampler's token GEMMs stream the UNet weights once per DDPM step: HBM-side view of that stage
+    sampler = {"ms_per_ddpm_step": round(1e3 * tm["sample_s"] / STEPS_DDPM, 4), "weight_bytes_per_step": int(a.n_floats * 4),
+               "hbm_gbps": round(a.n_floats * 4 / (tm["sample_s"] / STEPS_DDPM) / 1e9, 1), "hbm_peak_gbps": pk["hbm_gbs"],
+               "note": "latency-bound: ~170 dependent kernels per step on <= 256 tokens (one CUDA-graph launch per step)"}
 
     out = None
     if rank == 0:
@@ -225,6 +238,7 @@ def bench_gpu(args):
             "shape_stats": {"n_udf": stats[0]["n_udf"], "n_grad": stats[0]["n_grad"], "n_cand": stats[0]["n_cand"], "verts": stats[0]["n_verts"],
                             "faces": stats[0]["n_faces"]},
             "roofline": roofline,
+            "sampler": sampler,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference(stats[0], quick=True)

@@ -27,6 +27,7 @@ PROTOTYPES = {
     "surfd_dec_set_sm_budget": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "surfd_dec_num_sms": (ctypes.c_int, [c_vp]),
     "surfd_dec_chunk_points": (ctypes.c_int, [c_vp]),
+    "surfd_dec_profile": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_double)]),
     "surfd_dec_time_layer": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp]),
     "surfd_dec_debug_layer": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "surfd_udf_query": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -39,7 +40,7 @@ PROTOTYPES = {
     "surfd_mc_finish": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "surfd_mc_fetch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "surfd_mc_classify": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, ctypes.POINTER(c_i64), c_vp]),
-    "surfd_face_filter": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_vp]),
+    "surfd_face_filter": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, ctypes.c_int, c_vp, c_vp]),
     "surfd_unet_create": (ctypes.c_int, [c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "surfd_unet_destroy": (None, [c_vp]),
     "surfd_unet_set_lanes": (ctypes.c_int, [c_vp, ctypes.c_int]),

@@ -365,30 +365,45 @@ __global__ void gf_resolve_kernel(GfLevels lv, int N, float* __restrict__ udf) {
   }
 }
 
-// face filter points (meshudf.py:358-367): for face f and k in [0,9): edge e = k%3 -> (v[e], v[(e+1)%3]);
-// k/3: 0 first endpoint, 1 second endpoint, 2 midpoint (float64 math, then float32 like .float()).
-__global__ void face_points_kernel(const double* __restrict__ verts, const int32_t* __restrict__ faces, int64_t f0, int M,
-                                   float* __restrict__ pts) {
+// Face filter (meshudf.py:356-379).  The reference evaluates 9 points per face: for each of the 3 directed edges its two
+// end points and its midpoint (float64 math, then float32 like .float()).  The end points are the mesh vertices -- each is
+// requested ~12 times (2 per incident face) -- so the vertices are evaluated ONCE (same float32 coordinates, and a point's
+// udf does not depend on its position in a batch), and only the 3 midpoints per face are evaluated per face.
+__global__ void vert_points_kernel(const double* __restrict__ verts, int64_t v0, int M, float* __restrict__ pts) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
-  const int64_t f = f0 + m / 9;
-  const int k = m % 9;
-  const int e = k % 3, kind = k / 3;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) pts[3 * m + a] = (float)verts[3 * (v0 + m) + a];
+}
+
+__global__ void vert_flag_kernel(const float* __restrict__ udf, int M, float thr, uint8_t* __restrict__ far_v) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) far_v[m] = udf[m] > thr ? 1 : 0;
+}
+
+// midpoints of the edges (v[e], v[(e+1)%3]), e = 0..2, of faces f0 .. f0 + M/3
+__global__ void face_mid_points_kernel(const double* __restrict__ verts, const int32_t* __restrict__ faces, int64_t f0, int M,
+                                       float* __restrict__ pts) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int64_t f = f0 + m / 3;
+  const int e = m % 3;
   const int32_t va = faces[3 * f + e], vb = faces[3 * f + (e + 1) % 3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     const double xa = verts[3 * (int64_t)va + a], xb = verts[3 * (int64_t)vb + a];
-    const double x = kind == 0 ? xa : (kind == 1 ? xb : (xa + xb) / 2);
-    pts[3 * m + a] = (float)x;
+    pts[3 * m + a] = (float)((xa + xb) / 2);
   }
 }
 
-__global__ void face_keep_kernel(const float* __restrict__ udf, int n_faces, float thr, uint8_t* __restrict__ keep) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= n_faces) return;
+__global__ void face_keep_kernel(const float* __restrict__ udf_mid, const int32_t* __restrict__ faces, const uint8_t* __restrict__ far_v,
+                                 int64_t f0, int n_faces, float thr, uint8_t* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_faces) return;
+  const int64_t f = f0 + i;
   bool ok = true;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) ok = ok && !(udf[(size_t)f * 9 + k] > thr);
+  for (int k = 0; k < 3; ++k) ok = ok && !(udf_mid[(size_t)i * 3 + k] > thr) && !far_v[faces[3 * f + k]];
   keep[f] = ok ? 1 : 0;
 }
 
@@ -407,6 +422,11 @@ struct surfd_decoder {
   DevBuf wT;         // transposes: WpT [64][512], then 5x{W0T, W1T}
   DevBuf wR;         // TF32-rounded (rna) copies for the tensor-core path: 5x{W0, W1}, then 5x{W0T, W1T}
   DevBuf err;        // int error flag written by the tcgen05 kernel's bounded waits
+  DevBuf vflag;      // face filter: per-vertex "udf > 1/N" flags
+  bool profiling = false;             // surfd_dec_profile: event pair around every 512x512 layer GEMM
+  std::vector<cudaEvent_t> prof_events;
+  size_t prof_used = 0;
+  int64_t prof_points = 0;
   int num_sms = 148;
   int sm_budget = 0;     // persistent-kernel grid size (0 = all SMs); lower it while other long-running kernels hold SMs
   DevBuf fold;       // s[11][512], t[11][512]
@@ -530,7 +550,9 @@ extern "C" int surfd_dec_create(const float* packed, size_t n_floats, int L, int
 
 extern "C" void surfd_dec_destroy(surfd_decoder* d) {
   if (!d) return;
-  d->wR.release(); d->err.release();
+  d->wR.release(); d->err.release(); d->vflag.release();
+  for (cudaEvent_t ev : d->prof_events) cudaEventDestroy(ev);
+  d->prof_events.clear();
   d->weights.release(); d->wT.release(); d->fold.release(); d->acts.release(); d->net.release(); d->dnet.release();
   d->dh.release(); d->enc.release(); d->de.release(); d->pts.release(); d->dudf.release(); d->udf_tmp.release();
   d->dst.release(); d->bits.release(); d->list.release(); d->gf_state.release();
@@ -546,9 +568,52 @@ extern "C" int surfd_dec_set_precision(surfd_decoder* d, int mode) {
 }
 
 static int gemm512(surfd_decoder* d, const float* A, const float* W, const float* Wr, int M, Epilogue e, cudaStream_t st) {
-  if (d->precision == 0) return launch_gemm(A, HID, W, HID, M, HID, HID, e, st);
-  const int sms = d->sm_budget > 0 && d->sm_budget < d->num_sms ? d->sm_budget : d->num_sms;
-  return launch_gemm_tc(A, Wr, M, e, d->err.as<int>(), sms, st);
+  // measurement mode (surfd_dec_profile): every layer GEMM of the real chain is bracketed by its own event pair
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (d->profiling) {
+    if (d->prof_used + 2 > d->prof_events.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t ev;
+        SURFD_CUDA(cudaEventCreate(&ev));
+        d->prof_events.push_back(ev);
+      }
+    }
+    e0 = d->prof_events[d->prof_used]; e1 = d->prof_events[d->prof_used + 1];
+    d->prof_used += 2;
+    d->prof_points += M;
+    SURFD_CUDA(cudaEventRecord(e0, st));
+  }
+  int rc;
+  if (d->precision == 0) {
+    rc = launch_gemm(A, HID, W, HID, M, HID, HID, e, st);
+  } else {
+    const int sms = d->sm_budget > 0 && d->sm_budget < d->num_sms ? d->sm_budget : d->num_sms;
+    rc = launch_gemm_tc(A, Wr, M, e, d->err.as<int>(), sms, st);
+  }
+  if (e1) SURFD_CUDA(cudaEventRecord(e1, st));
+  return rc;
+}
+
+// Measurement of the dominant kernel inside the real layer chain.  on = 1 starts a measurement (counters reset); on = 0
+// stops it, waits for the device and reports: launches, total point rows (FLOPs = 2 * 512 * 512 per row) and the summed
+// launch durations in ms.
+extern "C" int surfd_dec_profile(surfd_decoder* d, int on, int64_t* launches, int64_t* points, double* total_ms) {
+  SURFD_REQUIRE(d != nullptr, "null argument");
+  if (on) {
+    d->profiling = true; d->prof_used = 0; d->prof_points = 0;
+    return 0;
+  }
+  d->profiling = false;
+  SURFD_REQUIRE(launches && points && total_ms, "null argument");
+  SURFD_CUDA(cudaDeviceSynchronize());
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < d->prof_used; i += 2) {
+    float ms = 0.f;
+    SURFD_CUDA(cudaEventElapsedTime(&ms, d->prof_events[i], d->prof_events[i + 1]));
+    tot += ms;
+  }
+  *launches = (int64_t)(d->prof_used / 2); *points = d->prof_points; *total_ms = tot;
+  return 0;
 }
 
 // The tcgen05 layer GEMM is persistent: one 215 KB CTA per SM.  An SM that already hosts another long-running kernel (a
@@ -792,20 +857,31 @@ extern "C" int surfd_dec_debug_layer(surfd_decoder* d, const float* A_dev, int M
   return launch_gemm_tc(A_dev, d->W0r(blk), M, e, d->err.as<int>(), d->sm_budget > 0 && d->sm_budget < d->num_sms ? d->sm_budget : d->num_sms, st);
 }
 
-extern "C" int surfd_face_filter(surfd_decoder* d, const double* verts64_dev, const int32_t* faces_dev, int64_t n_f, int N,
-                                 uint8_t* keep_dev, void* stream) {
+extern "C" int surfd_face_filter(surfd_decoder* d, const double* verts64_dev, int64_t n_v, const int32_t* faces_dev, int64_t n_f,
+                                 int N, uint8_t* keep_dev, void* stream) {
   SURFD_REQUIRE(d && d->latent_set, "decoder latent not set");
-  SURFD_REQUIRE(n_f >= 0 && (n_f == 0 || (verts64_dev && faces_dev && keep_dev)), "null argument");
+  SURFD_REQUIRE(n_f >= 0 && n_v >= 0 && (n_f == 0 || (verts64_dev && faces_dev && keep_dev && n_v > 0)), "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  const int faces_per_chunk = d->chunk / 9;
   const float thr = (float)(1.0 / N);  // meshudf.py:372
-  for (int64_t f0 = 0; f0 < n_f; f0 += faces_per_chunk) {
-    const int nf = (int)((n_f - f0) < faces_per_chunk ? (n_f - f0) : faces_per_chunk);
-    const int m = nf * 9;
-    face_points_kernel<<<(unsigned)cdiv(m, 256), 256, 0, st>>>(verts64_dev, faces_dev, f0, m, d->pts.as<float>());
+  if (n_f == 0) return 0;
+  SURFD_TRY(d->vflag.reserve((size_t)n_v));
+  uint8_t* far_v = d->vflag.as<uint8_t>();
+  for (int64_t v0 = 0; v0 < n_v; v0 += d->chunk) {
+    const int m = (int)((n_v - v0) < d->chunk ? (n_v - v0) : d->chunk);
+    vert_points_kernel<<<(unsigned)cdiv(m, 256), 256, 0, st>>>(verts64_dev, v0, m, d->pts.as<float>());
     SURFD_CHECK_LAUNCH();
     SURFD_TRY(dec_forward(d, m, false, d->udf_tmp.as<float>(), nullptr, st));
-    face_keep_kernel<<<(unsigned)cdiv(nf, 256), 256, 0, st>>>(d->udf_tmp.as<float>(), nf, thr, keep_dev + f0);
+    vert_flag_kernel<<<(unsigned)cdiv(m, 256), 256, 0, st>>>(d->udf_tmp.as<float>(), m, thr, far_v + v0);
+    SURFD_CHECK_LAUNCH();
+  }
+  const int faces_per_chunk = d->chunk / 3;
+  for (int64_t f0 = 0; f0 < n_f; f0 += faces_per_chunk) {
+    const int nf = (int)((n_f - f0) < faces_per_chunk ? (n_f - f0) : faces_per_chunk);
+    const int m = nf * 3;
+    face_mid_points_kernel<<<(unsigned)cdiv(m, 256), 256, 0, st>>>(verts64_dev, faces_dev, f0, m, d->pts.as<float>());
+    SURFD_CHECK_LAUNCH();
+    SURFD_TRY(dec_forward(d, m, false, d->udf_tmp.as<float>(), nullptr, st));
+    face_keep_kernel<<<(unsigned)cdiv(nf, 256), 256, 0, st>>>(d->udf_tmp.as<float>(), faces_dev, far_v, f0, nf, thr, keep_dev);
     SURFD_CHECK_LAUNCH();
   }
   return 0;

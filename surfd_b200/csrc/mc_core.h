@@ -936,8 +936,11 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, 
       sign_vs[vtx] = vote_accumulate_f32(sign_vs[vtx], (float)sn, cc.vote[vtx * 6 + d]);
     }
     if (mode != 0) {
+      // |sign| / visited < 0.707f, evaluated without the FP64 division: 0.707f * visited is exact in double (24 + 3 bits),
+      // and the rounded quotient can only differ from the exact one inside half an ulp53 of the threshold, which a
+      // 24-bit numerator over visited <= 6 never reaches unless it equals the product (then both tests are false).
       if (visited_vs[vtx] >= 1 &&
-          (double)(sign_vs[vtx] < 0 ? -sign_vs[vtx] : sign_vs[vtx]) / (double)visited_vs[vtx] < (double)0.707f &&
+          (double)(sign_vs[vtx] < 0 ? -sign_vs[vtx] : sign_vs[vtx]) < (double)0.707f * (double)visited_vs[vtx] &&
           !g.q.empty()) {
         if (mode == 1) {
           if (!g.q_unsure.push((int32_t)lin(g, z, y, x))) g.status = MC_QUEUE_OVERFLOW;

@@ -104,7 +104,7 @@ struct ConvArgs {
 constexpr int CT = 32;        // tile edge
 constexpr int CTP = CT + 4;   // padded row (floats)
 constexpr int KSPLIT = 8;     // max CTAs per cluster: the K reduction is split over a thread-block cluster (1, 2, 4 or 8)
-constexpr int CONV_STAGES = 2; // per-warp cp.async stages of the chunk stream
+constexpr int CONV_STAGES = 3; // per-warp cp.async stages of the chunk stream (two chunks in flight behind the one being multiplied)
 
 // One output tile (32 tokens x 32 channels) is owned by a cluster of KSPLIT CTAs.  K chunks (32 input channels of one
 // tap of one segment) are dealt round-robin to the 8 x 8 = 64 warps of the cluster, so even the deepest layers
@@ -126,15 +126,25 @@ __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, const uint
 
 // K slice `crank` of `ks` of output tile (n0, m0): every warp accumulates its chunks into register fragments.
 template <int MODE>
-__device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m0, int ks, int crank, float* smem, float (&acc)[8][4]) {
+__device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m0, int ks, int crank, float* smem, float (&acc)[8][4],
+                                                long long* prof = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* stage0 = smem + warp * (CONV_STAGES * 2 * CT * CTP);   // per warp: CONV_STAGES x (A tile | W tile)
   const int M = a.B * a.T_out;
 
-  // this lane's token row for loading
-  const int m_row = m0 + lane;
-  const int rb = m_row / a.T_out, rl = m_row % a.T_out;
-  const bool row_ok = m_row < M;
+  // Copy pattern: one cp.async instruction moves 4 rows x 128 B (lanes 0-7 cover row 0, 8-15 row 1, ...), i.e. 4 full
+  // lines per instruction.  (One row per lane would touch 32 different lines per instruction and saturate the L1
+  // wavefront pipeline: measured 2.5 us per 8 KB chunk.)  This lane serves rows lr + 4j, j = 0..7, 16-byte piece lp.
+  const int lr = lane >> 3, lp = lane & 7;
+  int rbv[8], rlv[8];
+  unsigned rokv = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int m_row = m0 + lr + 4 * j;
+    rbv[j] = m_row / a.T_out;
+    rlv[j] = m_row - rbv[j] * a.T_out;
+    rokv |= (m_row < M ? 1u : 0u) << j;
+  }
 
   const int ly = lane >> 3, lx = lane & 7;   // FFMA mapping: rows ly + 4i, cols lx + 8j
   const int fg = lane >> 2, ft = lane & 3;   // MMA fragment mapping: group id / thread in group
@@ -159,34 +169,44 @@ __device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m
     const int cpt = sg.Cin / CT;
     const int tap = g / cpt, c = g - tap * cpt;
     const int T_eff = sg.up ? 2 * sg.T_in : sg.T_in;
-    const int src = rl * sg.stride + tap - (sg.taps >> 1);
-    const bool ok = row_ok && src >= 0 && src < T_eff;
-    const int st = sg.up ? (src >> 1) : src;
-    const float* arow = sg.A + ((size_t)rb * sg.T_in + (ok ? st : 0)) * sg.Cin + c * CT;
-    const float* wrow = sg.W + ((size_t)tap * a.N + n0 + lane) * sg.Cin + c * CT;
-    const uint32_t da = (uint32_t)__cvta_generic_to_shared(As_ + lane * CTP);
-    const uint32_t dw = (uint32_t)__cvta_generic_to_shared(Ws_ + lane * CTP);
-    const int asz = ok ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled (padding rows / taps outside the sequence)
+    const float* abase = sg.A + c * CT + 4 * lp;
+    const float* wbase = sg.W + ((size_t)tap * a.N + n0 + lr) * sg.Cin + c * CT + 4 * lp;
+    const uint32_t da = (uint32_t)__cvta_generic_to_shared(As_ + lr * CTP + 4 * lp);
+    const uint32_t dw = (uint32_t)__cvta_generic_to_shared(Ws_ + lr * CTP + 4 * lp);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da + 16 * j), "l"(arow + 4 * j), "r"(asz) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dw + 16 * j), "l"(wrow + 4 * j) : "memory");
+      const int src = rlv[j] * sg.stride + tap - (sg.taps >> 1);
+      const bool ok = ((rokv >> j) & 1u) && src >= 0 && src < T_eff;
+      const int st = sg.up ? (src >> 1) : src;
+      const float* arow = abase + (ok ? (size_t)rbv[j] * sg.T_in + st : (size_t)0) * sg.Cin;
+      const int asz = ok ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled (padding rows / taps outside the sequence)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da + j * (4 * CTP * 4)), "l"(arow), "r"(asz) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dw + j * (4 * CTP * 4)), "l"(wbase + (size_t)(4 * j) * sg.Cin) : "memory");
     }
   };
   int f = my_slot;
   int stg = 0;
-  if (f < n_chunks) issue(f, stage0, stage0 + CT * CTP);
-  asm volatile("cp.async.commit_group;" ::: "memory");
+  const bool pf = prof != nullptr && threadIdx.x == 0;
+#pragma unroll
+  for (int p = 0; p < CONV_STAGES - 1; ++p) {
+    const int fp = f + p * stride_f;
+    if (fp < n_chunks) issue(fp, stage0 + p * (2 * CT * CTP), stage0 + p * (2 * CT * CTP) + CT * CTP);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (; f < n_chunks; f += stride_f) {
     {
       {
         float* As = stage0 + stg * (2 * CT * CTP);
         float* Ws = As + CT * CTP;
-        const int fn = f + stride_f;
-        if (fn < n_chunks) issue(fn, stage0 + (stg ^ 1) * (2 * CT * CTP), stage0 + (stg ^ 1) * (2 * CT * CTP) + CT * CTP);
+        const int fn = f + (CONV_STAGES - 1) * stride_f;
+        const int sn = stg + CONV_STAGES - 1 >= CONV_STAGES ? stg - 1 : stg + CONV_STAGES - 1;
+        if (fn < n_chunks) issue(fn, stage0 + sn * (2 * CT * CTP), stage0 + sn * (2 * CT * CTP) + CT * CTP);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        long long tw0 = 0;
+        if (pf) tw0 = clock64();
+        asm volatile("cp.async.wait_group %0;" ::"n"(CONV_STAGES - 1) : "memory");
         __syncwarp();
+        if (pf) { prof[27] += clock64() - tw0; prof[26] += 1; }
         if (MODE == 0) {
 #pragma unroll
           for (int kk = 0; kk < CT; kk += 4) {
@@ -240,8 +260,8 @@ __device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m
             }
           }
         }
-        __syncwarp();   // every lane is done reading this stage before the copy issued two chunks later overwrites it
-        stg ^= 1;
+        __syncwarp();   // every lane is done reading this stage before the next iteration's copy overwrites it
+        stg = stg + 1 == CONV_STAGES ? 0 : stg + 1;
       }
     }
   }
@@ -638,7 +658,7 @@ __device__ __forceinline__ void p_conv(const POp& o, float* smem, float* partial
     float acc[8][4];
     long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     if (pf) t0 = clock64();
-    conv_accumulate<MODE>(a, n0, m0, ks, crank, smem, acc);
+    conv_accumulate<MODE>(a, n0, m0, ks, crank, smem, acc, pf ? prof : nullptr);
     if (pf) t1 = clock64();
     float* part = conv_cta_partial<MODE>(acc, smem);
     __syncthreads();
@@ -1061,7 +1081,8 @@ struct Lane {
 struct surfd_unet {
   int L = 0, max_batch = 0;
   bool pdl = true;     // programmatic dependent launch between the step's kernels (falls back to false if capture rejects it)
-  int sampler = 1;     // surfd_sample: 1 = persistent cooperative kernel (default), 0 = CUDA-graph replay of the step
+  int sampler = 0;     // surfd_sample: 0 = CUDA-graph replay of the step (default: measured faster, 1.71 vs 1.89 ms/step at batch 8),
+                       // 1 = persistent cooperative kernel
   int sampler_sms = 0; // CTAs of the persistent kernel (0 = one per SM)
   bool profile = false; // persistent kernel: per-op-type cycle counters (diagnostics)
   int persist_split = 1; // token-GEMM K split of the persistent kernel: 0 = the graph path's rule (bit-identical samples),

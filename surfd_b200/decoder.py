@@ -134,12 +134,22 @@ class UdfDecoder:
                                               _lib.ptr(udf), _lib.ptr(grad), counts, _lib.stream_ptr()))
         return udf, grad, (int(counts[0]), int(counts[1]))
 
-    def time_layer(self, iters=20):
+    def time_layer(self, iters=20, points=None):
         """(ms per launch, points per launch) of the dominant kernel, CUDA-event timed on the current stream"""
-        M = int(self.lib.surfd_dec_chunk_points(self._h))
+        M = int(self.lib.surfd_dec_chunk_points(self._h)) if points is None else int(points)
         ms = ctypes.c_float()
         _lib.check(self.lib.surfd_dec_time_layer(self._h, M, int(iters), ctypes.byref(ms), _lib.stream_ptr()))
         return float(ms.value), M
+
+    def profile(self, on):
+        """on=True: start bracketing every layer GEMM of the real chain with CUDA events; on=False: stop and return
+        (launches, point rows, summed ms)"""
+        if on:
+            _lib.check(self.lib.surfd_dec_profile(self._h, 1, None, None, None))
+            return None
+        n, pts, ms = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double()
+        _lib.check(self.lib.surfd_dec_profile(self._h, 0, ctypes.byref(n), ctypes.byref(pts), ctypes.byref(ms)))
+        return int(n.value), int(pts.value), float(ms.value)
 
     def debug_layer(self, A, blk=0, mode=0):
         """one hidden layer over A [M,512] with the FFMA (mode 0) or tcgen05 (mode 1) kernel -- test hook"""
@@ -154,6 +164,6 @@ class UdfDecoder:
         faces = faces.to(self.device, torch.int32).contiguous()
         F = faces.shape[0]
         keep = torch.empty(F, device=self.device, dtype=torch.uint8)
-        _lib.check(self.lib.surfd_face_filter(self._h, _lib.ptr(verts64), _lib.ptr(faces), F, int(N), _lib.ptr(keep),
+        _lib.check(self.lib.surfd_face_filter(self._h, _lib.ptr(verts64), int(verts64.shape[0]), _lib.ptr(faces), F, int(N), _lib.ptr(keep),
                                               _lib.stream_ptr()))
         return keep

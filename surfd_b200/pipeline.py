@@ -27,7 +27,6 @@ class SurfDPipeline:
         budget = max(1, n_sms - mc_parallel)
         self.decoder = UdfDecoder(ae_state, latent_dim, device=device, packed=packed_decoder, max_chunk_points=budget * 256)
         self.decoder.set_sm_budget(budget)
-        self.sampler.set_sampler(1, budget)   # the persistent sampler kernel also leaves the replays' SMs alone (generate_many)
         self.mcs = [MarchingCubes(device) for _ in range(mc_parallel)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(mc_parallel)]
         self.schedule_cache = {}

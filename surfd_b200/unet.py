@@ -375,8 +375,8 @@ class UNetSampler:
         _lib.check(self.lib.surfd_unet_set_lanes(self._h, int(n)))
 
     def set_sampler(self, mode, n_sms=0):
-        """sample() engine: 1 = persistent cooperative kernel (default; `n_sms` CTAs, 0 = one per SM), 2 = the same with the
-        graph path's K split (bit-identical to mode 0), 0 = CUDA-graph replay of the step kernels"""
+        """sample() engine: 0 = CUDA-graph replay of the step kernels (default), 1 = persistent cooperative kernel (`n_sms`
+        CTAs, 0 = one per SM), 2 = the same with the graph path's K split (bit-identical to mode 0)"""
         _lib.check(self.lib.surfd_unet_set_sampler(self._h, int(mode), int(n_sms)))
 
     def profile(self, on=None):
@@ -387,7 +387,7 @@ class UNetSampler:
             return None
         buf = (ctypes.c_int64 * 48)()
         _lib.check(self.lib.surfd_unet_profile(self._h, 0, buf))
-        self.last_gemm_phases = dict(chunk_stream=buf[0], cta_partial=buf[1], publish=buf[2], reduce_epilogue=buf[24], units=buf[25])
+        self.last_gemm_phases = dict(chunk_stream=buf[0], cta_partial=buf[1], publish=buf[2], reduce_epilogue=buf[24], units=buf[25], chunks_warp0=buf[26], wait_cycles=buf[27])
         names = {1: "emb1", 2: "linear", 3: "inconv", 4: "groupnorm", 5: "token_gemm", 6: "attention", 7: "outconv+update"}
         return {("first_cta", "last_cta")[h]: {names[o]: tuple(buf[(h * 8 + o) * 3 + i] for i in range(3)) for o in names} for h in range(2)}
 

@@ -131,6 +131,29 @@ def test_face_filter_matches_oracle():
     assert 0 < keep.sum() < 300
 
 
+@pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "tf32"])
+def test_face_filter_vertex_sharing_equals_nine_queries_per_face(precision):
+    """the filter evaluates every vertex once + 3 midpoints per face; the decisions must equal the reference's literal
+    9 queries per face (same decoder, same precision: a point's udf does not depend on where it sits in a batch)"""
+    from surfd_b200.meshudf import MarchingCubes, finish_mesh
+    L, N = 32, 64
+    dec = UdfDecoder(synth.synth_ae_poly(L)["decoder"], L)
+    dec.set_precision(precision)
+    dec.set_latent(torch.randn(L, generator=torch.Generator().manual_seed(5)) * 0.7)
+    udf, grads, _ = dec.lattice(N, True)
+    v, f = MarchingCubes().run_raw(udf.clamp(min=0), grads)
+    verts, faces = finish_mesh(v, f, N)                       # float64 [V,3], shared vertices
+    assert faces.shape[0] > 1000 and verts.shape[0] < faces.shape[0]
+    keep = dec.face_filter(verts, faces, N).bool()
+    fl = faces.long()
+    e0 = fl[:, [0, 1, 2]].reshape(-1); e1 = fl[:, [1, 2, 0]].reshape(-1)
+    pts = torch.cat([verts[e0], verts[e1], (verts[e0] + verts[e1]) / 2]).float()      # meshudf.py:358-367
+    far = dec.query(pts) > (1.0 / N)
+    bad = far.reshape(3, faces.shape[0], 3).any(dim=2).any(dim=0)
+    assert torch.equal(keep, ~bad)
+    assert 0 < int(keep.sum())
+
+
 def test_missing_latent_and_foreign_callable_fail_loudly():
     from surfd_b200.meshudf import get_mesh_from_udf
     dec = UdfDecoder(synth.synth_ae_rand(32, 1)["decoder"], 32)

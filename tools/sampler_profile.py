@@ -29,7 +29,7 @@ def run(B, mode, n_sms=0, prof=False):
     return best, out
 
 
-for prec, B in ((1, 8), (1, 1), (2, 8), (0, 8)):
+for prec, B in ((1, 8),):
     net.set_precision(prec)
     print("---- token-GEMM precision mode %d (0 fp32 FFMA, 1 3xTF32, 2 TF32) ----" % prec)
     t0, r0 = run(B, 0)
@@ -44,8 +44,9 @@ for prec, B in ((1, 8), (1, 1), (2, 8), (0, 8)):
         net.profile(False)
         ph = net.last_gemm_phases
         if ph["units"]:
-            print("    first CTA token-GEMM phases (us per unit): " + ", ".join("%s %.2f" % (k, v / ph["units"] / 1965.0) for k, v in ph.items() if k != "units"),
-                  "| units per step %.1f" % (ph["units"] / 100))
+            print("    first CTA token-GEMM phases (us per unit): " + ", ".join("%s %.2f" % (k, v / ph["units"] / 1965.0) for k, v in ph.items() if k not in ("units", "chunks_warp0", "wait_cycles")),
+                  "| units per step %.1f | warp 0: %.1f chunks per unit, %.2f us waiting for copies per chunk"
+                  % (ph["units"] / 100, ph["chunks_warp0"] / ph["units"], ph["wait_cycles"] / max(1, ph["chunks_warp0"]) / 1965.0))
         print("  mode %d profiled %.3f ms/step; per op type (us per op: body / barrier, count per step)" % (mode, t))
         for cta in ("first_cta", "last_cta"):
             row = []
@@ -54,3 +55,11 @@ for prec, B in ((1, 8), (1, 1), (2, 8), (0, 8)):
                     row.append("%s %.1f/%.1f x%d" % (name, body / cnt / 1965.0, bar / cnt / 1965.0, cnt // 100))
             tot = sum(v[0] + v[1] for v in p[cta].values()) / 100 / 1965.0
             print("   ", cta, "| ".join(row), "| total %.0f us/step" % tot)
+
+# graph replay split over concurrent lanes (streams)
+net.set_precision(1); net.set_sampler(0)
+for lanes in (1, 2, 4):
+    net.set_lanes(lanes)
+    t, _ = run(8, 0)
+    print("graph replay, batch 8 over %d lane(s): %.3f ms/step" % (lanes, t))
+net.set_lanes(1)
