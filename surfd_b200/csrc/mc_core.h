@@ -696,6 +696,7 @@ struct CubeCache {
   int8_t sgn[64];
   uint8_t flg[64];
   uint8_t vstat[48];   // 0: skipped by the bounds rule, 1: usable, 2: neighbour udf == 0 (needs the extension rule)
+  int8_t nsgn[48];     // sign of the neighbour vertex of (corner, direction) as fetched
   // look-ahead windows: the next <= 32 entries of the BFS queue / of the raster candidate list, one per lane, with
   // bit0 = "visited flag already set" (kept coherent by note_done()), bit1 = "is a candidate cube"
   int32_t qw_cur[32];
@@ -742,6 +743,8 @@ MC_HD int64_t facelayer_index_xyz(int64_t nx, int x, int y, int z, int vi) {
 }
 
 #define MC_BLK(bz, by, bx) (((bz) << 4) | ((by) << 2) | (bx))
+// Lewiner corner id from its (z, y, x) bits: inverse of MC_CZ / MC_CY / MC_CX
+#define MC_CORNER(cz, cy, cx) (((cz) << 2) | ((cy) ? ((cx) ? 2 : 3) : ((cx) ? 1 : 0)))
 
 // check_tiling() on the cached slots.  A vertex index lives in exactly one face_layer slot, and the 13 edge ids of a
 // cube map to 13 distinct slots, so "distinct existing vertex indices" == "distinct edge ids whose slot is filled".
@@ -880,6 +883,7 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, 
         else { st = 1; vt = edge_vote(cc.gr + 3 * MC_BLK(bz, by, bx), cc.gr + 3 * nv, dz, dy, dx); }
       }
       cc.vstat[it] = st; cc.vote[it] = vt;
+      cc.nsgn[it] = st ? cc.sgn[MC_BLK(bz + dz, by + dy, bx + dx)] : (int8_t)0;   // as fetched; in-cube neighbours are tracked in registers
     }
   }
   MC_WARP_SYNC();
@@ -909,31 +913,44 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, 
         return r;
       }
   }
+  // The corner chain runs on registers: the signs / flags of the cube's own 8 corners live in csgn/cflg (updated as
+  // corners are decided), and each corner's six (status, vote, outside-neighbour sign) triples are loaded together
+  // before its accumulation loop -- one shared-memory latency per corner instead of three dependent ones per direction.
+  int8_t csgn[8];
+  uint8_t cflg[8];
+  MC_UNROLL
+  for (int i = 0; i < 8; ++i) { csgn[i] = cc.sgn[cb[i]]; cflg[i] = cc.flg[cb[i]]; }
   int visited_vs[8];
   float sign_vs[8];
   MC_UNROLL
   for (int vtx = 0; vtx < 8; ++vtx) {
     visited_vs[vtx] = 0;
     sign_vs[vtx] = 0.0f;
-    const int b0 = cb[vtx];
-    if (cc.flg[b0] & 1) {
+    if (cflg[vtx] & 1) {
       visited_vs[vtx] = 1;
-      sign_vs[vtx] = (float)cc.sgn[b0];
+      sign_vs[vtx] = (float)csgn[vtx];
       continue;
     }
     if (cim[vtx] == 0.0f) {
       visited_vs[vtx] = 1;
       continue;
     }
-    const int bz = 1 + MC_CZ(vtx), by = 1 + MC_CY(vtx), bx = 1 + MC_CX(vtx);
+    uint8_t st6[6];
+    float vt6[6];
+    int8_t ns6[6];
+    MC_UNROLL
+    for (int d = 0; d < 6; ++d) { st6[d] = cc.vstat[vtx * 6 + d]; vt6[d] = cc.vote[vtx * 6 + d]; ns6[d] = cc.nsgn[vtx * 6 + d]; }
     MC_UNROLL
     for (int d = 0; d < 6; ++d) {
-      if (cc.vstat[vtx * 6 + d] != 1) continue;
-      const int dz = (d == 0) - (d == 1), dy = (d == 2) - (d == 3), dx = (d == 4) - (d == 5);
-      const int8_t sn = cc.sgn[MC_BLK(bz + dz, by + dy, bx + dx)];
+      if (st6[d] != 1) continue;
+      // a step along an axis stays inside the cube iff it flips that axis' corner bit from 0 to 1 (or back)
+      const int cz = MC_CZ(vtx), cy = MC_CY(vtx), cx = MC_CX(vtx);
+      const int nz = cz + (d == 0) - (d == 1), ny = cy + (d == 2) - (d == 3), nx = cx + (d == 4) - (d == 5);
+      const bool in_cube = nz >= 0 && nz <= 1 && ny >= 0 && ny <= 1 && nx >= 0 && nx <= 1;
+      const int8_t sn = in_cube ? csgn[MC_CORNER(nz & 1, ny & 1, nx & 1)] : ns6[d];
       if (sn == 0) continue;
       visited_vs[vtx] += 1;
-      sign_vs[vtx] = vote_accumulate_f32(sign_vs[vtx], (float)sn, cc.vote[vtx * 6 + d]);
+      sign_vs[vtx] = vote_accumulate_f32(sign_vs[vtx], (float)sn, vt6[d]);
     }
     if (mode != 0) {
       // |sign| / visited < 0.707f, evaluated without the FP64 division: 0.707f * visited is exact in double (24 + 3 bits),
@@ -950,7 +967,7 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, 
       }
     }
     const int8_t ns = (int8_t)my_sign(sign_vs[vtx]);
-    cc.sgn[b0] = ns;
+    csgn[vtx] = ns;
     g.sgn[ci[vtx]] = ns;
   }
 
@@ -966,8 +983,8 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, 
     for (int k = 0; k < 8; ++k) {
       if (found) continue;
       const int b0 = cb[order[k]];
-      if ((cc.flg[b0] & 1) && non_zero_norm(cc.gr + 3 * b0)) {
-        anchor_sign = my_sign((float)cc.sgn[b0]);
+      if ((cflg[order[k]] & 1) && non_zero_norm(cc.gr + 3 * b0)) {
+        anchor_sign = my_sign((float)csgn[order[k]]);
         base[0] = cc.gr[3 * b0]; base[1] = cc.gr[3 * b0 + 1]; base[2] = cc.gr[3 * b0 + 2];
         found = true;
       }
@@ -996,7 +1013,7 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, 
         }
       }
       const int8_t ns = (int8_t)my_sign(s);
-      cc.sgn[cb[i]] = ns;
+      csgn[i] = ns;
       g.sgn[ci[i]] = ns;
     }
   }
@@ -1008,13 +1025,13 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, 
   double v[8];
   MC_UNROLL
   for (int i = 0; i < 8; ++i) {
-    float p = (float)cc.sgn[cb[i]] * cim[i];
+    float p = (float)csgn[i] * cim[i];
     v[i] = (double)p;
   }
   Cell c;
   cell_set(c, x, y, z, v);
   MC_UNROLL
-  for (int i = 0; i < 8; ++i) g.flg[ci[i]] = (uint8_t)(cc.flg[cb[i]] | 1);
+  for (int i = 0; i < 8; ++i) g.flg[ci[i]] = (uint8_t)(cflg[i] | 1);
 
   const int kase = LUT2(CASES, c.index, 0);
   const int64_t me = ci[0];
@@ -1045,7 +1062,7 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, 
       }
       if (existing < 2) return false;
     }
-    g.flg[me] = (uint8_t)(cc.flg[cb[0]] | 1 | 2);
+    g.flg[me] = (uint8_t)(cflg[0] | 1 | 2);
     done_set = true;
     MC_PROF_T(t_tiled);
     MC_PROF_ADD(3, t_signed, t_tiled);
@@ -1056,7 +1073,7 @@ MC_HD bool visit_cube_w(Grid& g, CubeCache& cc, const Grid* home, int z, int y, 
     MC_PROF_ADD(4, t_tiled, t_emitted);
     return true;
   }
-  g.flg[me] = (uint8_t)(cc.flg[cb[0]] | 1 | 2);
+  g.flg[me] = (uint8_t)(cflg[0] | 1 | 2);
   done_set = true;
   return false;
 }

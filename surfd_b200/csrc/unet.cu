@@ -63,22 +63,33 @@ gn_kernel(const float* __restrict__ in1, int C1, const float* __restrict__ in2, 
     __syncthreads();
     return red[0] + red[1] + red[2] + red[3];
   };
+  // the group's values are read once and kept in registers for the three passes (n <= 32 * 128; longer groups re-read)
+  constexpr int GN_CACHE = 32;
+  float xc[GN_CACHE];
+#pragma unroll
+  for (int k = 0; k < GN_CACHE; ++k) { const int i = threadIdx.x + 128 * k; xc[k] = i < n ? load(i) : 0.f; }
   float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += 128) s += load(i);
+#pragma unroll
+  for (int k = 0; k < GN_CACHE; ++k) if ((int)threadIdx.x + 128 * k < n) s += xc[k];
+  for (int i = threadIdx.x + 128 * GN_CACHE; i < n; i += 128) s += load(i);
   const float mean = block_sum(s) / (float)n;
   float q = 0.f;
-  for (int i = threadIdx.x; i < n; i += 128) { const float d = load(i) - mean; q += d * d; }
+#pragma unroll
+  for (int k = 0; k < GN_CACHE; ++k) if ((int)threadIdx.x + 128 * k < n) { const float d = xc[k] - mean; q += d * d; }
+  for (int i = threadIdx.x + 128 * GN_CACHE; i < n; i += 128) { const float d = load(i) - mean; q += d * d; }
   const float var = block_sum(q) / (float)n;
   const float rstd = 1.0f / sqrtf(var + 1e-5f);
-  for (int i = threadIdx.x; i < n; i += 128) {
+  auto emit = [&](int i, float x) {
     const int t = i / cg, c = g * cg + i % cg;
-    const float x = load(i);
     float y = (x - mean) * rstd * gamma[c] + beta[c];
     if (silu) y = y / (1.0f + expf(-y));
     const size_t o = ((size_t)b * T + t) * C + c;
     out[o] = y;
     if (raw) raw[o] = x;
-  }
+  };
+#pragma unroll
+  for (int k = 0; k < GN_CACHE; ++k) if ((int)threadIdx.x + 128 * k < n) emit((int)threadIdx.x + 128 * k, xc[k]);
+  for (int i = threadIdx.x + 128 * GN_CACHE; i < n; i += 128) emit(i, load(i));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -127,7 +138,7 @@ __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, const uint
 // K slice `crank` of `ks` of output tile (n0, m0): every warp accumulates its chunks into register fragments.
 template <int MODE>
 __device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m0, int ks, int crank, float* smem, float (&acc)[8][4],
-                                                long long* prof = nullptr) {
+                                                long long* prof = nullptr, bool pdl_wait = false) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* stage0 = smem + warp * (CONV_STAGES * 2 * CT * CTP);   // per warp: CONV_STAGES x (A tile | W tile)
   const int M = a.B * a.T_out;
@@ -162,7 +173,8 @@ __device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m
   const int n_chunks0 = a.seg[0].taps * (a.seg[0].Cin / CT);
   const int n_chunks = n_chunks0 + (a.nseg > 1 ? a.seg[1].taps * (a.seg[1].Cin / CT) : 0);
   const int stride_f = 8 * ks;
-  auto issue = [&](int f, float* As_, float* Ws_) {
+  // what = 1: weight rows only, 2: token rows only, 3: both
+  auto issue = [&](int f, float* As_, float* Ws_, int what) {
     const int s = f < n_chunks0 ? 0 : 1;
     const Seg& sg = a.seg[s];
     const int g = s ? f - n_chunks0 : f;
@@ -175,22 +187,33 @@ __device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m
     const uint32_t dw = (uint32_t)__cvta_generic_to_shared(Ws_ + lr * CTP + 4 * lp);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int src = rlv[j] * sg.stride + tap - (sg.taps >> 1);
-      const bool ok = ((rokv >> j) & 1u) && src >= 0 && src < T_eff;
-      const int st = sg.up ? (src >> 1) : src;
-      const float* arow = abase + (ok ? (size_t)rbv[j] * sg.T_in + st : (size_t)0) * sg.Cin;
-      const int asz = ok ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled (padding rows / taps outside the sequence)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da + j * (4 * CTP * 4)), "l"(arow), "r"(asz) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dw + j * (4 * CTP * 4)), "l"(wbase + (size_t)(4 * j) * sg.Cin) : "memory");
+      if (what & 2) {
+        const int src = rlv[j] * sg.stride + tap - (sg.taps >> 1);
+        const bool ok = ((rokv >> j) & 1u) && src >= 0 && src < T_eff;
+        const int st = sg.up ? (src >> 1) : src;
+        const float* arow = abase + (ok ? (size_t)rbv[j] * sg.T_in + st : (size_t)0) * sg.Cin;
+        const int asz = ok ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled (padding rows / taps outside the sequence)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da + j * (4 * CTP * 4)), "l"(arow), "r"(asz) : "memory");
+      }
+      if (what & 1)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dw + j * (4 * CTP * 4)), "l"(wbase + (size_t)(4 * j) * sg.Cin) : "memory");
     }
   };
   int f = my_slot;
   int stg = 0;
   const bool pf = prof != nullptr && threadIdx.x == 0;
+  // Programmatic dependent launch: the weight rows do not depend on the previous kernel, so they are requested before
+  // griddepcontrol.wait (their HBM latency overlaps the predecessor's tail); the token rows follow the wait.
 #pragma unroll
   for (int p = 0; p < CONV_STAGES - 1; ++p) {
     const int fp = f + p * stride_f;
-    if (fp < n_chunks) issue(fp, stage0 + p * (2 * CT * CTP), stage0 + p * (2 * CT * CTP) + CT * CTP);
+    if (fp < n_chunks) issue(fp, stage0 + p * (2 * CT * CTP), stage0 + p * (2 * CT * CTP) + CT * CTP, 1);
+  }
+  if (pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+#pragma unroll
+  for (int p = 0; p < CONV_STAGES - 1; ++p) {
+    const int fp = f + p * stride_f;
+    if (fp < n_chunks) issue(fp, stage0 + p * (2 * CT * CTP), stage0 + p * (2 * CT * CTP) + CT * CTP, 2);
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   for (; f < n_chunks; f += stride_f) {
@@ -200,7 +223,7 @@ __device__ __forceinline__ void conv_accumulate(const ConvArgs& a, int n0, int m
         float* Ws = As + CT * CTP;
         const int fn = f + (CONV_STAGES - 1) * stride_f;
         const int sn = stg + CONV_STAGES - 1 >= CONV_STAGES ? stg - 1 : stg + CONV_STAGES - 1;
-        if (fn < n_chunks) issue(fn, stage0 + sn * (2 * CT * CTP), stage0 + sn * (2 * CT * CTP) + CT * CTP);
+        if (fn < n_chunks) issue(fn, stage0 + sn * (2 * CT * CTP), stage0 + sn * (2 * CT * CTP) + CT * CTP, 3);
         asm volatile("cp.async.commit_group;" ::: "memory");
         long long tw0 = 0;
         if (pf) tw0 = clock64();
@@ -307,8 +330,8 @@ __device__ __forceinline__ float* conv_cta_partial(float (&acc)[8][4], float* sm
   return part;
 }
 
-// epilogue of one output element: + bias (+ per-sample embedding column) (+ residual)
-__device__ __forceinline__ void conv_store(const ConvArgs& a, int m0, int n0, int idx, float v) {
+// epilogue of one output element: + bias (+ per-sample embedding column) (+ residual), in this order
+__device__ __forceinline__ float conv_epilogue_operands(const ConvArgs& a, int m0, int n0, int idx, float v) {
   const int r = idx >> 5, col = idx & 31;
   const int m = m0 + r;
   if (m < a.B * a.T_out) {
@@ -316,16 +339,23 @@ __device__ __forceinline__ void conv_store(const ConvArgs& a, int m0, int n0, in
     const int b = m / a.T_out;
     v += a.bias[n];
     if (a.emb) v += a.emb[(size_t)b * a.emb_ld + n];
-    const size_t o = (size_t)m * a.N + n;
-    if (a.residual) v += a.residual[o];
-    a.out[o] = v;
+    if (a.residual) v += a.residual[(size_t)m * a.N + n];
   }
+  return v;
+}
+__device__ __forceinline__ void conv_store_value(const ConvArgs& a, int m0, int n0, int idx, float v) {
+  const int r = idx >> 5, col = idx & 31;
+  const int m = m0 + r;
+  if (m < a.B * a.T_out) a.out[(size_t)m * a.N + n0 + col] = v;
+}
+__device__ __forceinline__ void conv_store(const ConvArgs& a, int m0, int n0, int idx, float v) {
+  conv_store_value(a, m0, n0, idx, conv_epilogue_operands(a, m0, n0, idx, v));
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(256)
 conv_gemm_kernel(ConvArgs a) {
-  PDL_PROLOGUE();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the wait sits inside conv_accumulate, after the weight requests
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
@@ -333,22 +363,34 @@ conv_gemm_kernel(ConvArgs a) {
   const int n0 = blockIdx.x * CT;
   const int m0 = blockIdx.y * CT;
   float acc[8][4];
-  conv_accumulate<MODE>(a, n0, m0, ks, crank, smem, acc);
+  conv_accumulate<MODE>(a, n0, m0, ks, crank, smem, acc, nullptr, true);
   float* part = conv_cta_partial<MODE>(acc, smem);
   // (2) cross-CTA reduction over distributed shared memory: CTA `crank` finishes its 1/ks share of the 32x32 tile
   cluster.sync();
   {
     const int per = CT * CT / ks;
-    for (int idx = crank * per + threadIdx.x; idx < (crank + 1) * per; idx += 256) {
+    // <= 4 elements per thread: all remote partials and all epilogue operands (bias, embedding column, residual) are
+    // requested before the first store -- a load placed after a store to `out` could not be moved ahead of it by the compiler
+    float v[4], add[4];
+    int idxs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = crank * per + (int)threadIdx.x + 256 * i;
+      idxs[i] = idx < (crank + 1) * per ? idx : -1;
       float pv[KSPLIT];
 #pragma unroll
-      for (int j = 0; j < KSPLIT; ++j) pv[j] = j < ks ? cluster.map_shared_rank(part, j)[idx] : 0.f;   // remote loads in flight together
-      float v = 0.f;
+      for (int j = 0; j < KSPLIT; ++j) pv[j] = (idxs[i] >= 0 && j < ks) ? cluster.map_shared_rank(part, j)[idx] : 0.f;
+      float acc1 = 0.f;
 #pragma unroll
       for (int j = 0; j < KSPLIT; ++j)
-        if (j < ks) v += pv[j];
-      conv_store(a, m0, n0, idx, v);
+        if (j < ks) acc1 += pv[j];
+      v[i] = acc1;
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) add[i] = idxs[i] >= 0 ? conv_epilogue_operands(a, m0, n0, idxs[i], v[i]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (idxs[i] >= 0) conv_store_value(a, m0, n0, idxs[i], add[i]);
   }
   cluster.sync();   // keep this CTA's shared memory alive until every peer has read it
 }
@@ -664,11 +706,15 @@ __device__ __forceinline__ void p_conv(const POp& o, float* smem, float* partial
     __syncthreads();
     if (pf) t2 = clock64();
     if (ks == 1) {
-      for (int idx = threadIdx.x; idx < CT * CT; idx += 256) {
+      float vv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
         float v = 0.f;
-        v += part[idx];
-        conv_store(a, m0, n0, idx, v);
+        v += part[(int)threadIdx.x + 256 * i];
+        vv[i] = conv_epilogue_operands(a, m0, n0, (int)threadIdx.x + 256 * i, v);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) conv_store_value(a, m0, n0, (int)threadIdx.x + 256 * i, vv[i]);
     } else {
       float* mine = partials + ((size_t)tile * ks + crank) * (CT * CT);
       for (int idx = threadIdx.x; idx < CT * CT; idx += 256) __stcg(mine + idx, part[idx]);
@@ -692,14 +738,17 @@ __device__ __forceinline__ void p_conv(const POp& o, float* smem, float* partial
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < P_MAX_KS; ++j) pv[i][j] = j < ks ? __ldcg(base + (size_t)j * (CT * CT) + 256 * i) : 0.f;
+        float vv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float v = 0.f;
 #pragma unroll
           for (int j = 0; j < P_MAX_KS; ++j)
             if (j < ks) v += pv[i][j];
-          conv_store(a, m0, n0, (int)threadIdx.x + 256 * i, v);
+          vv[i] = conv_epilogue_operands(a, m0, n0, (int)threadIdx.x + 256 * i, v);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) conv_store_value(a, m0, n0, (int)threadIdx.x + 256 * i, vv[i]);
       }
     }
     __syncthreads();   // the staging buffers are reused by the next unit
