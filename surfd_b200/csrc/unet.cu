@@ -16,6 +16,7 @@
 // table uploads per step; here a step is one graph launch of ~170 small kernels reading the step index from
 // device memory.
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 #include <cooperative_groups.h>
@@ -403,9 +404,9 @@ conv_gemm_kernel(ConvArgs a) {
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline int attn_smem_floats(int T, int ch) { return 2 * T * (ch + 1) + T * ch + T * (T + 1); }
 
-template <typename Sync>
+template <typename Sync, typename Load>
 __device__ __forceinline__ void attn_unit(const float* qkv, int C, int T, int heads, float scale, float* out, int b, int h, float* sm,
-                                          int tid, int nthr, Sync sync) {
+                                          int tid, int nthr, Sync sync, Load load) {
   const int ch = C / heads;
   const int chp = ch + 1;
   float* q = sm;               // [T][chp] (scaled)
@@ -413,12 +414,29 @@ __device__ __forceinline__ void attn_unit(const float* qkv, int C, int T, int he
   float* v = k + T * chp;      // [T][ch]
   float* w = v + T * ch;       // [T][T+1]
   const float* base = qkv + (size_t)b * T * 3 * C + (size_t)h * 3 * ch;
-  for (int i = tid; i < T * ch; i += nthr) {
-    const int t = i / ch, c = i % ch;
-    const float* p = base + (size_t)t * 3 * C + c;
-    q[t * chp + c] = p[0] * scale;
-    k[t * chp + c] = p[ch] * scale;
-    v[i] = p[2 * ch];
+  for (int i0 = tid; i0 < T * ch; i0 += 4 * nthr) {   // four (q, k, v) triples in flight per thread
+    float qv[4], kv[4], vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthr;
+      qv[u] = kv[u] = vv[u] = 0.f;
+      if (i < T * ch) {
+        const int t = i / ch, c = i % ch;
+        const float* p = base + (size_t)t * 3 * C + c;
+        qv[u] = load(p, b * T + t, h * 3 * ch + c); kv[u] = load(p + ch, b * T + t, h * 3 * ch + ch + c);
+        vv[u] = load(p + 2 * ch, b * T + t, h * 3 * ch + 2 * ch + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthr;
+      if (i < T * ch) {
+        const int t = i / ch, c = i % ch;
+        q[t * chp + c] = qv[u] * scale;
+        k[t * chp + c] = kv[u] * scale;
+        v[i] = vv[u];
+      }
+    }
   }
   sync();
   for (int i = tid; i < T * T; i += nthr) {
@@ -458,7 +476,7 @@ attn_kernel(const float* __restrict__ qkv, int C, int T, int heads, float scale,
   PDL_PROLOGUE();
   extern __shared__ __align__(16) float sm[];
   attn_unit(qkv, C, T, heads, scale, out, (int)blockIdx.x / heads, (int)blockIdx.x % heads, sm, (int)threadIdx.x, 128,
-            [] { __syncthreads(); });
+            [] { __syncthreads(); }, [](const float* p, int, int) { return *p; });
 }
 
 // first conv (1 -> 224, k=3, pad 1) and last conv (224 -> 1)
@@ -619,8 +637,19 @@ __global__ void step_advance_kernel(StepState* st) {
 //   * the DDPM update is the epilogue of the last op (each output element needs only its own x0).
 // Activations are read with plain loads after the barrier's fence (weights are immutable and may use the read-only path).
 // =================================================================================================================
+constexpr int P_SYNC_WORDS = 64;   // [0] barrier counter, [1] abort flag
 constexpr int P_MAX_KS = 16;   // most K slices per output tile in the persistent kernel
 enum { P_EMB1 = 1, P_LIN = 2, P_INCONV = 3, P_GN = 4, P_CONV = 5, P_ATTN = 6, P_OUTCONV = 7 };
+
+// A token-GEMM output that its producer left as K-slice partial tiles ("deferred"): the consumer (GroupNorm or attention)
+// sums the slices in slice order and applies the GEMM's epilogue while it loads.  ks == 0: a plain [B][T][C] tensor.
+struct PartSrc {
+  const float* part;          // [tile][slice][32][128]
+  const float* bias;
+  const float* emb;           // [B][emb_ld] or null
+  const float* res;           // [B*T][N] or null
+  int ks, tiles_n, emb_ld, N;
+};
 
 struct POp {
   int type;
@@ -636,7 +665,9 @@ struct POp {
   float* out1;
   int i0, i1, i2, i3, i4, i5;
   float f0;
-  int pad;
+  int wide;                   // P_CONV: 1 = wide unit (32 x 128 tile, distributed slice reduction), 0 = narrow unit
+  int defer;                  // P_CONV (wide, ks > 1): leave the K-slice partial tiles to the next op (no exchange inside this op)
+  PartSrc ps;                 // P_GN / P_ATTN: the first input is a deferred token-GEMM output
 };
 
 struct PersistArgs {
@@ -651,25 +682,43 @@ struct PersistArgs {
   float* x;                   // [B][L] current sample, updated in place
   float* x0a;                 // [B][L] first-pass prediction when n_pass == 2
   float* partials;            // [tile][slice][32*32] K-slice partial tiles
-  unsigned* sems;             // per-tile arrival counters (zero between ops)
+  unsigned* sems;             // per-tile arrival counters: [2 banks for the wide units | narrow units (zero between ops)] x sem_bank
+  int sem_bank;
   unsigned* sync;             // [0] barrier counter, [1] abort flag
   long long* prof;            // diagnostics (may be null): [cta 0 | cta G-1][op type][body cycles, barrier cycles, count]
 };
 
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// all CTAs of the (co-resident) grid; returns false when the run was aborted (a CTA waited > ~1 s: never expected)
-__device__ __forceinline__ bool grid_barrier(unsigned* sync, unsigned& target, unsigned G, int* s_ok) {
-  __syncthreads();
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid barrier over all CTAs of the (co-resident) grid, split in two so that work which does not depend on the other
+// CTAs (the next op's weight copies) can be issued between arriving and waiting.  One release-increment and an
+// acquire-poll of one counter by thread 0; the CTA barriers around them order the other threads.  (Measured on B200:
+// 1.85 us per barrier at 148 CTAs; per-CTA flag words polled by a warp, and a two-level counter tree, were both slower.)
+__device__ __forceinline__ void grid_arrive(unsigned* sync) {   // call after a __syncthreads()
+  if (threadIdx.x == 0) red_release_add(sync, 1u);
+}
+// returns false when the run was aborted (a CTA waited > ~1 s: never expected)
+__device__ __forceinline__ bool grid_wait(unsigned* sync, unsigned& target, unsigned G, int* s_ok) {
   if (threadIdx.x == 0) {
     target += G;
-    __threadfence();
-    atomicAdd(sync, 1u);
     int ok = 1;
     const long long t0 = clock64();
     unsigned spins = 0;
     for (;;) {
-      const unsigned v = *(volatile unsigned*)sync;
+      const unsigned v = ld_acquire(sync);
       if ((int)(v - target) >= 0) break;
       if ((++spins & 1023u) == 0u) {
         if (*(volatile unsigned*)(sync + 1) != 0u || clock64() - t0 > 2000000000LL) {
@@ -679,7 +728,6 @@ __device__ __forceinline__ bool grid_barrier(unsigned* sync, unsigned& target, u
         }
       }
     }
-    __threadfence();
     *s_ok = ok;
   }
   __syncthreads();
@@ -787,6 +835,392 @@ __device__ __forceinline__ void p_conv_prefetch(const POp& o, int cta, int G) {
   }
 }
 
+// ---- wide token-GEMM units (default engine) --------------------------------------------------------------------
+// The narrow unit above moves one 4 KB activation chunk per 4 KB weight chunk (32 x 32 tile): half of the L2 -> SM
+// traffic of a weight-streaming op is activations, and every warp runs its own short, latency-exposed copy chain.
+// The wide unit owns 32 tokens x 128 outputs of one contiguous K slice:
+//   * CTA-wide cp.async ring of W_STAGES stages; a stage holds TWO K chunks (32 channels each): 2 x (32 x 32) token rows
+//     + 2 x (128 x 32) weight rows = 40 KB of payload, three stages (120 KB) in flight per SM -- activations are 1/5
+//     of the traffic and a slice of <= 8 chunks is requested in full before the first MMA;
+//   * warp w multiplies n-subtile (w & 3) of chunk (w >> 2) of the stage; the 3xTF32 products of the 8 independent
+//     accumulator fragments are issued term by term (lo*hi for all, hi*lo for all, hi*hi for all), so consecutive
+//     mma.sync instructions never depend on each other;
+//   * the two chunk groups meet in shared memory, the K slices of a tile meet through L2 partial tiles and a per-tile
+//     arrival counter; once all slices have arrived EVERY slice's CTA reduces 1/ks of the tile in slice order (fixed
+//     summation order: the result depends on the slice count but not on timing) and applies the epilogue.
+// A unit's slices must be co-resident (they wait for each other): the host only splits K when tiles * ks <= grid.
+constexpr int WN = 128;                                // outputs per wide tile
+constexpr int W_STAGES = 4;
+constexpr int WTP = 40;                                // padded row (floats): 8-byte fragment loads of rows g, g+1, .. hit disjoint banks
+constexpr int W_STAGE = (2 * CT + 2 * WN) * WTP;       // floats per stage
+constexpr int WIDE_SMEM = W_STAGES * W_STAGE * (int)sizeof(float);
+constexpr int P_MAX_KS_WIDE = 32;
+
+__device__ __forceinline__ void mma_tf32_nv(float* c, const uint32_t* a, const uint32_t* b) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ void mma_f16(float* c, const uint32_t* a, const uint32_t* b) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// x = hi + lo / 4096 with hi, lo in fp16 (11 significant bits each, the same split as 3xTF32's hi + lo; the residual is
+// scaled by 2^12 so that it stays a normal fp16 number).  Packed pairs: (x.x, x.y) -> low / high half.
+constexpr float F16_LO_SCALE = 4096.0f;
+__device__ __forceinline__ void split_f16x2(float2 x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x.y), "f"(x.x));
+  float hx, hy;
+  asm("{ .reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(hx), "=f"(hy) : "r"(hi));
+  const float rx = (x.x - hx) * F16_LO_SCALE, ry = (x.y - hy) * F16_LO_SCALE;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(ry), "f"(rx));
+}
+
+// One warp: acc[mt*4+nt] += As[32 tok][32 k] * Ws[32 n][32 k]^T (rows padded to WTP floats).
+// MODE 1: fp32-class product on the fp16 tensor path, mma.sync m16n8k16: acc += a_hi b_hi, acc2 += a_hi b_lo + a_lo b_hi
+// (acc2 carries the 2^12 scale; the caller adds acc2 / 4096).  Half the tensor-pipe work of the 3xTF32 m16n8k8 split, which
+// bounded the wide units (measured 1.55 us per chunk pair and SM).  Values must lie inside the fp16 range (|x| < 65504).
+// MODE 2: single-pass TF32, m16n8k8.
+template <int MODE>
+__device__ __forceinline__ void mma_chunk(const float* __restrict__ As, const float* __restrict__ Ws, float (&acc)[8][4], float (&acc2)[8][4],
+                                          int fg, int ft) {
+  if (MODE == 1) {
+#pragma unroll
+    for (int k0 = 0; k0 < CT; k0 += 16) {
+      // A fragment (16x16, row-major): a0 (g, 2t..) a1 (g+8, 2t..) a2 (g, 2t+8..) a3 (g+8, 2t+8..); B (16x8): b0 (k 2t.., n g) b1 (k 2t+8.., n g)
+      uint32_t ahi[2][4], alo[2][4], bhi[4][2], blo[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float* ap = As + (mt * 16 + fg) * WTP + k0 + 2 * ft;
+        split_f16x2(*reinterpret_cast<const float2*>(ap), ahi[mt][0], alo[mt][0]);
+        split_f16x2(*reinterpret_cast<const float2*>(ap + 8 * WTP), ahi[mt][1], alo[mt][1]);
+        split_f16x2(*reinterpret_cast<const float2*>(ap + 8), ahi[mt][2], alo[mt][2]);
+        split_f16x2(*reinterpret_cast<const float2*>(ap + 8 * WTP + 8), ahi[mt][3], alo[mt][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float* bp = Ws + (nt * 8 + fg) * WTP + k0 + 2 * ft;
+        split_f16x2(*reinterpret_cast<const float2*>(bp), bhi[nt][0], blo[nt][0]);
+        split_f16x2(*reinterpret_cast<const float2*>(bp + 8), bhi[nt][1], blo[nt][1]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_f16(acc2[mt * 4 + nt], alo[mt], bhi[nt]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_f16(acc[mt * 4 + nt], ahi[mt], bhi[nt]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_f16(acc2[mt * 4 + nt], ahi[mt], blo[nt]);
+    }
+  } else {
+#pragma unroll
+    for (int k0 = 0; k0 < CT; k0 += 8) {
+      uint32_t ahi[2][4], bhi[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float* ap = As + (mt * 16 + fg) * WTP + k0 + ft;
+        ahi[mt][0] = to_tf32(ap[0]); ahi[mt][1] = to_tf32(ap[8 * WTP]); ahi[mt][2] = to_tf32(ap[4]); ahi[mt][3] = to_tf32(ap[8 * WTP + 4]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float* bp = Ws + (nt * 8 + fg) * WTP + k0 + ft;
+        bhi[nt][0] = to_tf32(bp[0]); bhi[nt][1] = to_tf32(bp[4]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_nv(acc[mt * 4 + nt], ahi[mt], bhi[nt]);
+    }
+  }
+}
+
+// cp.async copies of chunk pair `pair` of a wide unit into stage `stg`: what & 1 = the 2 x 128 weight rows, what & 2 = the
+// 2 x 32 token rows.  Copy mapping: thread -> 16-byte piece tid & 7 of row tid >> 3 (8 consecutive lanes = one 128 B line).
+__device__ __forceinline__ void wide_issue(const ConvArgs& a, int n_chunks0, int f_begin, int f_end, int n0, int m0, int pair, float* stg, int what) {
+  const int tid = (int)threadIdx.x;
+  const int lp = tid & 7, cr = tid >> 3;
+  const int m_row = m0 + cr;
+  const bool rok = m_row < a.B * a.T_out;
+  const int rb = m_row / a.T_out, rl = m_row - rb * a.T_out;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int f = f_begin + 2 * pair + g;
+    if (f < f_end) {
+      const int s = f < n_chunks0 ? 0 : 1;
+      const Seg& sg = a.seg[s];
+      const int q = s ? f - n_chunks0 : f;
+      const int cpt = sg.Cin / CT;
+      const int tap = q / cpt, c = q - tap * cpt;
+      if (what & 2) {
+        const int T_eff = sg.up ? 2 * sg.T_in : sg.T_in;
+        const int src = rl * sg.stride + tap - (sg.taps >> 1);
+        const bool ok = rok && src >= 0 && src < T_eff;
+        const int st = sg.up ? (src >> 1) : src;
+        const float* arow = sg.A + (ok ? ((size_t)rb * sg.T_in + st) * sg.Cin : (size_t)0) + c * CT + 4 * lp;
+        const uint32_t da = (uint32_t)__cvta_generic_to_shared(stg + (g * CT + cr) * WTP + 4 * lp);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(arow), "r"(ok ? 16 : 0) : "memory");
+      }
+      if (what & 1) {
+        const float* wbase = sg.W + (size_t)tap * a.N * sg.Cin + c * CT + 4 * lp;
+        const uint32_t dw = (uint32_t)__cvta_generic_to_shared(stg + (2 * CT + g * WN + cr) * WTP + 4 * lp);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + cr + 32 * j;
+          const bool okw = n < a.N;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dw + j * (32 * WTP * 4)), "l"(wbase + (size_t)(okw ? n : 0) * sg.Cin),
+                       "r"(okw ? 16 : 0) : "memory");
+        }
+      }
+    }
+  }
+}
+
+// weight rows of the first W_STAGES - 1 chunk pairs of this CTA's first unit of a wide token GEMM, requested while the
+// CTA waits at the grid barrier in front of that op (weights do not depend on the other CTAs).  Not committed: the
+// copies join the first commit group of the unit's own prologue.
+__device__ __forceinline__ void wide_preissue(const POp& o, float* smem, int cta) {
+  const ConvArgs& a = o.conv;
+  const int ks = o.ks;
+  if (cta >= o.tiles_n * o.tiles_m * ks) return;
+  const int crank = cta % ks, tile = cta / ks;
+  const int n0 = (tile % o.tiles_n) * WN, m0 = (tile / o.tiles_n) * CT;
+  const int n_chunks0 = a.seg[0].taps * (a.seg[0].Cin / CT);
+  const int n_chunks = n_chunks0 + (a.nseg > 1 ? a.seg[1].taps * (a.seg[1].Cin / CT) : 0);
+  const int f_begin = (crank * n_chunks) / ks, f_end = ((crank + 1) * n_chunks) / ks;
+  const int n_pairs = (f_end - f_begin + 1) >> 1;
+#pragma unroll
+  for (int p = 0; p < W_STAGES - 1; ++p)
+    if (p < n_pairs) wide_issue(a, n_chunks0, f_begin, f_end, n0, m0, p, smem + p * W_STAGE, 1);
+}
+
+// spin until *p >= want (another CTA's release); false on abort / timeout (never expected)
+__device__ __forceinline__ bool spin_until(const unsigned* p, unsigned want, unsigned* abort_flag) {
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  for (;;) {
+    if (ld_acquire(p) >= want) return true;
+    if ((++spins & 1023u) == 0u) {
+      if (*(volatile unsigned*)abort_flag != 0u || clock64() - t0 > 2000000000LL) {
+        atomicExch(abort_flag, 1u);
+        return false;
+      }
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void p_conv_wide(const POp& o, float* smem, float* partials, unsigned* sems, unsigned* abort_flag, bool pre_issued,
+                                            int cta, int G, long long* prof) {
+  const bool pf = prof != nullptr && cta == 0 && threadIdx.x == 0;
+  const ConvArgs& a = o.conv;
+  const int ks = o.ks;
+  const int n_units = o.tiles_n * o.tiles_m * ks;
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nsub = warp & 3, kg = warp >> 2;
+  const int fg = lane >> 2, ft = lane & 3;
+  const int M = a.B * a.T_out;
+  const int n_chunks0 = a.seg[0].taps * (a.seg[0].Cin / CT);
+  const int n_chunks = n_chunks0 + (a.nseg > 1 ? a.seg[1].taps * (a.seg[1].Cin / CT) : 0);
+  for (int u = cta; u < n_units; u += G) {
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    if (pf) t0 = clock64();
+    const int crank = u % ks, tile = u / ks;
+    const int tn = tile % o.tiles_n, tm = tile / o.tiles_n;
+    const int n0 = tn * WN, m0 = tm * CT;
+    const int f_begin = (crank * n_chunks) / ks, f_end = ((crank + 1) * n_chunks) / ks;
+    const int n_pairs = (f_end - f_begin + 1) >> 1;
+
+    auto issue_pair = [&](int pair, float* stg, int what) {
+      wide_issue(a, n_chunks0, f_begin, f_end, n0, m0, pair, stg, what);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float acc[8][4], acc2[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; acc2[i][j] = 0.f; }
+    const int first_what = (pre_issued && u == cta) ? 2 : 3;   // this CTA's first unit: the weight rows are already in flight
+#pragma unroll
+    for (int p = 0; p < W_STAGES - 1; ++p) {
+      if (p < n_pairs) issue_pair(p, smem + p * W_STAGE, first_what);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    int stg = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(W_STAGES - 2) : "memory");
+      __syncthreads();   // pair p has landed for every thread; everybody is done with pair p-1 (its stage is refilled below)
+      if (pf && p == 0) { prof[27] += clock64() - t0; prof[26] += n_pairs; }   // time to the first pair, pairs of this unit
+      const int nxt = p + W_STAGES - 1;
+      if (nxt < n_pairs) issue_pair(nxt, smem + (stg == 0 ? W_STAGES - 1 : stg - 1) * W_STAGE, 3);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      if (f_begin + 2 * p + kg < f_end) {
+        const float* As = smem + stg * W_STAGE + kg * CT * WTP;
+        const float* Ws = smem + stg * W_STAGE + (2 * CT + kg * WN + nsub * 32) * WTP;
+        mma_chunk<MODE>(As, Ws, acc, acc2, fg, ft);
+      }
+      stg = stg + 1 == W_STAGES ? 0 : stg + 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += acc2[i][j] * (1.0f / F16_LO_SCALE);
+    }
+    if (pf) t1 = clock64();
+    // the two chunk groups meet: group 1 parks its fragments (lane-major, conflict-free), group 0 adds them
+    float* red = smem;
+    if (kg == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) red[(nsub * 32 + i) * 32 + lane] = acc[i >> 2][i & 3];
+    }
+    __syncthreads();
+    if (kg == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i >> 2][i & 3] += red[(nsub * 32 + i) * 32 + lane];
+    }
+    if (pf) t2 = clock64();
+    // accumulator fragment: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+    if (ks == 1) {
+      if (kg == 0) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int m = m0 + mt * 16 + fg + h * 8;
+            if (m < M) {
+              const int b = m / a.T_out;
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) {
+                const int n = n0 + nsub * 32 + nt * 8 + 2 * ft;
+                if (n < a.N) {
+                  float2 v = make_float2(acc[mt * 4 + nt][2 * h], acc[mt * 4 + nt][2 * h + 1]);
+                  const float2 bv = *reinterpret_cast<const float2*>(a.bias + n);
+                  v.x += bv.x; v.y += bv.y;
+                  if (a.emb) { const float2 e = *reinterpret_cast<const float2*>(a.emb + (size_t)b * a.emb_ld + n); v.x += e.x; v.y += e.y; }
+                  if (a.residual) { const float2 r = *reinterpret_cast<const float2*>(a.residual + (size_t)m * a.N + n); v.x += r.x; v.y += r.y; }
+                  *reinterpret_cast<float2*>(a.out + (size_t)m * a.N + n) = v;
+                }
+              }
+            }
+          }
+      }
+      if (pf) t3 = clock64();
+    } else {
+      float* mine = partials + ((size_t)tile * ks + crank) * (CT * WN);
+      if (o.defer) {   // the consumer sums the slices: publish and go straight to the grid barrier
+        if (kg == 0) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt)
+                __stcg(reinterpret_cast<float2*>(mine + (mt * 16 + fg + h * 8) * WN + nsub * 32 + nt * 8 + 2 * ft),
+                       make_float2(acc[mt * 4 + nt][2 * h], acc[mt * 4 + nt][2 * h + 1]));
+        }
+        __syncthreads();
+        if (pf) { const long long t4 = clock64(); prof[0] += t1 - t0; prof[1] += t2 - t1; prof[2] += t4 - t2; prof[25] += 1; }
+        continue;
+      }
+      if (kg == 0) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+              __stcg(reinterpret_cast<float2*>(mine + (mt * 16 + fg + h * 8) * WN + nsub * 32 + nt * 8 + 2 * ft),
+                     make_float2(acc[mt * 4 + nt][2 * h], acc[mt * 4 + nt][2 * h + 1]));
+      }
+      __syncthreads();
+      if (tid == 0) {
+        red_release_add(sems + tile, 1u);   // releases the CTA's partial tile (ordered before it by the barrier above)
+        spin_until(sems + tile, (unsigned)ks, abort_flag);   // acquires the other slices' tiles
+      }
+      __syncthreads();
+      if (pf) t3 = clock64();
+      // this slice's share of the tile: elements [e0, e1), summed over the slices in slice order
+      const int e0 = (crank * (CT * WN)) / ks, e1 = ((crank + 1) * (CT * WN)) / ks;
+      const float* base = partials + (size_t)tile * ks * (CT * WN);
+      for (int idx = e0 + tid; idx < e1; idx += 256) {
+        // every slice's value and the epilogue operands are requested together (one L2 round trip), then summed in slice order
+        const int m = m0 + (idx >> 7), n = n0 + (idx & (WN - 1));
+        const bool live = m < M && n < a.N;
+        float pv[P_MAX_KS_WIDE];
+#pragma unroll
+        for (int j = 0; j < P_MAX_KS_WIDE; ++j) pv[j] = j < ks ? __ldcg(base + (size_t)j * (CT * WN) + idx) : 0.f;
+        float bv = 0.f, ev = 0.f, rv = 0.f;
+        if (live) {
+          bv = a.bias[n];
+          if (a.emb) ev = a.emb[(size_t)(m / a.T_out) * a.emb_ld + n];
+          if (a.residual) rv = a.residual[(size_t)m * a.N + n];
+        }
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < P_MAX_KS_WIDE; ++j)
+          if (j < ks) v += pv[j];
+        if (live) {
+          v += bv;
+          if (a.emb) v += ev;
+          if (a.residual) v += rv;
+          a.out[(size_t)m * a.N + n] = v;
+        }
+      }
+    }
+    __syncthreads();   // the staging buffers are reused by the next unit
+    if (pf) {
+      const long long t4 = clock64();
+      prof[0] += t1 - t0;      // chunk stream (copies + MMA)
+      prof[1] += t2 - t1;      // chunk groups -> CTA partial
+      prof[2] += t3 - t2;      // publish + wait for the other slices (or the direct epilogue when ks == 1)
+      prof[24] += t4 - t3;     // distributed slice reduction + epilogue
+      prof[25] += 1;
+    }
+  }
+}
+
+// value of element (m, c) of a deferred token-GEMM output: slices summed in slice order, then + bias (+ emb) (+ residual) --
+// the same order of additions as the in-op epilogue of p_conv_wide.  All loads are requested together.
+__device__ __forceinline__ float part_value(const PartSrc& ps, int T, int m, int c) {
+  const float* base = ps.part + ((size_t)((m >> 5) * ps.tiles_n + (c >> 7)) * ps.ks) * (CT * WN) + (m & 31) * WN + (c & (WN - 1));
+  float pv[P_MAX_KS_WIDE];
+#pragma unroll
+  for (int j0 = 0; j0 < P_MAX_KS_WIDE; j0 += 8) {   // whole groups of 8 slices are skipped (uniform branch)
+    if (j0 < ps.ks) {
+#pragma unroll
+      for (int j = j0; j < j0 + 8; ++j) pv[j] = j < ps.ks ? __ldcg(base + (size_t)j * (CT * WN)) : 0.f;
+    } else {
+#pragma unroll
+      for (int j = j0; j < j0 + 8; ++j) pv[j] = 0.f;
+    }
+  }
+  const float bv = ps.bias[c];
+  const float ev = ps.emb ? ps.emb[(size_t)(m / T) * ps.emb_ld + c] : 0.f;
+  const float rv = ps.res ? ps.res[(size_t)m * ps.N + c] : 0.f;
+  float v = 0.f;
+#pragma unroll
+  for (int j0 = 0; j0 < P_MAX_KS_WIDE; j0 += 8) {
+    if (j0 < ps.ks) {
+#pragma unroll
+      for (int j = j0; j < j0 + 8; ++j)
+        if (j < ps.ks) v += pv[j];
+    }
+  }
+  v += bv;
+  if (ps.emb) v += ev;
+  if (ps.res) v += rv;
+  return v;
+}
+
 // ---- GroupNorm unit (128 threads = one half of the CTA), arithmetic of gn_kernel -------------------------------
 __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, float* red) {
   const int tid = threadIdx.x & 127;
@@ -800,8 +1234,11 @@ __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, 
   const int C = C1 + C2;
   const int cg = C / 32;
   const int n = T * cg;
+  const bool deferred = o.ps.ks > 0;
+  float* fin = const_cast<float*>(o.in0);   // a deferred first input is finalised in place for its later consumers
   auto load = [&](int idx) -> float {
     const int t = idx / cg, c = g * cg + idx % cg;
+    if (deferred && c < C1) return part_value(o.ps, T, b * T + t, c);
     return c < C1 ? in1[((size_t)b * T + t) * C1 + c] : in2[((size_t)b * T + t) * C2 + (c - C1)];
   };
   auto block_sum = [&](float v) -> float {
@@ -812,22 +1249,41 @@ __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, 
     named_bar(1 + half, 128);
     return red[0] + red[1] + red[2] + red[3];
   };
+  // the unit's values are read once and kept in registers for the three passes (n <= 6 * 128 in this network; longer
+  // groups re-read); same per-thread element order and the same summation trees as gn_kernel
+  constexpr int PGN_CACHE = 6;
+  float xc[PGN_CACHE], gc[PGN_CACHE], bc[PGN_CACHE];
+#pragma unroll
+  for (int k = 0; k < PGN_CACHE; ++k) {   // scale / shift are requested with the values (not after the statistics)
+    const int i = tid + 128 * k;
+    const int c = g * cg + (i < n ? i % cg : 0);
+    gc[k] = gamma[c]; bc[k] = beta[c];
+  }
+#pragma unroll
+  for (int k = 0; k < PGN_CACHE; ++k) { const int i = tid + 128 * k; xc[k] = i < n ? load(i) : 0.f; }
   float s = 0.f;
-  for (int i = tid; i < n; i += 128) s += load(i);
+#pragma unroll
+  for (int k = 0; k < PGN_CACHE; ++k) if (tid + 128 * k < n) s += xc[k];
+  for (int i = tid + 128 * PGN_CACHE; i < n; i += 128) s += load(i);
   const float mean = block_sum(s) / (float)n;
   float q = 0.f;
-  for (int i = tid; i < n; i += 128) { const float d = load(i) - mean; q += d * d; }
+#pragma unroll
+  for (int k = 0; k < PGN_CACHE; ++k) if (tid + 128 * k < n) { const float d = xc[k] - mean; q += d * d; }
+  for (int i = tid + 128 * PGN_CACHE; i < n; i += 128) { const float d = load(i) - mean; q += d * d; }
   const float var = block_sum(q) / (float)n;
   const float rstd = 1.0f / sqrtf(var + 1e-5f);
-  for (int i = tid; i < n; i += 128) {
+  auto emit = [&](int i, float x, float gm, float bt) {
     const int t = i / cg, c = g * cg + i % cg;
-    const float x = load(i);
-    float y = (x - mean) * rstd * gamma[c] + beta[c];
+    float y = (x - mean) * rstd * gm + bt;
     if (silu) y = y / (1.0f + expf(-y));
     const size_t oo = ((size_t)b * T + t) * C + c;
     out[oo] = y;
     if (raw) raw[oo] = x;
-  }
+    if (deferred && c < C1) fin[((size_t)b * T + t) * C1 + c] = x;
+  };
+#pragma unroll
+  for (int k = 0; k < PGN_CACHE; ++k) if (tid + 128 * k < n) emit(tid + 128 * k, xc[k], gc[k], bc[k]);
+  for (int i = tid + 128 * PGN_CACHE; i < n; i += 128) { const int c = g * cg + i % cg; emit(i, load(i), gamma[c], beta[c]); }
 }
 
 // ---- small-M linears: rows [mb, mb+8) staged in shared memory (xs, row stride K), two output columns per warp pass ----
@@ -838,20 +1294,29 @@ __device__ __forceinline__ void p_lin_cols(const POp& o, const float* xs, int mb
   const float* bias = o.w1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_stride = G * 8;
-  for (int nA = cta * 8 + warp; nA < N; nA += 2 * n_stride) {
+  // the weight rows of pass i+1 are requested before pass i is multiplied (two column pairs in flight per warp)
+  float4 wa[7], wb[7], na[7], nb[7];
+  float ba = 0.f, bb = 0.f, nba = 0.f, nbb = 0.f;
+  auto fetch = [&](int nA, float4 (&ra)[7], float4 (&rb)[7], float& bA, float& bB) {
     const int nB = nA + n_stride;
-    const bool hasB = nB < N;
-    float4 wa[7], wb[7];
+    bA = nA < N ? __ldg(bias + nA) : 0.f;
+    bB = nB < N ? __ldg(bias + nB) : 0.f;
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
       const int k = lane * 4 + 128 * i;
-      wa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      wb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k < K) {
-        wa[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)nA * K + k));
-        if (hasB) wb[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)nB * K + k));
+      ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K && nA < N) {
+        ra[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)nA * K + k));
+        if (nB < N) rb[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)nB * K + k));
       }
     }
+  };
+  fetch(cta * 8 + warp, wa, wb, ba, bb);
+  for (int nA = cta * 8 + warp; nA < N; nA += 2 * n_stride) {
+    const int nB = nA + n_stride;
+    const bool hasB = nB < N;
+    fetch(nA + 2 * n_stride, na, nb, nba, nbb);
     float accA[8], accB[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) { accA[r] = 0.f; accB[r] = 0.f; }
@@ -878,26 +1343,27 @@ __device__ __forceinline__ void p_lin_cols(const POp& o, const float* xs, int mb
         accA[r] += __shfl_xor_sync(0xffffffffu, accA[r], of);
         accB[r] += __shfl_xor_sync(0xffffffffu, accB[r], of);
       }
-    if (lane == 0) {
+    // every lane holds all 16 sums: lane r finishes row r of column A, lane 8 + r row r of column B
+    if (lane < 16) {
+      const int r = lane & 7, c = lane >> 3;
+      float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int n = c ? nB : nA;
-        if (c && !hasB) break;
-        const float bv = bias[n];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          if (r < rows) {
-            float v = (c ? accB[r] : accA[r]) + bv;
-            if (out_silu) v = v / (1.0f + expf(-v));
-            const int row = mb + r;
-            if (o.lab) v = v + o.w2[(size_t)o.lab[row] * EMB + n];    // label_emb row (label_add_kernel)
-            if (o.in1) v = v + o.in1[(size_t)row * N + n];            // projected context (accumulating linear)
-            o.out0[(size_t)row * N + n] = v;
-            if (o.out1) o.out1[(size_t)row * N + n] = v / (1.0f + expf(-v));   // SiLU once, for the consumer
-          }
-        }
+      for (int rr = 0; rr < 8; ++rr)
+        if (r == rr) sum = c ? accB[rr] : accA[rr];
+      const int n = c ? nB : nA;
+      if (r < rows && (c == 0 || hasB)) {
+        float v = sum + (c ? bb : ba);
+        if (out_silu) v = v / (1.0f + expf(-v));
+        const int row = mb + r;
+        if (o.lab) v = v + o.w2[(size_t)o.lab[row] * EMB + n];    // label_emb row (label_add_kernel)
+        if (o.in1) v = v + o.in1[(size_t)row * N + n];            // projected context (accumulating linear)
+        o.out0[(size_t)row * N + n] = v;
+        if (o.out1) o.out1[(size_t)row * N + n] = v / (1.0f + expf(-v));   // SiLU once, for the consumer
       }
     }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { wa[i] = na[i]; wb[i] = nb[i]; }
+    ba = nba; bb = nbb;
   }
 }
 
@@ -911,6 +1377,8 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
   const int half = tid >> 7;
   const int n_ops = pa.n_emb + pa.n_prog;
   unsigned target = 0;
+  unsigned seq = 0;   // ops executed so far (selects the arrival-counter bank)
+  bool pre_issued = false;   // the current op's first weight copies were issued before the barrier in front of it
   auto fetch_op = [&](int slot, int oi) {
     const int* src = reinterpret_cast<const int*>(pa.ops + oi);
     int* dst = reinterpret_cast<int*>(&sop[slot]);
@@ -964,10 +1432,20 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
             for (int mb = 0; mb < M; mb += 8) {
               const int rows = M - mb < 8 ? M - mb : 8;
               __syncthreads();
-              for (int i = tid; i < rows * K; i += 256) {
-                float x = o.in0[(size_t)mb * K + i];
-                if (in_silu) x = x / (1.0f + expf(-x));
-                smem[i] = x;
+              // independent loads are requested eight at a time (a plain loop pays one L2 round trip per iteration)
+              for (int i0 = tid; i0 < rows * K; i0 += 8 * 256) {
+                float xv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { const int i = i0 + 256 * q; xv[q] = i < rows * K ? o.in0[(size_t)mb * K + i] : 0.f; }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const int i = i0 + 256 * q;
+                  if (i < rows * K) {
+                    float x = xv[q];
+                    if (in_silu) x = x / (1.0f + expf(-x));
+                    smem[i] = x;
+                  }
+                }
               }
               __syncthreads();
               p_lin_cols(o, smem, mb, rows, cta, G);
@@ -994,13 +1472,25 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
             break;
           }
           case P_CONV:
-            p_conv<MODE>(o, smem, pa.partials, pa.sems, &s_last, cta, G, pa.prof);
+            if (MODE != 0 && o.wide) {
+              // arrival counters: ops alternate between two banks; the bank of the previous op is cleared here (its
+              // waiters all passed the grid barrier in front of this op, its next users arrive behind the one after it)
+              unsigned* bank = pa.sems + (size_t)(seq & 1u) * pa.sem_bank;
+              p_conv_wide<(MODE == 0 ? 1 : MODE)>(o, smem, pa.partials, bank, pa.sync + 1, pre_issued, cta, G, pa.prof);
+            } else {
+              p_conv<MODE>(o, smem, pa.partials, pa.sems + 2 * (size_t)pa.sem_bank, &s_last, cta, G, pa.prof);
+            }
             break;
           case P_ATTN: {   // one (batch, head) unit per CTA pass, same arithmetic as attn_kernel
             const int heads = o.i2;
             const int n_units = pa.B * heads;
             for (int u = cta; u < n_units; u += G)
-              attn_unit(o.in0, o.i0, o.i1, heads, o.f0, o.out0, u / heads, u % heads, smem, tid, 256, [] { __syncthreads(); });
+              if (o.ps.ks > 0)
+                attn_unit(o.in0, o.i0, o.i1, heads, o.f0, o.out0, u / heads, u % heads, smem, tid, 256, [] { __syncthreads(); },
+                          [&](const float*, int m, int c) { return part_value(o.ps, o.i1, m, c); });
+              else
+                attn_unit(o.in0, o.i0, o.i1, heads, o.f0, o.out0, u / heads, u % heads, smem, tid, 256, [] { __syncthreads(); },
+                          [](const float* p, int, int) { return *p; });
             break;
           }
           case P_OUTCONV: {   // last conv (224 -> 1) + the DDPM update of the element it produces
@@ -1041,12 +1531,22 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
           default:
             break;
         }
+        if (cta == 0) {
+          unsigned* other = pa.sems + (size_t)((seq + 1u) & 1u) * pa.sem_bank;
+          for (int i = tid; i < pa.sem_bank; i += 256) other[i] = 0u;
+        }
+        ++seq;
         if (has_next && tid < (int)(sizeof(POp) / sizeof(int))) reinterpret_cast<int*>(&sop[slot ^ 1])[tid] = next_word;
-        __syncthreads();
-        if (has_next && sop[slot ^ 1].type == P_CONV) p_conv_prefetch(sop[slot ^ 1], cta, G);
+        __syncthreads();   // the op is complete in this CTA, the next descriptor is in place
         long long t_op1 = 0;
         if (profiled) t_op1 = clock64();
-        if (!grid_barrier(pa.sync, target, (unsigned)G, &s_ok)) return;
+        grid_arrive(pa.sync);
+        pre_issued = false;
+        if (MODE != 0 && has_next && sop[slot ^ 1].type == P_CONV && sop[slot ^ 1].wide) {
+          wide_preissue(sop[slot ^ 1], smem, cta);
+          pre_issued = true;
+        }
+        if (!grid_wait(pa.sync, target, (unsigned)G, &s_ok)) return;
         if (profiled) {
           long long* pr = pa.prof + ((cta == 0 ? 0 : 8) + sop[slot].type) * 3;
           pr[0] += t_op1 - t_op0;
@@ -1096,7 +1596,7 @@ struct Lane {
   DevBuf pool, emb_all, temb, e1, emb, t_cur, x0a, x0b, xcur, state;
   // persistent sampler: op descriptors, K-slice scratch, semaphores, barrier word + abort flag
   DevBuf emb_silu, ctxv, p_ops, p_partials, p_sems, p_sync, p_prof;
-  int p_B = -1, p_n_emb = 0, p_n_prog = 0, p_smem = 0, p_grid = 0, p_split = -1;
+  int p_B = -1, p_n_emb = 0, p_n_prog = 0, p_smem = 0, p_grid = 0, p_split = -1, p_wide = -1, p_sem_bank = 0;
   const float* p_ctx = nullptr;
   const int64_t* p_lab = nullptr;
   cudaStream_t stream = nullptr;
@@ -1130,10 +1630,11 @@ struct Lane {
 struct surfd_unet {
   int L = 0, max_batch = 0;
   bool pdl = true;     // programmatic dependent launch between the step's kernels (falls back to false if capture rejects it)
-  int sampler = 0;     // surfd_sample: 0 = CUDA-graph replay of the step (default: measured faster, 1.71 vs 1.89 ms/step at batch 8),
-                       // 1 = persistent cooperative kernel
+  int sampler = 1;     // surfd_sample: 1 = persistent cooperative kernel (default), 0 = CUDA-graph replay of the step kernels
+                       // (also the fallback when cooperative launch is unavailable)
   int sampler_sms = 0; // CTAs of the persistent kernel (0 = one per SM)
   bool profile = false; // persistent kernel: per-op-type cycle counters (diagnostics)
+  int persist_defer = 1; // wide units: consumers sum the K slices of the GEMM in front of them (0 = exchange inside the GEMM op)
   int persist_split = 1; // token-GEMM K split of the persistent kernel: 0 = the graph path's rule (bit-identical samples),
                          // 1 = as many slices as fit in ONE round of the resident CTAs (faster; same fp32-class accuracy)
   int num_sms = 0;
@@ -1401,7 +1902,12 @@ static int persist_max_grid(int smem, int num_sms, int* out) {
 
 // op descriptors for batch B on lane `ln` (cached per (B, ctx, lab))
 static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const int64_t* lab, int grid) {
-  if (ln.p_B == B && ln.p_ctx == ctx && ln.p_lab == lab && ln.p_grid == grid && ln.p_split == u->persist_split) return 0;
+  const bool wide = u->persist_split == 1 && u->precision != 0;
+  // diagnostics (tools/sampler_profile.py): SURFD_UNET_DEBUG bit 1 = no deferred exchange,
+  // bit 2 = every op replaced by an empty one (barrier cost only; results are garbage)
+  const char* dbg_env = getenv("SURFD_UNET_DEBUG");
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
+  if (ln.p_B == B && ln.p_ctx == ctx && ln.p_lab == lab && ln.p_grid == grid && ln.p_split == u->persist_split && ln.p_wide == (int)wide) return 0;
   const auto& h = u->hdr;
   std::vector<POp> ops;
   auto blank = [](int type) { POp o; memset(&o, 0, sizeof(o)); o.type = type; return o; };
@@ -1429,7 +1935,7 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
   }
   const int n_emb = (int)ops.size();
   size_t max_partial_tiles = 0, max_tiles = 1;
-  int smem_floats = CONV_SMEM / (int)sizeof(float);
+  int smem_floats = (wide ? WIDE_SMEM : CONV_SMEM) / (int)sizeof(float);
   if (smem_floats < 8 * EMB) smem_floats = 8 * EMB;
   for (const auto& r : u->prog) {
     switch (r[0]) {
@@ -1461,12 +1967,28 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
         a.emb = r[20] >= 0 ? ln.emb_all.as<float>() + r[20] : nullptr;
         a.emb_ld = u->emb_cols;
         a.residual = r[21] >= 0 ? ln.buf(r[21]) : nullptr;
-        // same K-split rule as the graph path (decided per sample, so results do not depend on B)
         const int tiles = (a.N / CT) * (int)cdiv((int64_t)a.T_out, CT);
         int ksplit = 1;
+        if (wide) {
+          // wide units: 32 x 128 tiles; one round -- every (tile, slice) unit gets its own CTA, and a slice keeps at
+          // least one chunk pair; K is only split when all slices of all tiles are co-resident
+          o.wide = 1;
+          o.tiles_n = (int)cdiv((int64_t)a.N, WN); o.tiles_m = (int)cdiv((int64_t)B * a.T_out, CT);
+          const size_t nt = (size_t)o.tiles_n * o.tiles_m;
+          ksplit = (int)((int64_t)grid / (int64_t)nt);
+          if (ksplit > chunks / 2) ksplit = chunks / 2;
+          if (ksplit > P_MAX_KS_WIDE) ksplit = P_MAX_KS_WIDE;
+          if (ksplit < 1) ksplit = 1;
+          o.ks = ksplit;
+          if (nt > max_tiles) max_tiles = nt;
+          if (ksplit > 1 && nt * ksplit * (WN / CT) > max_partial_tiles) max_partial_tiles = nt * ksplit * (WN / CT);
+          ops.push_back(o);
+          break;
+        }
         o.tiles_n = a.N / CT; o.tiles_m = (int)cdiv((int64_t)B * a.T_out, CT);
         const size_t nt = (size_t)o.tiles_n * o.tiles_m;
         if (u->persist_split == 0) {
+          // same K-split rule as the graph path (decided per sample, so results do not depend on B)
           while (ksplit < KSPLIT && tiles * ksplit < 148 && chunks >= 16 * (ksplit * 2)) ksplit *= 2;
         } else {
           // one round: every (tile, slice) unit gets its own CTA (any slice count, not only powers of two); a slice
@@ -1503,14 +2025,35 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
         return set_error(SURFD_BAD_ARGUMENT, "unknown op in program", __FILE__, __LINE__);
     }
   }
+  // deferred K-slice exchange: a wide token GEMM whose output is consumed first by the very next op (GroupNorm of it, or the
+  // attention that follows a qkv projection) leaves its partial tiles to that op
+  if (wide && u->persist_defer && !(dbg & 2)) {
+    for (size_t i = 0; i + 1 < ops.size(); ++i) {
+      POp& c = ops[i];
+      POp& nx = ops[i + 1];
+      if (c.type != P_CONV || !c.wide || c.ks <= 1) continue;
+      // (attention consumers were measured slower with the slice sum in their load phase than the qkv GEMM's own exchange)
+      if (!(nx.type == P_GN && nx.in0 == c.conv.out)) continue;
+      if (nx.type == P_GN && nx.i0 != c.conv.N) continue;
+      if (nx.type == P_ATTN && (c.conv.emb || c.conv.residual || 3 * nx.i0 != c.conv.N)) continue;
+      c.defer = 1;
+      nx.ps.part = ln.p_partials.as<float>();   // patched below once the scratch buffer has its final address
+      nx.ps.bias = c.conv.bias; nx.ps.emb = c.conv.emb; nx.ps.res = c.conv.residual;
+      nx.ps.ks = c.ks; nx.ps.tiles_n = c.tiles_n; nx.ps.emb_ld = c.conv.emb_ld; nx.ps.N = c.conv.N;
+    }
+  }
+  if (dbg & 4) for (auto& o : ops) o.type = 0;
+  SURFD_TRY(ln.p_partials.reserve((max_partial_tiles ? max_partial_tiles : 1) * CT * CT * sizeof(float)));
+  for (auto& o : ops) if (o.ps.ks > 0) o.ps.part = ln.p_partials.as<float>();
   SURFD_TRY(ln.p_ops.reserve(ops.size() * sizeof(POp)));
   SURFD_CUDA(cudaMemcpy(ln.p_ops.p, ops.data(), ops.size() * sizeof(POp), cudaMemcpyHostToDevice));
-  SURFD_TRY(ln.p_partials.reserve((max_partial_tiles ? max_partial_tiles : 1) * CT * CT * sizeof(float)));
-  SURFD_TRY(ln.p_sems.reserve(max_tiles * sizeof(unsigned)));
-  SURFD_TRY(ln.p_sync.reserve(2 * sizeof(unsigned)));
+  max_tiles = (max_tiles + 63) / 64 * 64;
+  SURFD_TRY(ln.p_sems.reserve(3 * max_tiles * sizeof(unsigned)));
+  SURFD_TRY(ln.p_sync.reserve(P_SYNC_WORDS * sizeof(unsigned)));
   SURFD_TRY(ln.p_prof.reserve(48 * sizeof(long long)));
-  SURFD_CUDA(cudaMemset(ln.p_sems.p, 0, max_tiles * sizeof(unsigned)));
+  ln.p_sem_bank = (int)max_tiles;
   ln.p_n_emb = n_emb; ln.p_n_prog = (int)ops.size() - n_emb; ln.p_smem = smem_floats * (int)sizeof(float);
+  ln.p_wide = (int)wide;
   ln.p_B = B; ln.p_ctx = ctx; ln.p_lab = lab; ln.p_grid = grid; ln.p_split = u->persist_split;
   return 0;
 }
@@ -1530,7 +2073,8 @@ static int sample_persistent(surfd_unet* u, int B, int n_steps, const int64_t* t
   else SURFD_TRY(persist_max_grid<2>(ln.p_smem, u->num_sms, &max_grid));
   SURFD_REQUIRE(max_grid >= grid, "persistent sampler kernel: the requested CTAs cannot all be resident");
   SURFD_CUDA(cudaMemcpyAsync(ln.xcur.p, noise_dev, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, st));   // x_T = noise row 0
-  SURFD_CUDA(cudaMemsetAsync(ln.p_sync.p, 0, 2 * sizeof(unsigned), st));
+  SURFD_CUDA(cudaMemsetAsync(ln.p_sync.p, 0, P_SYNC_WORDS * sizeof(unsigned), st));
+  SURFD_CUDA(cudaMemsetAsync(ln.p_sems.p, 0, 3 * (size_t)ln.p_sem_bank * sizeof(unsigned), st));
   if (ctx) {   // projected context: constant over the loop, computed once (the graph path accumulates it every step)
     const dim3 g1((unsigned)cdiv(EMB, 8), (unsigned)cdiv(B, 8));
     const auto& h = u->hdr;
@@ -1541,7 +2085,7 @@ static int sample_persistent(surfd_unet* u, int B, int n_steps, const int64_t* t
   pa.n_steps = n_steps; pa.B = B; pa.L = L; pa.n_pass = guidance != 1.0f ? 2 : 1;
   pa.tmap = tmap_dev; pa.coef = coef_dev; pa.noise = noise_dev; pa.noise_stride = (long long)B * L; pa.guidance = guidance;
   pa.x = ln.xcur.as<float>(); pa.x0a = ln.x0a.as<float>();
-  pa.partials = ln.p_partials.as<float>(); pa.sems = ln.p_sems.as<unsigned>(); pa.sync = ln.p_sync.as<unsigned>();
+  pa.partials = ln.p_partials.as<float>(); pa.sems = ln.p_sems.as<unsigned>(); pa.sem_bank = ln.p_sem_bank; pa.sync = ln.p_sync.as<unsigned>();
   pa.prof = nullptr;
   if (u->profile) {
     SURFD_CUDA(cudaMemsetAsync(ln.p_prof.p, 0, 48 * sizeof(long long), st));

@@ -375,8 +375,9 @@ class UNetSampler:
         _lib.check(self.lib.surfd_unet_set_lanes(self._h, int(n)))
 
     def set_sampler(self, mode, n_sms=0):
-        """sample() engine: 0 = CUDA-graph replay of the step kernels (default), 1 = persistent cooperative kernel (`n_sms`
-        CTAs, 0 = one per SM), 2 = the same with the graph path's K split (bit-identical to mode 0)"""
+        """sample() engine: 1 = persistent cooperative kernel with wide token-GEMM units (default; `n_sms` CTAs, 0 = one per
+        SM), 0 = CUDA-graph replay of the step kernels, 2 = persistent kernel with the graph path's units and K split
+        (bit-identical to mode 0)"""
         _lib.check(self.lib.surfd_unet_set_sampler(self._h, int(mode), int(n_sms)))
 
     def profile(self, on=None):

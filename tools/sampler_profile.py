@@ -32,21 +32,26 @@ def run(B, mode, n_sms=0, prof=False):
 for prec, B in ((1, 8),):
     net.set_precision(prec)
     print("---- token-GEMM precision mode %d (0 fp32 FFMA, 1 3xTF32, 2 TF32) ----" % prec)
-    t0, r0 = run(B, 0)
-    t2, r2 = run(B, 2)
-    t1, r1 = run(B, 1)
-    t1b, _ = run(B, 1, 140)
-    print("B=%d: graph %.3f ms/step | persistent(graph split) %.3f | persistent(one round) %.3f | one round on 140 CTAs %.3f | maxdiff %.2e / %.2e"
-          % (B, t0, t2, t1, t1b, float((r2 - r0).abs().max()), float((r1 - r0).abs().max())))
-    for mode in (2, 1):
+    if os.environ.get("SURFD_UNET_DEBUG"):
+        t1, r1 = run(B, 1)
+        t1b, _ = run(B, 1, 100)
+        print("debug %s B=%d: persistent(wide) %.3f ms/step | on 100 CTAs %.3f" % (os.environ["SURFD_UNET_DEBUG"], B, t1, t1b))
+    else:
+        t0, r0 = run(B, 0)
+        t2, r2 = run(B, 2)
+        t1, r1 = run(B, 1)
+        t1b, _ = run(B, 1, 100)
+        print("B=%d: graph %.3f ms/step | persistent(graph split) %.3f | persistent(wide) %.3f | wide on 100 CTAs %.3f | maxdiff %.2e / %.2e"
+              % (B, t0, t2, t1, t1b, float((r2 - r0).abs().max()), float((r1 - r0).abs().max())))
+    for mode in (1,):
         t, _ = run(B, mode, 0, True)
         p = net.profile()
         net.profile(False)
         ph = net.last_gemm_phases
         if ph["units"]:
             print("    first CTA token-GEMM phases (us per unit): " + ", ".join("%s %.2f" % (k, v / ph["units"] / 1965.0) for k, v in ph.items() if k not in ("units", "chunks_warp0", "wait_cycles")),
-                  "| units per step %.1f | warp 0: %.1f chunks per unit, %.2f us waiting for copies per chunk"
-                  % (ph["units"] / 100, ph["chunks_warp0"] / ph["units"], ph["wait_cycles"] / max(1, ph["chunks_warp0"]) / 1965.0))
+                  "| units per step %.1f | %.2f chunk pairs per unit, %.2f us until the first pair has landed"
+                  % (ph["units"] / 100, ph["chunks_warp0"] / ph["units"], ph["wait_cycles"] / ph["units"] / 1965.0))
         print("  mode %d profiled %.3f ms/step; per op type (us per op: body / barrier, count per step)" % (mode, t))
         for cta in ("first_cta", "last_cta"):
             row = []
@@ -56,10 +61,3 @@ for prec, B in ((1, 8),):
             tot = sum(v[0] + v[1] for v in p[cta].values()) / 100 / 1965.0
             print("   ", cta, "| ".join(row), "| total %.0f us/step" % tot)
 
-# graph replay split over concurrent lanes (streams)
-net.set_precision(1); net.set_sampler(0)
-for lanes in (1, 2, 4):
-    net.set_lanes(lanes)
-    t, _ = run(8, 0)
-    print("graph replay, batch 8 over %d lane(s): %.3f ms/step" % (lanes, t))
-net.set_lanes(1)
