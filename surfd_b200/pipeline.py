@@ -27,6 +27,9 @@ class SurfDPipeline:
         budget = max(1, n_sms - mc_parallel)
         self.decoder = UdfDecoder(ae_state, latent_dim, device=device, packed=packed_decoder, max_chunk_points=budget * 256)
         self.decoder.set_sm_budget(budget)
+        # the persistent sampler kernel (one CTA per SM, cooperative launch) leaves the same SMs free: the marching-cubes
+        # replays of the previous batch keep running next to it instead of delaying its launch
+        self.sampler.set_sampler(1, budget)
         self.mcs = [MarchingCubes(device) for _ in range(mc_parallel)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(mc_parallel)]
         self.schedule_cache = {}
