@@ -135,6 +135,9 @@ def bench_gpu(args):
                          packed_unet=(blob_u, prog.cpu()), packed_decoder=blob_d)
     if args.precision == "tf32":
         pipe.decoder.set_precision(1)
+    if args.split:
+        ns, nd = (int(v) for v in args.split.split(","))
+        pipe.overlap_split = (ns, nd) if ns > 0 else None
     noise_host = make_noise(world, rank, BATCH, STEPS_DDPM, LAT).pin_memory()
     noise_dev = noise_host.to(dev)
 
@@ -362,6 +365,8 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
                     help="decoder 512x512 layer GEMMs: tf32 = tcgen05 kind::tf32 (default; the precision class of the reference's own GPU runs, "
                          "udf within 2e-4 of fp32), fp32 = FFMA.  The UNet token GEMMs are 3xTF32 (fp32-class) in both.")
+    ap.add_argument("--split", default="0,0", help="SMs of the sampler kernel, SMs of the decoder GEMMs while consecutive batches run "
+                                                       "concurrently (the rest runs the marching-cubes replays); 0,0 = one stream")
     ap.add_argument("--ddpm-steps", type=int, default=STEPS_DDPM, help="profiling runs only (ncu launch lists); the metric is defined at 1000")
     ap.add_argument("--resolution", type=int, default=RES, help="profiling runs only; the N=1 workload is 256")
     args = ap.parse_args()

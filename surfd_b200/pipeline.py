@@ -30,6 +30,11 @@ class SurfDPipeline:
         # the persistent sampler kernel (one CTA per SM, cooperative launch) leaves the same SMs free: the marching-cubes
         # replays of the previous batch keep running next to it instead of delaying its launch
         self.sampler.set_sampler(1, budget)
+        self.sm_budget = budget
+        # generate_many(): (sampler SMs, decoder SMs) while consecutive batches run concurrently; None = the sampler of batch
+        # i+1 runs between the lattices and the face filters of batch i on one stream
+        self.overlap_split = None
+        self.sampler_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self.mcs = [MarchingCubes(device) for _ in range(mc_parallel)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(mc_parallel)]
         self.schedule_cache = {}
@@ -111,8 +116,9 @@ class SurfDPipeline:
     def generate_many(self, noises, N, contexts=None, labels=None, guidance=1.0, n_steps=1000, use_fast_grid_filler=True,
                       noise_schedule="cosine", timings=None, to_host=False, io=None):
         """Several independent batches, software-pipelined on one GPU: while batch i's marching-cubes replays (one warp
-        each, latency-bound) run on their side streams, the sampler of batch i+1 already runs on the main stream; batch
-        i's face filters follow it.  Each batch must fit one wave (B <= mc_parallel).
+        each, latency-bound) run on their side streams, the sampler of batch i+1 already runs -- on the main stream between
+        batch i's lattices and face filters, or (self.overlap_split set) on its own stream and SM partition next to the
+        whole extraction of batch i.  Each batch must fit one wave (B <= mc_parallel).
         noises: list of [n_steps+1, B, L] tensors, on the device or in (pinned) host memory -- host tensors are copied
         inside the loop, just before their sampler is launched.  to_host=True also copies every batch's latents/meshes
         to host memory as soon as they are complete.  `io` (dict) accumulates h2d/d2h byte counts.
@@ -148,16 +154,55 @@ class SurfDPipeline:
                 meshes, stats = self.extract(lat, N, use_fast_grid_filler, timings=timings)
                 out.append(host(lat, meshes) + (stats,) if to_host else (lat, meshes, stats))
             return out
-        lat = sample(0)
-        for i in range(K):
-            B = lat.shape[0]
-            wave = list(range(B))
-            fields = self._launch_fields(wave, lat, N, use_fast_grid_filler, 0.1, marks)
-            lat_next = sample(i + 1) if i + 1 < K else None
-            meshes, stats = [None] * B, [None] * B
-            self._finish_fields(wave, lat, N, fields, meshes, stats, marks)
-            out.append(host(lat, meshes) + (stats,) if to_host else (lat, meshes, stats))
-            lat = lat_next
+        split = self.overlap_split if K > 1 else None
+        if split is None:
+            lat = sample(0)
+            for i in range(K):
+                B = lat.shape[0]
+                wave = list(range(B))
+                fields = self._launch_fields(wave, lat, N, use_fast_grid_filler, 0.1, marks)
+                lat_next = sample(i + 1) if i + 1 < K else None
+                meshes, stats = [None] * B, [None] * B
+                self._finish_fields(wave, lat, N, fields, meshes, stats, marks)
+                out.append(host(lat, meshes) + (stats,) if to_host else (lat, meshes, stats))
+                lat = lat_next
+            self._account(marks, timings)
+            return out
+        # Concurrent mode: the sampler of batch i+1 (one persistent kernel on `split[0]` SMs, its own stream) runs NEXT TO the
+        # whole extraction of batch i (lattices, replays, face filters on the remaining SMs).  The sampler is latency-bound
+        # and the extraction is interleaved with host round trips (query counts per GridFiller level, mesh sizes), so
+        # each hides the other's idle time; a batch costs max(sampler, extraction) instead of their sum.
+        main = torch.cuda.current_stream(self.device)
+        n_samp, n_dec = split
+        self.sampler.set_sampler(1, n_samp)
+        self.decoder.set_sm_budget(n_dec)
+        try:
+            side = self.sampler_stream
+            side.wait_stream(main)
+            done = []
+            with torch.cuda.stream(side):
+                lat = sample(0)
+                ev = torch.cuda.Event(); ev.record(side); done.append(ev)
+            keep = [lat]
+            for i in range(K):
+                main.wait_event(done[i])
+                lat_next = None
+                if i + 1 < K:
+                    with torch.cuda.stream(side):
+                        lat_next = sample(i + 1)
+                        ev = torch.cuda.Event(); ev.record(side); done.append(ev)
+                    keep.append(lat_next)
+                B = lat.shape[0]
+                wave = list(range(B))
+                fields = self._launch_fields(wave, lat, N, use_fast_grid_filler, 0.1, marks)
+                meshes, stats = [None] * B, [None] * B
+                self._finish_fields(wave, lat, N, fields, meshes, stats, marks)
+                out.append(host(lat, meshes) + (stats,) if to_host else (lat, meshes, stats))
+                lat = lat_next
+            main.wait_stream(side)
+        finally:
+            self.sampler.set_sampler(1, self.sm_budget)
+            self.decoder.set_sm_budget(self.sm_budget)
         self._account(marks, timings)
         return out
 

@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-( time timeout -s KILL 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
-( time timeout -s KILL 600 python bench.py --steps 3 --warmup 3 ) > gpurun_out/bench_tf32.json 2> gpurun_out/bench_tf32.err
-cat gpurun_out/bench_tf32.json; tail -5 gpurun_out/bench_tf32.err
+( time timeout -s KILL 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 2 ) > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+cat gpurun_out/bench_n2.json | cut -c1-700; tail -5 gpurun_out/bench_n2.err
