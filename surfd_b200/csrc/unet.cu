@@ -98,9 +98,11 @@ gn_kernel(const float* __restrict__ in1, int C1, const float* __restrict__ in2, 
 // CTA tile 32 tokens x 32 outputs; 8 warps split the K chunks (32 channels each) and reduce through smem.
 // ------------------------------------------------------------------------------------------------
 struct Seg {
-  const float* A;  // [B][T_in][Cin]
+  const float* A;  // [B][T_in][Cin]  (wide units: channels [0, C1) of a virtual concat [A | A2])
   const float* W;  // [taps][N][Cin]
   int Cin, taps, stride, up, T_in;
+  const float* A2; // wide units only: channels [C1, Cin) come from A2 [B][T_in][Cin - C1]; C1 == Cin: single source
+  int C1;
 };
 struct ConvArgs {
   Seg seg[2];
@@ -111,6 +113,12 @@ struct ConvArgs {
   int emb_ld;
   const float* residual;  // [B][T_out][N] or null
   float* out;             // [B][T_out][N]
+  // wide units only: GroupNorm(32, Cin) (+ SiLU) of segment 0's input fused into this GEMM (pn_on): the unit computes the
+  // statistics of the (sample, group) pairs its K slice touches and normalises the token rows in shared memory
+  const float* pn_gamma;
+  const float* pn_beta;
+  int pn_on, pn_silu, pn_cg, pn_logT;
+  float pn_inv_cg;
 };
 
 constexpr int CT = 32;        // tile edge
@@ -853,7 +861,7 @@ constexpr int WN = 128;                                // outputs per wide tile
 constexpr int W_STAGES = 4;
 constexpr int WTP = 40;                                // padded row (floats): 8-byte fragment loads of rows g, g+1, .. hit disjoint banks
 constexpr int W_STAGE = (2 * CT + 2 * WN) * WTP;       // floats per stage
-constexpr int WIDE_SMEM = W_STAGES * W_STAGE * (int)sizeof(float);
+constexpr int WIDE_SMEM = (W_STAGES * W_STAGE + 1536) * (int)sizeof(float);   // staging ring + fused-GroupNorm tables (PN_TAB)
 constexpr int P_MAX_KS_WIDE = 32;
 
 __device__ __forceinline__ void mma_tf32_nv(float* c, const uint32_t* a, const uint32_t* b) {
@@ -955,19 +963,22 @@ __device__ __forceinline__ void wide_issue(const ConvArgs& a, int n_chunks0, int
       const int s = f < n_chunks0 ? 0 : 1;
       const Seg& sg = a.seg[s];
       const int q = s ? f - n_chunks0 : f;
-      const int cpt = sg.Cin / CT;
-      const int tap = q / cpt, c = q - tap * cpt;
+      const int cb = q / sg.taps, tap = q - cb * sg.taps;   // block-major: the taps of one 32-channel block are adjacent chunks
       if (what & 2) {
         const int T_eff = sg.up ? 2 * sg.T_in : sg.T_in;
         const int src = rl * sg.stride + tap - (sg.taps >> 1);
         const bool ok = rok && src >= 0 && src < T_eff;
         const int st = sg.up ? (src >> 1) : src;
-        const float* arow = sg.A + (ok ? ((size_t)rb * sg.T_in + st) * sg.Cin : (size_t)0) + c * CT + 4 * lp;
+        const bool second = cb * CT >= sg.C1;
+        const float* base = second ? sg.A2 : sg.A;
+        const int ld = second ? sg.Cin - sg.C1 : sg.C1;
+        const int coff = second ? cb * CT - sg.C1 : cb * CT;
+        const float* arow = base + (ok ? ((size_t)rb * sg.T_in + st) * ld : (size_t)0) + coff + 4 * lp;
         const uint32_t da = (uint32_t)__cvta_generic_to_shared(stg + (g * CT + cr) * WTP + 4 * lp);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(arow), "r"(ok ? 16 : 0) : "memory");
       }
       if (what & 1) {
-        const float* wbase = sg.W + (size_t)tap * a.N * sg.Cin + c * CT + 4 * lp;
+        const float* wbase = sg.W + (size_t)tap * a.N * sg.Cin + cb * CT + 4 * lp;
         const uint32_t dw = (uint32_t)__cvta_generic_to_shared(stg + (2 * CT + g * WN + cr) * WTP + 4 * lp);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -975,6 +986,117 @@ __device__ __forceinline__ void wide_issue(const ConvArgs& a, int n_chunks0, int
           const bool okw = n < a.N;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dw + j * (32 * WTP * 4)), "l"(wbase + (size_t)(okw ? n : 0) * sg.Cin),
                        "r"(okw ? 16 : 0) : "memory");
+        }
+      }
+    }
+  }
+}
+
+// x / d for 0 <= x < 2^20 with inv = 1.0f / d (reciprocal multiply + one correction step)
+__device__ __forceinline__ int div_small(int x, int d, float inv) {
+  int q = (int)((float)x * inv);
+  const int r = x - q * d;
+  if (r < 0) --q;
+  else if (r >= d) ++q;
+  return q;
+}
+
+// Fused GroupNorm, part 1: statistics of the (sample, group) pairs touched by this unit's segment-0 chunks, and the
+// scale / shift of its channel range, into the tables behind the staging ring.  One warp per pair; a pair's T * cg values
+// are padded to whole 32-lane slots and the slots of up to 32 / slots-per-pair pairs are requested together (one L2 round
+// trip per round; two-pass mean / variance in registers like gn_kernel).  tab: gam[512] bet[512] mu[256] rs[256].
+constexpr int PN_TAB = 1536;
+struct PnRange { int c_lo, g_lo, ng; };
+__device__ __forceinline__ PnRange wide_prenorm_stats(const ConvArgs& a, int n_chunks0, int f_begin, int f_end, int m0, float* tab) {
+  PnRange R{0, 0, 0};
+  const int fe0 = f_end < n_chunks0 ? f_end : n_chunks0;
+  if (f_begin >= fe0) return R;
+  const Seg& sg = a.seg[0];
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cb_lo = f_begin / sg.taps, cb_hi = (fe0 - 1) / sg.taps;
+  const int c_lo = cb_lo * CT, c_hi = (cb_hi + 1) * CT;
+  const int cg = a.pn_cg, T = 1 << a.pn_logT;
+  const int g_lo = c_lo / cg, g_hi = (c_hi - 1) / cg;
+  const int ng = g_hi - g_lo + 1;
+  R.c_lo = c_lo; R.g_lo = g_lo; R.ng = ng;
+  float* gam = tab; float* bet = tab + 512; float* mu = tab + 1024; float* rs = tab + 1280;
+  for (int c = c_lo + tid; c < c_hi; c += 256) { gam[c - c_lo] = a.pn_gamma[c]; bet[c - c_lo] = a.pn_beta[c]; }
+  const int M = a.B * a.T_out;
+  const int rows = M - m0 < CT ? M - m0 : CT;
+  const int nb = rows >> a.pn_logT, b0 = m0 >> a.pn_logT;
+  const int P = nb * ng;
+  const int n = T * cg;
+  const int sp = (n + 31) >> 5;          // slots per pair
+  const int kpr = 32 / sp;               // pairs per round (sp <= 21 in this network; the host checks sp <= 32)
+  const int C1 = sg.C1, C2 = sg.Cin - sg.C1;
+  const int pw = P > warp ? (P - warp + 7) >> 3 : 0;   // pairs of this warp: warp, warp + 8, ...
+  for (int k0 = 0; k0 < pw; k0 += kpr) {
+    float xv[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      xv[q] = 0.f;
+      const int kk = q / sp, k = k0 + kk;
+      const int e = (q - kk * sp) * 32 + lane;
+      if (kk < kpr && k < pw && e < n) {
+        const int pr = warp + 8 * k;
+        const int bl = pr / ng, gi = pr - bl * ng;
+        const int t = div_small(e, cg, a.pn_inv_cg), cc = e - t * cg;
+        const int c = (g_lo + gi) * cg + cc;
+        const size_t m = (size_t)(b0 + bl) * T + t;
+        xv[q] = c < C1 ? __ldcg(sg.A + m * C1 + c) : __ldcg(sg.A2 + m * C2 + (c - C1));
+      }
+    }
+    for (int kk = 0; kk < kpr && k0 + kk < pw; ++kk) {
+      float sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (q / sp == kk) sum += xv[q];
+#pragma unroll
+      for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
+      const float mean = sum / (float)n;
+      float sq = 0.f;
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (q / sp == kk && (q - kk * sp) * 32 + lane < n) { const float d = xv[q] - mean; sq += d * d; }
+#pragma unroll
+      for (int of = 16; of > 0; of >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, of);
+      if (lane == 0) {
+        const int pr = warp + 8 * (k0 + kk);
+        mu[pr] = mean;
+        rs[pr] = 1.0f / sqrtf(sq / (float)n + 1e-5f);
+      }
+    }
+  }
+  return R;
+}
+
+// Fused GroupNorm, part 2: the landed token rows of a stage's segment-0 chunks are normalised (+ SiLU) in place.  Rows that
+// the copy zero-filled (conv padding, rows past the batch) stay zero.  Thread -> column tid & 31, rows (tid >> 5) + 8 i.
+__device__ __forceinline__ void wide_prenorm_apply(const ConvArgs& a, int n_chunks0, int f_begin, int f_end, int m0, int pair, float* stg,
+                                                   const float* tab, const PnRange& R) {
+  const Seg& sg = a.seg[0];
+  const int tid = (int)threadIdx.x, j = tid & 31, r0 = tid >> 5;
+  const int T = 1 << a.pn_logT;
+  const int M = a.B * a.T_out;
+  const float* gam = tab; const float* bet = tab + 512; const float* mu = tab + 1024; const float* rs = tab + 1280;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int f = f_begin + 2 * pair + g;
+    if (f < f_end && f < n_chunks0) {
+      const int cb = f / sg.taps, tap = f - cb * sg.taps;
+      const int c = cb * CT + j;
+      const int gi = div_small(c, a.pn_cg, a.pn_inv_cg) - R.g_lo;
+      const float gm = gam[c - R.c_lo], bt = bet[c - R.c_lo];
+      float* base = stg + g * CT * WTP + j;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 8 * i;
+        const int src = (r & (T - 1)) + tap - (sg.taps >> 1);
+        if (m0 + r < M && src >= 0 && src < T) {
+          const int pr = (r >> a.pn_logT) * R.ng + gi;
+          float y = (base[r * WTP] - mu[pr]) * rs[pr] * gm + bt;
+          if (a.pn_silu) y = y / (1.0f + expf(-y));
+          base[r * WTP] = y;
         }
       }
     }
@@ -1052,6 +1174,9 @@ __device__ __forceinline__ void p_conv_wide(const POp& o, float* smem, float* pa
       if (p < n_pairs) issue_pair(p, smem + p * W_STAGE, first_what);
       else asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    float* tab = smem + W_STAGES * W_STAGE;
+    PnRange pn{0, 0, 0};
+    if (a.pn_on) pn = wide_prenorm_stats(a, n_chunks0, f_begin, f_end, m0, tab);   // overlaps the copies in flight
     int stg = 0;
     for (int p = 0; p < n_pairs; ++p) {
       asm volatile("cp.async.wait_group %0;" ::"n"(W_STAGES - 2) : "memory");
@@ -1060,6 +1185,10 @@ __device__ __forceinline__ void p_conv_wide(const POp& o, float* smem, float* pa
       const int nxt = p + W_STAGES - 1;
       if (nxt < n_pairs) issue_pair(nxt, smem + (stg == 0 ? W_STAGES - 1 : stg - 1) * W_STAGE, 3);
       else asm volatile("cp.async.commit_group;" ::: "memory");
+      if (a.pn_on && f_begin + 2 * p < n_chunks0) {
+        wide_prenorm_apply(a, n_chunks0, f_begin, f_end, m0, p, smem + stg * W_STAGE, tab, pn);
+        __syncthreads();
+      }
       if (f_begin + 2 * p + kg < f_end) {
         const float* As = smem + stg * W_STAGE + kg * CT * WTP;
         const float* Ws = smem + stg * W_STAGE + (2 * CT + kg * WN + nsub * 32) * WTP;
@@ -1634,6 +1763,9 @@ struct surfd_unet {
                        // (also the fallback when cooperative launch is unavailable)
   int sampler_sms = 0; // CTAs of the persistent kernel (0 = one per SM)
   bool profile = false; // persistent kernel: per-op-type cycle counters (diagnostics)
+  int persist_fuse_gn = 0; // wide units: 1 = GroupNorm ops are folded into the token GEMM behind them.  Off: measured slower (1.95 vs
+                           // 1.33 ms/step) -- the per-unit statistics prologue is instruction-bound and every GEMM then pays the in-op
+                           // K-slice exchange instead of leaving it to the GroupNorm op.  SURFD_UNET_DEBUG bit 4 switches it on.
   int persist_defer = 1; // wide units: consumers sum the K slices of the GEMM in front of them (0 = exchange inside the GEMM op)
   int persist_split = 1; // token-GEMM K split of the persistent kernel: 0 = the graph path's rule (bit-identical samples),
                          // 1 = as many slices as fit in ONE round of the resident CTAs (faster; same fp32-class accuracy)
@@ -1903,7 +2035,7 @@ static int persist_max_grid(int smem, int num_sms, int* out) {
 // op descriptors for batch B on lane `ln` (cached per (B, ctx, lab))
 static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const int64_t* lab, int grid) {
   const bool wide = u->persist_split == 1 && u->precision != 0;
-  // diagnostics (tools/sampler_profile.py): SURFD_UNET_DEBUG bit 1 = no deferred exchange,
+  // diagnostics (tools/sampler_profile.py): SURFD_UNET_DEBUG bit 1 = no deferred exchange, bit 3 = no fused GroupNorm,
   // bit 2 = every op replaced by an empty one (barrier cost only; results are garbage)
   const char* dbg_env = getenv("SURFD_UNET_DEBUG");
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
@@ -1961,6 +2093,7 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
           const int64_t* q = &r[5 + 7 * s];
           a.seg[s].A = ln.buf(q[0]); a.seg[s].Cin = (int)q[1]; a.seg[s].taps = (int)q[2]; a.seg[s].stride = (int)q[3];
           a.seg[s].up = (int)q[4]; a.seg[s].T_in = (int)q[5]; a.seg[s].W = u->w(q[6]);
+          a.seg[s].A2 = nullptr; a.seg[s].C1 = a.seg[s].Cin;
           chunks += a.seg[s].taps * (a.seg[s].Cin / CT);
         }
         a.bias = u->w(r[19]);
@@ -2024,6 +2157,54 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
       default:
         return set_error(SURFD_BAD_ARGUMENT, "unknown op in program", __FILE__, __LINE__);
     }
+  }
+  // fused GroupNorm: a GroupNorm op whose output feeds segment 0 of the wide token GEMM right behind it disappears -- the
+  // GEMM's units normalise their own token rows (statistics recomputed per unit from the raw input, which the producer
+  // finalised); a later 1x1 skip segment that read the GroupNorm's raw concat copy reads the two concat sources instead
+  if (wide && (u->persist_fuse_gn || (dbg & 16)) && !(dbg & 8)) {
+    struct RawSrc { const float* raw; const float* in1; const float* in2; int C1; };
+    std::vector<RawSrc> raws;
+    std::vector<POp> fused;
+    for (size_t i = 0; i < ops.size(); ++i) {
+      POp g = ops[i];
+      if (g.type == P_CONV && g.conv.nseg > 1) {
+        for (const auto& rsrc : raws)
+          if (g.conv.seg[1].A == rsrc.raw) { g.conv.seg[1].A = rsrc.in1; g.conv.seg[1].A2 = rsrc.in2; g.conv.seg[1].C1 = rsrc.C1; }
+      }
+      if (g.type == P_GN && i + 1 < ops.size() && ops[i + 1].type == P_CONV && ops[i + 1].wide) {
+        POp c = ops[i + 1];
+        Seg& s0 = c.conv.seg[0];
+        const int C1 = g.i0, C2 = g.i1, T = g.i2, C = C1 + C2;
+        bool ok = s0.A == g.out0 && s0.stride == 1 && s0.up == 0 && s0.T_in == T && c.conv.T_out == T && s0.Cin == C &&
+                  (T & (T - 1)) == 0 && T <= CT && C1 % CT == 0 && C % 32 == 0;
+        if (ok) {
+          int n_chunks = 0;
+          for (int sgi = 0; sgi < c.conv.nseg; ++sgi) n_chunks += c.conv.seg[sgi].taps * (c.conv.seg[sgi].Cin / CT);
+          const int per_unit = (n_chunks + c.ks - 1) / c.ks + 1;
+          const int channels = (per_unit / s0.taps + 2) * CT;
+          const int cg = C / 32;
+          const int ng_max = channels / cg + 2, nb = CT / T;
+          ok = channels <= 512 && nb * ng_max <= 256 && (T * cg + 31) / 32 <= 32;
+          if (ok) {
+            int logT = 0;
+            while ((1 << logT) < T) ++logT;
+            s0.A = g.in0; s0.A2 = g.in1; s0.C1 = C1;
+            c.conv.pn_on = 1; c.conv.pn_silu = g.i3; c.conv.pn_cg = cg; c.conv.pn_logT = logT; c.conv.pn_inv_cg = 1.0f / (float)cg;
+            c.conv.pn_gamma = g.w0; c.conv.pn_beta = g.w1;
+            if (g.out1) raws.push_back(RawSrc{g.out1, g.in0, g.in1, C1});
+            if (c.conv.nseg > 1) {
+              for (const auto& rsrc : raws)
+                if (c.conv.seg[1].A == rsrc.raw) { c.conv.seg[1].A = rsrc.in1; c.conv.seg[1].A2 = rsrc.in2; c.conv.seg[1].C1 = rsrc.C1; }
+            }
+            fused.push_back(c);
+            ++i;
+            continue;
+          }
+        }
+      }
+      fused.push_back(g);
+    }
+    ops.swap(fused);
   }
   // deferred K-slice exchange: a wide token GEMM whose output is consumed first by the very next op (GroupNorm of it, or the
   // attention that follows a qkv projection) leaves its partial tiles to that op

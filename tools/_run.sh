@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-( time timeout -s KILL 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 2 ) > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-cat gpurun_out/bench_n2.json | cut -c1-700; tail -5 gpurun_out/bench_n2.err
+timeout -s KILL 300 python tools/pipeline_probe.py 256 2>&1 | grep -v Warning > gpurun_out/pipeline_probe.txt
+grep -E "iter2|iter1" -A 9 gpurun_out/pipeline_probe.txt | tail -34
+tail -8 gpurun_out/pipeline_probe.txt
