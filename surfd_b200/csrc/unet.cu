@@ -1382,14 +1382,21 @@ __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, 
   // groups re-read); same per-thread element order and the same summation trees as gn_kernel
   constexpr int PGN_CACHE = 6;
   float xc[PGN_CACHE], gc[PGN_CACHE], bc[PGN_CACHE];
+  int tt[PGN_CACHE], cc[PGN_CACHE];   // (token, channel) of the cached elements, computed once (the unit is issue-bound on index math)
+  const float inv_cg = 1.0f / (float)cg;
+  auto load_tc = [&](int t, int c) -> float {
+    if (deferred && c < C1) return part_value(o.ps, T, b * T + t, c);
+    return c < C1 ? in1[((size_t)b * T + t) * C1 + c] : in2[((size_t)b * T + t) * C2 + (c - C1)];
+  };
 #pragma unroll
   for (int k = 0; k < PGN_CACHE; ++k) {   // scale / shift are requested with the values (not after the statistics)
     const int i = tid + 128 * k;
-    const int c = g * cg + (i < n ? i % cg : 0);
-    gc[k] = gamma[c]; bc[k] = beta[c];
+    const int t = i < n ? div_small(i, cg, inv_cg) : 0;
+    tt[k] = t; cc[k] = g * cg + (i < n ? i - t * cg : 0);
+    gc[k] = gamma[cc[k]]; bc[k] = beta[cc[k]];
   }
 #pragma unroll
-  for (int k = 0; k < PGN_CACHE; ++k) { const int i = tid + 128 * k; xc[k] = i < n ? load(i) : 0.f; }
+  for (int k = 0; k < PGN_CACHE; ++k) xc[k] = tid + 128 * k < n ? load_tc(tt[k], cc[k]) : 0.f;
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < PGN_CACHE; ++k) if (tid + 128 * k < n) s += xc[k];
@@ -1401,8 +1408,7 @@ __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, 
   for (int i = tid + 128 * PGN_CACHE; i < n; i += 128) { const float d = load(i) - mean; q += d * d; }
   const float var = block_sum(q) / (float)n;
   const float rstd = 1.0f / sqrtf(var + 1e-5f);
-  auto emit = [&](int i, float x, float gm, float bt) {
-    const int t = i / cg, c = g * cg + i % cg;
+  auto emit = [&](int t, int c, float x, float gm, float bt) {
     float y = (x - mean) * rstd * gm + bt;
     if (silu) y = y / (1.0f + expf(-y));
     const size_t oo = ((size_t)b * T + t) * C + c;
@@ -1411,8 +1417,8 @@ __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, 
     if (deferred && c < C1) fin[((size_t)b * T + t) * C1 + c] = x;
   };
 #pragma unroll
-  for (int k = 0; k < PGN_CACHE; ++k) if (tid + 128 * k < n) emit(tid + 128 * k, xc[k], gc[k], bc[k]);
-  for (int i = tid + 128 * PGN_CACHE; i < n; i += 128) { const int c = g * cg + i % cg; emit(i, load(i), gamma[c], beta[c]); }
+  for (int k = 0; k < PGN_CACHE; ++k) if (tid + 128 * k < n) emit(tt[k], cc[k], xc[k], gc[k], bc[k]);
+  for (int i = tid + 128 * PGN_CACHE; i < n; i += 128) { const int c = g * cg + i % cg; emit(i / cg, c, load(i), gamma[c], beta[c]); }
 }
 
 // ---- small-M linears: rows [mb, mb+8) staged in shared memory (xs, row stride K), two output columns per warp pass ----

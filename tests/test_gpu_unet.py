@@ -134,3 +134,27 @@ def test_persistent_sampler_precision_modes(mode):
     net.set_sampler(2); out = net.sample(S, noise)
     torch.cuda.synchronize(); net.status()
     assert torch.equal(out, ref), float((out - ref).abs().max())
+
+
+@pytest.mark.parametrize("debug,what", [("2", "in-op K-slice exchange (no deferral)"), ("16", "GroupNorm fused into the token GEMM")],
+                         ids=["no-defer", "fused-gn"])
+def test_persistent_sampler_variants_agree(debug, what, monkeypatch):
+    """The wide-unit engine's alternative dataflows (SURFD_UNET_DEBUG, read when the op list is built) compute the same
+    network: each stays within fp32-rounding distance of the graph engine, for plain, concat (output blocks) and
+    attention sites, conditioning and the CFG double pass."""
+    L, cond = 64, "img"
+    gen = torch.Generator().manual_seed(12)
+    S = U.SpacedSchedule(U.cosine_betas(), U.space_timesteps(1000, [6]))
+    sd = synth.synth_mdm(L, cond)
+    ref_net = U.UNetSampler(sd, L, cond, max_batch=8)
+    ref_net.set_sampler(0)
+    monkeypatch.setenv("SURFD_UNET_DEBUG", debug)
+    net = U.UNetSampler(sd, L, cond, max_batch=8)      # its op list is built under the variant
+    for B, guidance in ((8, 1.0), (3, 2.5)):
+        noise = torch.randn(7, B, L, generator=gen)
+        ctx = torch.randn(B, 512, generator=gen)
+        ref = ref_net.sample(S, noise, ctx, None, guidance)
+        out = net.sample(S, noise, ctx, None, guidance)
+        torch.cuda.synchronize(); net.status()
+        assert torch.isfinite(out).all()
+        assert float((out - ref).abs().max()) < 2e-4, (what, B, float((out - ref).abs().max()))

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout -s KILL 300 python tools/pipeline_probe.py 256 2>&1 | grep -v Warning > gpurun_out/pipeline_probe.txt
-grep -E "iter2|iter1" -A 9 gpurun_out/pipeline_probe.txt | tail -34
-tail -8 gpurun_out/pipeline_probe.txt
+( timeout -s KILL 600 python -m pytest tests/test_gpu_unet.py -x -q ) > gpurun_out/pytest_unet.log 2>&1; tail -8 gpurun_out/pytest_unet.log
+timeout -s KILL 200 python tools/sampler_profile.py 2>&1 | grep -v Warning | tail -6 > gpurun_out/sampler_debug.txt 2>&1
+cat gpurun_out/sampler_debug.txt
