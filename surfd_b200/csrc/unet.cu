@@ -103,6 +103,7 @@ struct Seg {
   int Cin, taps, stride, up, T_in;
   const float* A2; // wide units only: channels [C1, Cin) come from A2 [B][T_in][Cin - C1]; C1 == Cin: single source
   int C1;
+  const float* Wh; // tcgen05 units only: W with every 32-float block replaced by its fp16 split [32 x hi | 32 x lo] (same offsets)
 };
 struct ConvArgs {
   Seg seg[2];
@@ -692,6 +693,7 @@ struct PersistArgs {
   float* partials;            // [tile][slice][32*32] K-slice partial tiles
   unsigned* sems;             // per-tile arrival counters: [2 banks for the wide units | narrow units (zero between ops)] x sem_bank
   int sem_bank;
+  int use_tc;                 // precision mode 1: wide units run on tcgen05 (ops with wide == 2); the kernel holds 64 TMEM columns
   unsigned* sync;             // [0] barrier counter, [1] abort flag
   long long* prof;            // diagnostics (may be null): [cta 0 | cta G-1][op type][body cycles, barrier cycles, count]
 };
@@ -950,6 +952,7 @@ __device__ __forceinline__ void mma_chunk(const float* __restrict__ As, const fl
 
 // cp.async copies of chunk pair `pair` of a wide unit into stage `stg`: what & 1 = the 2 x 128 weight rows, what & 2 = the
 // 2 x 32 token rows.  Copy mapping: thread -> 16-byte piece tid & 7 of row tid >> 3 (8 consecutive lanes = one 128 B line).
+template <int PITCH>
 __device__ __forceinline__ void wide_issue(const ConvArgs& a, int n_chunks0, int f_begin, int f_end, int n0, int m0, int pair, float* stg, int what) {
   const int tid = (int)threadIdx.x;
   const int lp = tid & 7, cr = tid >> 3;
@@ -974,17 +977,17 @@ __device__ __forceinline__ void wide_issue(const ConvArgs& a, int n_chunks0, int
         const int ld = second ? sg.Cin - sg.C1 : sg.C1;
         const int coff = second ? cb * CT - sg.C1 : cb * CT;
         const float* arow = base + (ok ? ((size_t)rb * sg.T_in + st) * ld : (size_t)0) + coff + 4 * lp;
-        const uint32_t da = (uint32_t)__cvta_generic_to_shared(stg + (g * CT + cr) * WTP + 4 * lp);
+        const uint32_t da = (uint32_t)__cvta_generic_to_shared(stg + (g * CT + cr) * PITCH + 4 * lp);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(arow), "r"(ok ? 16 : 0) : "memory");
       }
       if (what & 1) {
         const float* wbase = sg.W + (size_t)tap * a.N * sg.Cin + cb * CT + 4 * lp;
-        const uint32_t dw = (uint32_t)__cvta_generic_to_shared(stg + (2 * CT + g * WN + cr) * WTP + 4 * lp);
+        const uint32_t dw = (uint32_t)__cvta_generic_to_shared(stg + (2 * CT + g * WN + cr) * PITCH + 4 * lp);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int n = n0 + cr + 32 * j;
           const bool okw = n < a.N;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dw + j * (32 * WTP * 4)), "l"(wbase + (size_t)(okw ? n : 0) * sg.Cin),
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dw + j * (32 * PITCH * 4)), "l"(wbase + (size_t)(okw ? n : 0) * sg.Cin),
                        "r"(okw ? 16 : 0) : "memory");
         }
       }
@@ -1106,6 +1109,7 @@ __device__ __forceinline__ void wide_prenorm_apply(const ConvArgs& a, int n_chun
 // weight rows of the first W_STAGES - 1 chunk pairs of this CTA's first unit of a wide token GEMM, requested while the
 // CTA waits at the grid barrier in front of that op (weights do not depend on the other CTAs).  Not committed: the
 // copies join the first commit group of the unit's own prologue.
+template <int PITCH, int STAGE_FLOATS, int N_STAGES>
 __device__ __forceinline__ void wide_preissue(const POp& o, float* smem, int cta) {
   const ConvArgs& a = o.conv;
   const int ks = o.ks;
@@ -1117,8 +1121,8 @@ __device__ __forceinline__ void wide_preissue(const POp& o, float* smem, int cta
   const int f_begin = (crank * n_chunks) / ks, f_end = ((crank + 1) * n_chunks) / ks;
   const int n_pairs = (f_end - f_begin + 1) >> 1;
 #pragma unroll
-  for (int p = 0; p < W_STAGES - 1; ++p)
-    if (p < n_pairs) wide_issue(a, n_chunks0, f_begin, f_end, n0, m0, p, smem + p * W_STAGE, 1);
+  for (int p = 0; p < N_STAGES - 1; ++p)
+    if (p < n_pairs) wide_issue<PITCH>(a, n_chunks0, f_begin, f_end, n0, m0, p, smem + p * STAGE_FLOATS, 1);
 }
 
 // spin until *p >= want (another CTA's release); false on abort / timeout (never expected)
@@ -1159,7 +1163,7 @@ __device__ __forceinline__ void p_conv_wide(const POp& o, float* smem, float* pa
     const int n_pairs = (f_end - f_begin + 1) >> 1;
 
     auto issue_pair = [&](int pair, float* stg, int what) {
-      wide_issue(a, n_chunks0, f_begin, f_end, n0, m0, pair, stg, what);
+      wide_issue<WTP>(a, n_chunks0, f_begin, f_end, n0, m0, pair, stg, what);
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
@@ -1350,6 +1354,338 @@ __device__ __forceinline__ float part_value(const PartSrc& ps, int T, int m, int
   return v;
 }
 
+// ---- wide token-GEMM units on the 5th-generation tensor cores (tcgen05 + TMEM), precision mode 1 --------------------------
+// Same unit, slicing, exchange and summation orders as p_conv_wide; the product moves from mma.sync to tcgen05.mma.
+// The fp16 two-term split (x = hi + lo / 4096) of the WEIGHTS is done once at load time: every 32-float block of a weight row
+// is stored as [32 x hi | 32 x lo] halves in the same 128 bytes (`Seg::Wh`, same offsets as the fp32 blob), so the per-step
+// weight stream has the same size and 16-byte cp.async copies drop the planes straight into K-major SWIZZLE_128B operand
+// tiles -- no conversion pass over the weights (the F2F conversions bounded both the mma.sync and a first tcgen05 variant:
+// 1.06 / 1.97 us per chunk pair).  Only the token rows (32 x 64 values per stage) are split on the fly.
+//   stage (40 KB, 4-deep ring) = one K = 64 step: W_hi, W_lo [128 rows x 128 B], A_hi, A_lo [32 rows x 128 B];
+//   one thread issues 4 k16-steps x 3 tcgen05.mma.kind::f16 (M = 128 outputs, N = 32 tokens): D1 += W_hi A_hi,
+//   D2 += W_lo A_hi + W_hi A_lo (32 TMEM columns each); tcgen05.commit -> mbarrier frees the stage for the copies of the
+//   pair three ahead; warps 0-3 read the accumulators (tcgen05.ld 32x32b: thread = output channel, 32 token values).
+constexpr int TC_STAGES = 4;
+constexpr int TC_OP_BYTES = (WN + CT) * 128 * 2;               // hi + lo planes of W (128 rows) and A (32 rows), 128-byte rows
+constexpr int TC_W_LO = WN * 128, TC_A_HI = 2 * WN * 128, TC_A_LO = 2 * WN * 128 + CT * 128;
+constexpr int TC_ASTG = 2 * CT * CT;                            // floats per fp32 token-row stage (2 chunks x 32 rows x 32)
+constexpr int TC_SMEM = 1024 + TC_STAGES * TC_OP_BYTES + TC_STAGES * TC_ASTG * 4;
+__device__ __forceinline__ uint8_t* tc_ops(float* smem) {   // operand ring: first 1024-byte boundary of the dynamic shared memory
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+}
+__device__ __forceinline__ float* tc_astage(float* smem) { return reinterpret_cast<float*>(tc_ops(smem) + TC_STAGES * TC_OP_BYTES); }
+
+__device__ __forceinline__ uint32_t tcw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tcw_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tcw_smem_u32(bar)), "r"(count));
+}
+// bounded wait: false after ~1 s (never expected; the caller aborts the run)
+__device__ __forceinline__ bool tcw_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(tcw_smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 24)) return false;
+  }
+  return true;
+}
+// K-major SWIZZLE_128B operand tile: 128-byte rows, 8-row atoms of 1024 B (same encoding as decoder_tc.cu)
+__device__ __forceinline__ uint64_t tcw_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D = F32 (bit 4), A = B = F16 (format 0), both K-major, N = 32 tokens, M = 128 outputs
+__device__ __forceinline__ uint32_t tcw_idesc() { return (1u << 4) | ((uint32_t)(CT >> 3) << 17) | ((uint32_t)(WN >> 4) << 24); }
+__device__ __forceinline__ void tcw_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcw_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tcw_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcw_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// per-CTA state of the tcgen05 path (static shared memory of the persistent kernel)
+struct TcState {
+  uint64_t stage_free[TC_STAGES];   // the MMAs that read operand stage s have completed
+  uint64_t done;                    // all MMAs of the unit have completed
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+// thread-local, uniform: commits issued so far per barrier (a wait targets the phase of the latest commit; waiting twice for
+// the same phase is harmless, so no wait is ever "owed")
+struct TcPhase { uint32_t stage[TC_STAGES]; uint32_t done; };
+
+// load-time split of a weight tensor: block of 32 floats -> [32 x hi | 32 x lo] halves in the same 128 bytes
+__global__ void split_weights_kernel(const float* __restrict__ W, float* __restrict__ Wh, size_t n_blocks) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per pair of floats
+  if (i >= n_blocks * 16) return;
+  const size_t blk = i >> 4;
+  const int j = (int)(i & 15);
+  const float2 x = *reinterpret_cast<const float2*>(W + blk * 32 + 2 * j);
+  uint32_t hi, lo;
+  split_f16x2(x, hi, lo);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(Wh + blk * 32);
+  dst[j] = hi;
+  dst[16 + j] = lo;
+}
+
+// cp.async copies of chunk pair `pair` of a tcgen05 unit: what & 1 = split weight rows straight into the swizzled operand
+// tiles of `ob`; what & 2 = fp32 token rows into `astg`.  Weight mapping: thread -> 16-byte piece tid & 7 of the 128-byte
+// block (pieces 0-3 hi, 4-7 lo) of row (tid >> 3) + 32 j: 8 consecutive lanes read one full line.
+__device__ __forceinline__ void tc_issue(const ConvArgs& a, int n_chunks0, int f_begin, int f_end, int n0, int m0, int pair, uint8_t* ob,
+                                         float* astg, int what) {
+  const int tid = (int)threadIdx.x;
+  const int lp = tid & 7, cr = tid >> 3;
+  const int m_row = m0 + cr;
+  const bool rok = m_row < a.B * a.T_out;
+  const int rb = m_row / a.T_out, rl = m_row - rb * a.T_out;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int f = f_begin + 2 * pair + g;
+    if (f < f_end) {
+      const int s = f < n_chunks0 ? 0 : 1;
+      const Seg& sg = a.seg[s];
+      const int q = s ? f - n_chunks0 : f;
+      const int cb = q / sg.taps, tap = q - cb * sg.taps;
+      if (what & 2) {
+        const int T_eff = sg.up ? 2 * sg.T_in : sg.T_in;
+        const int src = rl * sg.stride + tap - (sg.taps >> 1);
+        const bool ok = rok && src >= 0 && src < T_eff;
+        const int st = sg.up ? (src >> 1) : src;
+        const bool second = cb * CT >= sg.C1;
+        const float* base = second ? sg.A2 : sg.A;
+        const int ld = second ? sg.Cin - sg.C1 : sg.C1;
+        const int coff = second ? cb * CT - sg.C1 : cb * CT;
+        const float* arow = base + (ok ? ((size_t)rb * sg.T_in + st) * ld : (size_t)0) + coff + 4 * lp;
+        const uint32_t da = tcw_smem_u32(astg + (g * CT + cr) * CT + 4 * lp);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(arow), "r"(ok ? 16 : 0) : "memory");
+      }
+      if (what & 1) {
+        const float* wbase = sg.Wh + (size_t)tap * a.N * sg.Cin + cb * CT + 4 * lp;
+        const int plane = lp >> 2, p = 4 * g + (lp & 3);   // operand plane (hi / lo), 16-byte piece of the 128-byte K row
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rr = cr + 32 * j;
+          const int n = n0 + rr;
+          const bool okw = n < a.N;
+          const uint32_t dw = tcw_smem_u32(ob + (plane ? TC_W_LO : 0) + rr * 128 + ((p ^ (rr & 7)) << 4));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dw), "l"(wbase + (size_t)(okw ? n : 0) * sg.Cin), "r"(okw ? 16 : 0)
+                       : "memory");
+        }
+      }
+    }
+  }
+}
+
+// weight copies of the first two chunk pairs of this CTA's first unit, issued before the barrier in front of the op
+__device__ __forceinline__ void tc_preissue(const POp& o, float* smem, int cta) {
+  const ConvArgs& a = o.conv;
+  const int ks = o.ks;
+  if (cta >= o.tiles_n * o.tiles_m * ks) return;
+  const int crank = cta % ks, tile = cta / ks;
+  const int n0 = (tile % o.tiles_n) * WN, m0 = (tile / o.tiles_n) * CT;
+  const int n_chunks0 = a.seg[0].taps * (a.seg[0].Cin / CT);
+  const int n_chunks = n_chunks0 + (a.nseg > 1 ? a.seg[1].taps * (a.seg[1].Cin / CT) : 0);
+  const int f_begin = (crank * n_chunks) / ks, f_end = ((crank + 1) * n_chunks) / ks;
+  const int n_pairs = (f_end - f_begin + 1) >> 1;
+  uint8_t* ops = tc_ops(smem);
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+    if (p < n_pairs) tc_issue(a, n_chunks0, f_begin, f_end, n0, m0, p, ops + p * TC_OP_BYTES, nullptr, 1);
+}
+
+// returns false when a wait timed out (the caller aborts the run)
+__device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* partials, unsigned* sems, unsigned* abort_flag, bool pre_issued,
+                                          int cta, int G, long long* prof, TcState* ts, TcPhase& ph) {
+  const bool pf = prof != nullptr && cta == 0 && threadIdx.x == 0;
+  const ConvArgs& a = o.conv;
+  const int ks = o.ks;
+  const int n_units = o.tiles_n * o.tiles_m * ks;
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = a.B * a.T_out;
+  const int n_chunks0 = a.seg[0].taps * (a.seg[0].Cin / CT);
+  const int n_chunks = n_chunks0 + (a.nseg > 1 ? a.seg[1].taps * (a.seg[1].Cin / CT) : 0);
+  uint8_t* ops = tc_ops(smem);
+  float* astg = tc_astage(smem);
+  const uint32_t idesc = tcw_idesc();
+  const uint32_t tmem = ts->tmem_base;
+  bool ok = true;
+  // the operand stage of pair `pr` may be rewritten once the MMAs of its previous user have completed
+  auto wait_stage = [&](int s) {
+    if (ph.stage[s] > 0u && !tcw_mbar_wait(&ts->stage_free[s], (ph.stage[s] - 1u) & 1u)) ok = false;
+  };
+  for (int u = cta; u < n_units; u += G) {
+    long long t0 = 0, t1 = 0, t3 = 0;
+    if (pf) t0 = clock64();
+    const int crank = u % ks, tile = u / ks;
+    const int tn = tile % o.tiles_n, tm = tile / o.tiles_n;
+    const int n0 = tn * WN, m0 = tm * CT;
+    const int f_begin = (crank * n_chunks) / ks, f_end = ((crank + 1) * n_chunks) / ks;
+    const int n_pairs = (f_end - f_begin + 1) >> 1;
+    auto issue_pair = [&](int pair, int what) {
+      const int s = pair & (TC_STAGES - 1);
+      tc_issue(a, n_chunks0, f_begin, f_end, n0, m0, pair, ops + s * TC_OP_BYTES, astg + s * TC_ASTG, what);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // (every MMA of the previous unit / op has completed: its `done` wait; stages 0 and 1 are free)
+    const int first_what = (pre_issued && u == cta) ? 2 : 3;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (p < n_pairs) issue_pair(p, first_what);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int p = 0; p < n_pairs; ++p) {
+      const int s = p & (TC_STAGES - 1);
+      if (p + 2 < n_pairs) {
+        wait_stage((p + 2) & (TC_STAGES - 1));   // read by the MMAs of pair p - 2 (issued one iteration ago at the latest)
+        issue_pair(p + 2, 3);
+      } else {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      __syncthreads();   // pair p has landed for every thread
+      if (pf && p == 0) { prof[27] += clock64() - t0; prof[26] += n_pairs; }
+      {   // split this pair's token rows: thread -> 8 consecutive channels (one 16-byte piece of halves) of one row
+        const int rr = tid >> 3, pc = tid & 7;
+        const int g = pc >> 2, kk0 = (pc & 3) * 8;
+        const float* src = astg + s * TC_ASTG + (g * CT + rr) * CT + kk0;
+        float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
+        if (g == 1 && !(f_begin + 2 * p + 1 < f_end)) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }   // odd chunk count
+        uint4 hi, lo;
+        split_f16x2(make_float2(x0.x, x0.y), hi.x, lo.x);
+        split_f16x2(make_float2(x0.z, x0.w), hi.y, lo.y);
+        split_f16x2(make_float2(x1.x, x1.y), hi.z, lo.z);
+        split_f16x2(make_float2(x1.z, x1.w), hi.w, lo.w);
+        uint8_t* ob = ops + s * TC_OP_BYTES;
+        const int off = rr * 128 + ((pc ^ (rr & 7)) << 4);
+        *reinterpret_cast<uint4*>(ob + TC_A_HI + off) = hi;
+        *reinterpret_cast<uint4*>(ob + TC_A_LO + off) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (copies, split) -> tensor core reads
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = tcw_smem_u32(ops + s * TC_OP_BYTES);
+        const uint64_t whi = tcw_desc(sa), wlo = tcw_desc(sa + TC_W_LO), ahi = tcw_desc(sa + TC_A_HI), alo = tcw_desc(sa + TC_A_LO);
+        const bool has2 = f_begin + 2 * p + 1 < f_end;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // 16 halves = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+          if (k >= 2 && !has2) break;    // odd chunk count: the second half of the K row is absent
+          const uint32_t acc = (p | k) != 0 ? 1u : 0u;
+          tcw_mma(tmem + CT, wlo + (uint64_t)(2 * k), ahi + (uint64_t)(2 * k), idesc, acc);
+          tcw_mma(tmem, whi + (uint64_t)(2 * k), ahi + (uint64_t)(2 * k), idesc, acc);
+          tcw_mma(tmem + CT, whi + (uint64_t)(2 * k), alo + (uint64_t)(2 * k), idesc, 1u);
+        }
+        tcw_commit(&ts->stage_free[s]);
+        if (p == n_pairs - 1) tcw_commit(&ts->done);
+      }
+      ph.stage[s] += 1u;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    ph.done += 1u;
+    if (!tcw_mbar_wait(&ts->done, (ph.done - 1u) & 1u)) ok = false;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (pf) t1 = clock64();
+    float* mine = partials + ((size_t)tile * ks + crank) * (CT * WN);
+    if (warp < 4) {
+      uint32_t r1[32], r2[32];
+      tcw_ld32(tmem + ((uint32_t)(warp * 32) << 16), r1);
+      tcw_ld32(tmem + ((uint32_t)(warp * 32) << 16) + CT, r2);
+      const int n = n0 + warp * 32 + lane;
+      if (ks == 1) {
+        if (n < a.N) {
+          const float bv = a.bias[n];
+#pragma unroll
+          for (int j = 0; j < CT; ++j) {
+            const int m = m0 + j;
+            if (m < M) {
+              float v = __uint_as_float(r1[j]) + __uint_as_float(r2[j]) * (1.0f / F16_LO_SCALE);
+              v += bv;
+              if (a.emb) v += a.emb[(size_t)(m / a.T_out) * a.emb_ld + n];
+              if (a.residual) v += a.residual[(size_t)m * a.N + n];
+              a.out[(size_t)m * a.N + n] = v;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CT; ++j)
+          __stcg(mine + j * WN + warp * 32 + lane, __uint_as_float(r1[j]) + __uint_as_float(r2[j]) * (1.0f / F16_LO_SCALE));
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();   // the accumulators have been read: the next unit may overwrite them
+    if (ks > 1 && !o.defer) {
+      if (tid == 0) {
+        red_release_add(sems + tile, 1u);
+        spin_until(sems + tile, (unsigned)ks, abort_flag);
+      }
+      __syncthreads();
+      if (pf) t3 = clock64();
+      const int e0 = (crank * (CT * WN)) / ks, e1 = ((crank + 1) * (CT * WN)) / ks;
+      const float* base = partials + (size_t)tile * ks * (CT * WN);
+      for (int idx = e0 + tid; idx < e1; idx += 256) {
+        const int m = m0 + (idx >> 7), n = n0 + (idx & (WN - 1));
+        const bool live = m < M && n < a.N;
+        float pv[P_MAX_KS_WIDE];
+#pragma unroll
+        for (int j = 0; j < P_MAX_KS_WIDE; ++j) pv[j] = j < ks ? __ldcg(base + (size_t)j * (CT * WN) + idx) : 0.f;
+        float bv = 0.f, ev = 0.f, rv = 0.f;
+        if (live) {
+          bv = a.bias[n];
+          if (a.emb) ev = a.emb[(size_t)(m / a.T_out) * a.emb_ld + n];
+          if (a.residual) rv = a.residual[(size_t)m * a.N + n];
+        }
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < P_MAX_KS_WIDE; ++j)
+          if (j < ks) v += pv[j];
+        if (live) {
+          v += bv;
+          if (a.emb) v += ev;
+          if (a.residual) v += rv;
+          a.out[(size_t)m * a.N + n] = v;
+        }
+      }
+      __syncthreads();
+    }
+    if (pf) {
+      const long long t4 = clock64();
+      prof[0] += t1 - t0;                      // chunk stream (copies + split + MMA)
+      prof[2] += (t3 ? t3 : t4) - t1;          // accumulator read-out, publish (+ wait for the other slices)
+      prof[24] += t3 ? t4 - t3 : 0;            // distributed slice reduction + epilogue
+      prof[25] += 1;
+    }
+  }
+  return ok;
+}
+
 // ---- GroupNorm unit (128 threads = one half of the CTA), arithmetic of gn_kernel -------------------------------
 __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, float* red) {
   const int tid = threadIdx.x & 127;
@@ -1521,8 +1857,25 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
   };
   static_assert(sizeof(POp) <= 256 * sizeof(int), "descriptor must fit one word per thread");
   fetch_op(0, 0);
+  __shared__ TcState tcs;
+  TcPhase tph{};
+  const bool use_tc = MODE == 1 && pa.use_tc != 0;
+  if (use_tc) {   // tcgen05 path: mbarriers + 64 TMEM columns (two 128 x 32 fp32 accumulators), held for the whole run
+    if (tid == 0) {
+      for (int i = 0; i < TC_STAGES; ++i) tcw_mbar_init(&tcs.stage_free[i], 1);
+      tcw_mbar_init(&tcs.done, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(tcw_smem_u32(&tcs.tmem_base)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
   __syncthreads();
+  if (use_tc) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   int slot = 0;
+  [&]() {   // the op loop; `return` leaves it early when the run is aborted (TMEM is released below in every case)
   for (int iter = 0; iter < pa.n_steps; ++iter) {
     const int sidx = pa.n_steps - 1 - iter;
     for (int pass = 0; pass < pa.n_pass; ++pass) {
@@ -1607,7 +1960,12 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
             break;
           }
           case P_CONV:
-            if (MODE != 0 && o.wide) {
+            if (MODE == 1 && o.wide == 2) {
+              unsigned* bank = pa.sems + (size_t)(seq & 1u) * pa.sem_bank;
+              if (!p_conv_tc(o, smem, pa.partials, bank, pa.sync + 1, pre_issued, cta, G, pa.prof, &tcs, tph)) {
+                if (tid == 0) atomicExch(pa.sync + 1, 1u);   // a tensor-core wait timed out: abort the run (reported by surfd_unet_status)
+              }
+            } else if (MODE != 0 && o.wide) {
               // arrival counters: ops alternate between two banks; the bank of the previous op is cleared here (its
               // waiters all passed the grid barrier in front of this op, its next users arrive behind the one after it)
               unsigned* bank = pa.sems + (size_t)(seq & 1u) * pa.sem_bank;
@@ -1678,7 +2036,8 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
         grid_arrive(pa.sync);
         pre_issued = false;
         if (MODE != 0 && has_next && sop[slot ^ 1].type == P_CONV && sop[slot ^ 1].wide) {
-          wide_preissue(sop[slot ^ 1], smem, cta);
+          if (sop[slot ^ 1].wide == 2) tc_preissue(sop[slot ^ 1], smem, cta);
+          else wide_preissue<WTP, W_STAGE, W_STAGES>(sop[slot ^ 1], smem, cta);
           pre_issued = true;
         }
         if (!grid_wait(pa.sync, target, (unsigned)G, &s_ok)) return;
@@ -1691,6 +2050,11 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
         slot ^= 1;
       }
     }
+  }
+  }();
+  if (use_tc) {
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tcs.tmem_base) : "memory");
   }
 }
 
@@ -1731,7 +2095,7 @@ struct Lane {
   DevBuf pool, emb_all, temb, e1, emb, t_cur, x0a, x0b, xcur, state;
   // persistent sampler: op descriptors, K-slice scratch, semaphores, barrier word + abort flag
   DevBuf emb_silu, ctxv, p_ops, p_partials, p_sems, p_sync, p_prof;
-  int p_B = -1, p_n_emb = 0, p_n_prog = 0, p_smem = 0, p_grid = 0, p_split = -1, p_wide = -1, p_sem_bank = 0;
+  int p_B = -1, p_n_emb = 0, p_n_prog = 0, p_smem = 0, p_grid = 0, p_split = -1, p_wide = -1, p_sem_bank = 0, p_use_tc = 0;
   const float* p_ctx = nullptr;
   const int64_t* p_lab = nullptr;
   cudaStream_t stream = nullptr;
@@ -1769,6 +2133,7 @@ struct surfd_unet {
                        // (also the fallback when cooperative launch is unavailable)
   int sampler_sms = 0; // CTAs of the persistent kernel (0 = one per SM)
   bool profile = false; // persistent kernel: per-op-type cycle counters (diagnostics)
+  int persist_tc = 1;      // precision mode 1: the wide units' products run on tcgen05 (0 / SURFD_UNET_DEBUG bit 5: mma.sync)
   int persist_fuse_gn = 0; // wide units: 1 = GroupNorm ops are folded into the token GEMM behind them.  Off: measured slower (1.95 vs
                            // 1.33 ms/step) -- the per-unit statistics prologue is instruction-bound and every GEMM then pays the in-op
                            // K-slice exchange instead of leaving it to the GroupNorm op.  SURFD_UNET_DEBUG bit 4 switches it on.
@@ -1780,6 +2145,8 @@ struct surfd_unet {
   unsigned* h_abort = nullptr;   // pinned: abort flag of the last persistent run
   int precision = 1;   // token GEMMs: 0 fp32 FFMA, 1 3xTF32 mma.sync (fp32-class accuracy, default), 2 single-pass TF32
   DevBuf weights;
+  DevBuf weights_split;   // tcgen05 units: token-GEMM weights with every 32-float block stored as its fp16 hi | lo split
+  bool split_done = false;
   std::vector<int64_t> hdr, buf_sizes;
   std::vector<std::vector<int64_t>> prog;
   int emb_cols = 0;
@@ -1889,6 +2256,7 @@ extern "C" void surfd_unet_destroy(surfd_unet* u) {
   if (u->fork) cudaEventDestroy(u->fork);
   if (u->h_abort) cudaFreeHost(u->h_abort);
   u->weights.release();
+  u->weights_split.release();
   delete u;
 }
 
@@ -2041,12 +2409,29 @@ static int persist_max_grid(int smem, int num_sms, int* out) {
 // op descriptors for batch B on lane `ln` (cached per (B, ctx, lab))
 static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const int64_t* lab, int grid) {
   const bool wide = u->persist_split == 1 && u->precision != 0;
+  const char* dbg_env0 = getenv("SURFD_UNET_DEBUG");
+  const bool use_tc = wide && u->precision == 1 && u->persist_tc && !((dbg_env0 ? atoi(dbg_env0) : 0) & 32);
   // diagnostics (tools/sampler_profile.py): SURFD_UNET_DEBUG bit 1 = no deferred exchange, bit 3 = no fused GroupNorm,
   // bit 2 = every op replaced by an empty one (barrier cost only; results are garbage)
   const char* dbg_env = getenv("SURFD_UNET_DEBUG");
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
-  if (ln.p_B == B && ln.p_ctx == ctx && ln.p_lab == lab && ln.p_grid == grid && ln.p_split == u->persist_split && ln.p_wide == (int)wide) return 0;
+  if (ln.p_B == B && ln.p_ctx == ctx && ln.p_lab == lab && ln.p_grid == grid && ln.p_split == u->persist_split && ln.p_wide == (int)wide + (int)use_tc) return 0;
   const auto& h = u->hdr;
+  if (use_tc && !u->split_done) {
+    // load-time fp16 split of every token-GEMM weight tensor (same offsets as the fp32 blob), see p_conv_tc
+    SURFD_TRY(u->weights_split.reserve(u->n_floats * sizeof(float)));
+    for (const auto& r : u->prog) {
+      if (r[0] != OP_CONV) continue;
+      for (int sgi = 0; sgi < (int)r[4]; ++sgi) {
+        const int64_t* q = &r[5 + 7 * sgi];
+        const size_t n_blocks = (size_t)q[2] * (size_t)r[2] * (size_t)q[1] / 32;   // taps * N * Cin / 32
+        split_weights_kernel<<<(unsigned)cdiv((int64_t)(n_blocks * 16), 256), 256>>>(u->w(q[6]), u->weights_split.as<float>() + q[6], n_blocks);
+        SURFD_CHECK_LAUNCH();
+      }
+    }
+    SURFD_CUDA(cudaDeviceSynchronize());
+    u->split_done = true;
+  }
   std::vector<POp> ops;
   auto blank = [](int type) { POp o; memset(&o, 0, sizeof(o)); o.type = type; return o; };
   {
@@ -2073,7 +2458,7 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
   }
   const int n_emb = (int)ops.size();
   size_t max_partial_tiles = 0, max_tiles = 1;
-  int smem_floats = (wide ? WIDE_SMEM : CONV_SMEM) / (int)sizeof(float);
+  int smem_floats = (wide ? (use_tc ? (TC_SMEM > WIDE_SMEM ? TC_SMEM : WIDE_SMEM) : WIDE_SMEM) : CONV_SMEM) / (int)sizeof(float);
   if (smem_floats < 8 * EMB) smem_floats = 8 * EMB;
   for (const auto& r : u->prog) {
     switch (r[0]) {
@@ -2100,6 +2485,7 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
           a.seg[s].A = ln.buf(q[0]); a.seg[s].Cin = (int)q[1]; a.seg[s].taps = (int)q[2]; a.seg[s].stride = (int)q[3];
           a.seg[s].up = (int)q[4]; a.seg[s].T_in = (int)q[5]; a.seg[s].W = u->w(q[6]);
           a.seg[s].A2 = nullptr; a.seg[s].C1 = a.seg[s].Cin;
+          a.seg[s].Wh = use_tc ? u->weights_split.as<float>() + q[6] : nullptr;
           chunks += a.seg[s].taps * (a.seg[s].Cin / CT);
         }
         a.bias = u->w(r[19]);
@@ -2111,7 +2497,7 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
         if (wide) {
           // wide units: 32 x 128 tiles; one round -- every (tile, slice) unit gets its own CTA, and a slice keeps at
           // least one chunk pair; K is only split when all slices of all tiles are co-resident
-          o.wide = 1;
+          o.wide = use_tc ? 2 : 1;
           o.tiles_n = (int)cdiv((int64_t)a.N, WN); o.tiles_m = (int)cdiv((int64_t)B * a.T_out, CT);
           const size_t nt = (size_t)o.tiles_n * o.tiles_m;
           ksplit = (int)((int64_t)grid / (int64_t)nt);
@@ -2195,6 +2581,7 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
             int logT = 0;
             while ((1 << logT) < T) ++logT;
             s0.A = g.in0; s0.A2 = g.in1; s0.C1 = C1;
+            c.wide = 1;   // the fused normalisation lives in the mma.sync unit
             c.conv.pn_on = 1; c.conv.pn_silu = g.i3; c.conv.pn_cg = cg; c.conv.pn_logT = logT; c.conv.pn_inv_cg = 1.0f / (float)cg;
             c.conv.pn_gamma = g.w0; c.conv.pn_beta = g.w1;
             if (g.out1) raws.push_back(RawSrc{g.out1, g.in0, g.in1, C1});
@@ -2240,7 +2627,8 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
   SURFD_TRY(ln.p_prof.reserve(48 * sizeof(long long)));
   ln.p_sem_bank = (int)max_tiles;
   ln.p_n_emb = n_emb; ln.p_n_prog = (int)ops.size() - n_emb; ln.p_smem = smem_floats * (int)sizeof(float);
-  ln.p_wide = (int)wide;
+  ln.p_wide = (int)wide + (int)use_tc;
+  ln.p_use_tc = (int)use_tc;
   ln.p_B = B; ln.p_ctx = ctx; ln.p_lab = lab; ln.p_grid = grid; ln.p_split = u->persist_split;
   return 0;
 }
@@ -2272,7 +2660,7 @@ static int sample_persistent(surfd_unet* u, int B, int n_steps, const int64_t* t
   pa.n_steps = n_steps; pa.B = B; pa.L = L; pa.n_pass = guidance != 1.0f ? 2 : 1;
   pa.tmap = tmap_dev; pa.coef = coef_dev; pa.noise = noise_dev; pa.noise_stride = (long long)B * L; pa.guidance = guidance;
   pa.x = ln.xcur.as<float>(); pa.x0a = ln.x0a.as<float>();
-  pa.partials = ln.p_partials.as<float>(); pa.sems = ln.p_sems.as<unsigned>(); pa.sem_bank = ln.p_sem_bank; pa.sync = ln.p_sync.as<unsigned>();
+  pa.partials = ln.p_partials.as<float>(); pa.sems = ln.p_sems.as<unsigned>(); pa.sem_bank = ln.p_sem_bank; pa.use_tc = ln.p_use_tc; pa.sync = ln.p_sync.as<unsigned>();
   pa.prof = nullptr;
   if (u->profile) {
     SURFD_CUDA(cudaMemsetAsync(ln.p_prof.p, 0, 48 * sizeof(long long), st));

@@ -25,7 +25,7 @@ class SurfDPipeline:
         # to whole tiles per CTA: (148 - 8) CTAs x 2 x 128 rows
         n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         budget = max(1, n_sms - mc_parallel)
-        self.decoder = UdfDecoder(ae_state, latent_dim, device=device, packed=packed_decoder, max_chunk_points=budget * 256)
+        self.decoder = UdfDecoder(ae_state, latent_dim, device=device, packed=packed_decoder, max_chunk_points=budget * 768)
         self.decoder.set_sm_budget(budget)
         # the persistent sampler kernel (one CTA per SM, cooperative launch) leaves the same SMs free: the marching-cubes
         # replays of the previous batch keep running next to it instead of delaying its launch
