@@ -234,11 +234,12 @@ def bench_gpu(args):
                 "frac": round(bytes_sampler / (ms_sampler * 1e-3) / 1e9 / pk["hbm_gbs"], 4), "traffic": traffic_s,
                 "peak_source": pk["source"] + " copy bandwidth (sustained: the kernel runs for >1 s)",
                 "bytes_per_launch": int(bytes_sampler), "ms_per_launch": round(ms_sampler, 2), "ms_per_ddpm_step": round(ms_sampler / STEPS_DDPM, 4),
-                "note": "latency-bound, not bandwidth-bound: <= 256 tokens per GEMM, 165 grid-wide dependencies per step at ~1.5 us each; "
-                        "the weight stream itself needs 0.09 ms of the step at peak"}
+                "note": "dependency-bound, not bandwidth-bound: <= 256 tokens per GEMM, ~165 grid-wide dependencies per DDPM step at ~1.5 us each plus "
+                        "one or two L2 round trips per op; inside a GEMM op the weight stream runs at ~5.4 TB/s (1.1 us per 40 KB chunk pair "
+                        "and SM), over the whole step the 604 MB need 0.09 ms at peak"}
     sampler = {"ms_per_ddpm_step": round(1e3 * tm["sample_s"] / STEPS_DDPM, 4), "weight_bytes_per_step": int(a.n_floats * 4),
                "hbm_gbps": round(a.n_floats * 4 / (tm["sample_s"] / STEPS_DDPM) / 1e9, 1), "hbm_peak_gbps": pk["hbm_gbs"],
-               "engine": "persistent cooperative kernel, wide token-GEMM units, fp16 two-term split (fp32-class) on mma.sync"}
+               "engine": "persistent cooperative kernel, wide token-GEMM units on tcgen05 (kind::f16, fp16 two-term split: fp32-class products, TMEM accumulators)"}
 
     out = None
     if rank == 0:

@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-( timeout -s KILL 300 python -m pytest tests/test_gpu_unet.py -x -q ) > gpurun_out/pytest_unet.log 2>&1; tail -12 gpurun_out/pytest_unet.log
-timeout -s KILL 200 python tools/sampler_profile.py 2>&1 | grep -v Warning | tail -6 > gpurun_out/sampler_debug.txt 2>&1
-cat gpurun_out/sampler_debug.txt
+timeout -s KILL 420 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
+tail -c 400 gpurun_out/bench_ncu.log; wc -l gpurun_out/launches_bench.csv
