@@ -2606,8 +2606,10 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
       POp& c = ops[i];
       POp& nx = ops[i + 1];
       if (c.type != P_CONV || !c.wide || c.ks <= 1) continue;
-      // (attention consumers were measured slower with the slice sum in their load phase than the qkv GEMM's own exchange)
-      if (!(nx.type == P_GN && nx.in0 == c.conv.out)) continue;
+      // (attention consumers were measured slower with the slice sum in their load phase than the qkv GEMM's own exchange;
+      // SURFD_UNET_DEBUG bit 6 enables it for experiments)
+      const bool attn_ok = (dbg & 64) && nx.type == P_ATTN;
+      if (!((nx.type == P_GN || attn_ok) && nx.in0 == c.conv.out)) continue;
       if (nx.type == P_GN && nx.i0 != c.conv.N) continue;
       if (nx.type == P_ATTN && (c.conv.emb || c.conv.residual || 3 * nx.i0 != c.conv.N)) continue;
       c.defer = 1;

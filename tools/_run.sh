@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout -s KILL 420 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
-tail -c 400 gpurun_out/bench_ncu.log; wc -l gpurun_out/launches_bench.csv
+SURFD_UNET_DEBUG=64 timeout -s KILL 120 python tools/sampler_profile.py 2>&1 | grep -v Warning | tail -6 > gpurun_out/sampler_attn_defer.txt 2>&1
+cat gpurun_out/sampler_attn_defer.txt
+timeout -s KILL 150 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_extract.csv python tools/ncu_extract.py 256 > gpurun_out/ncu_extract.log 2>&1
+tail -2 gpurun_out/ncu_extract.log | cut -c1-300; wc -l gpurun_out/launches_extract.csv
