@@ -2411,7 +2411,8 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
   const bool wide = u->persist_split == 1 && u->precision != 0;
   const char* dbg_env0 = getenv("SURFD_UNET_DEBUG");
   const bool use_tc = wide && u->precision == 1 && u->persist_tc && !((dbg_env0 ? atoi(dbg_env0) : 0) & 32);
-  // diagnostics (tools/sampler_profile.py): SURFD_UNET_DEBUG bit 1 = no deferred exchange, bit 3 = no fused GroupNorm,
+  // diagnostics (tools/sampler_profile.py): SURFD_UNET_DEBUG bit 1 = no deferred exchange, bit 3 = no fused GroupNorm, bit 4 = fused
+  // GroupNorm on, bit 5 = mma.sync instead of tcgen05 units, bit 6 = attention sums the qkv GEMM's K slices,
   // bit 2 = every op replaced by an empty one (barrier cost only; results are garbage)
   const char* dbg_env = getenv("SURFD_UNET_DEBUG");
   const int dbg = dbg_env ? atoi(dbg_env) : 0;

@@ -136,8 +136,9 @@ def test_persistent_sampler_precision_modes(mode):
     assert torch.equal(out, ref), float((out - ref).abs().max())
 
 
-@pytest.mark.parametrize("debug,what", [("2", "in-op K-slice exchange (no deferral)"), ("16", "GroupNorm fused into the token GEMM")],
-                         ids=["no-defer", "fused-gn"])
+@pytest.mark.parametrize("debug,what", [("2", "in-op K-slice exchange (no deferral)"), ("16", "GroupNorm fused into the token GEMM"),
+                                        ("32", "mma.sync units instead of tcgen05")],
+                         ids=["no-defer", "fused-gn", "mma-sync"])
 def test_persistent_sampler_variants_agree(debug, what, monkeypatch):
     """The wide-unit engine's alternative dataflows (SURFD_UNET_DEBUG, read when the op list is built) compute the same
     network: each stays within fp32-rounding distance of the graph engine, for plain, concat (output blocks) and
