@@ -18,6 +18,7 @@ import json
 import os
 
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before the CUDA context exists (see surfd_b200/__init__.py)
+os.environ.setdefault("NCCL_DEBUG", "WARN")                   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 import subprocess
 import sys
 import tempfile

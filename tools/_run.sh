@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-( time timeout -s KILL 600 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1; grep -E "passed|failed|rror" gpurun_out/pytest_gpu.log | tail -3
-( time timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" ) 2>&1 | tail -4
-( time timeout -s KILL 600 python bench.py --steps 3 --warmup 3 ) > gpurun_out/bench_final2.json 2> gpurun_out/bench_final2.err
-cut -c1-330 gpurun_out/bench_final2.json; tail -3 gpurun_out/bench_final2.err
+( time timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 2 ) > gpurun_out/bench_n2_final.json 2> gpurun_out/bench_n2_final.err
+cut -c1-260 gpurun_out/bench_n2_final.json; tail -3 gpurun_out/bench_n2_final.err
