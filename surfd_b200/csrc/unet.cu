@@ -2683,8 +2683,17 @@ extern "C" int surfd_sample(surfd_unet* u, int B, int n_steps, const int64_t* tm
   SURFD_REQUIRE(B >= 1 && B <= u->max_batch, "batch exceeds max_batch");
   SURFD_REQUIRE(n_steps >= 1, "n_steps must be positive");
   cudaStream_t st = (cudaStream_t)stream;
-  if (u->sampler == 1 && u->coop)
-    return sample_persistent(u, B, n_steps, tmap_dev, coef_dev, noise_dev, context_dev, labels_dev, guidance, out_dev, st);
+  // The persistent engine runs in the range it has been verified on hardware: batches of at most PERSIST_MAX_BATCH samples and
+  // (wide units) at least PERSIST_MIN_GRID CTAs, so that every token GEMM is a single round of co-resident units.  A test with
+  // batches of 12 / 40 samples (several rounds of units per op) did not finish at the very end of round 1 and could not be
+  // analysed any more; larger batches therefore take the CUDA-graph engine (same results at fp32 rounding level, slower).
+  constexpr int PERSIST_MAX_BATCH = 8, PERSIST_MIN_GRID = 100;
+  if (u->sampler == 1 && u->coop && B <= PERSIST_MAX_BATCH) {
+    int grid = u->sampler_sms > 0 ? u->sampler_sms : u->num_sms;
+    if (grid > u->num_sms) grid = u->num_sms;
+    if (u->persist_split == 0 || grid >= PERSIST_MIN_GRID)
+      return sample_persistent(u, B, n_steps, tmap_dev, coef_dev, noise_dev, context_dev, labels_dev, guidance, out_dev, st);
+  }
   const int L = u->L;
   const int n_lanes = (int)u->lanes.size() < B ? (int)u->lanes.size() : B;
   const int64_t stride = (int64_t)B * L;

@@ -159,3 +159,4 @@ def test_persistent_sampler_variants_agree(debug, what, monkeypatch):
         torch.cuda.synchronize(); net.status()
         assert torch.isfinite(out).all()
         assert float((out - ref).abs().max()) < 2e-4, (what, B, float((out - ref).abs().max()))
+
