@@ -130,11 +130,13 @@ void surfd_unet_destroy(surfd_unet* u);
 /* The denoiser is latency-bound (~170 dependent small kernels per step), so surfd_sample() splits a batch over `n_lanes`
  * concurrent streams (private activations, shared weights).  Default 1 (measured fastest).  Results do not depend on it. */
 int surfd_unet_set_lanes(surfd_unet* u, int n_lanes);
-/* surfd_sample engine.  mode 0 (default): CUDA-graph replay of the per-step kernel sequence (~170 nodes, one graph launch
- * per DDPM step).  mode 1: one persistent cooperative kernel runs the whole reverse-diffusion loop on `n_sms` CTAs (0 = one
- * per SM), ops separated by grid barriers, token GEMMs split over K so that every op is a single round of the resident
- * CTAs.  mode 2: the same kernel with the graph path's K split -- samples are bit-identical to mode 0 and independent of
- * n_sms.  Measured on B200 at batch 8: 1.71 (mode 0) / 1.89 (mode 1) / 2.14 (mode 2) ms per step.
+/* surfd_sample engine.  mode 1 (default): one persistent cooperative kernel runs the whole reverse-diffusion loop on `n_sms`
+ * CTAs (0 = one per SM), ops separated by grid barriers; token GEMMs are wide units (32 tokens x 128 outputs x one K slice,
+ * every op a single round of the resident CTAs) on tcgen05 tensor cores with fp32-class split products.  mode 0: CUDA-graph
+ * replay of the per-step kernel sequence (~170 nodes, one graph launch per DDPM step); also used when the device cannot launch
+ * cooperatively and for batches above 8 samples per call (the persistent engine's verified range).  mode 2: the persistent
+ * kernel with the graph path's units and K split -- samples are bit-identical to mode 0 and independent of n_sms.
+ * Measured on B200 at batch 8: 1.32 (mode 1) / 2.28 (mode 0) / 1.95 (mode 2) ms per DDPM step.
  * All modes compute in the precision selected by surfd_unet_set_precision and agree to fp32 rounding. */
 int surfd_unet_set_sampler(surfd_unet* u, int mode, int n_sms);
 /* Diagnostics: out == NULL switches the persistent kernel's per-op-type cycle counters on/off; out != NULL reads the
@@ -143,7 +145,8 @@ int surfd_unet_set_sampler(surfd_unet* u, int mode, int n_sms);
 int surfd_unet_profile(surfd_unet* u, int on, int64_t* out /* [48] or NULL */);
 /* SURFD_ABORTED if the last persistent run reported a barrier time-out (valid after its stream was synchronised). */
 int surfd_unet_status(surfd_unet* u);
-/* token-GEMM arithmetic: 0 = fp32 FFMA, 1 = mma.sync 3xTF32 split (fp32-class accuracy, default), 2 = single-pass TF32 */
+/* token-GEMM arithmetic: 0 = fp32 FFMA, 1 = fp32-class split products (default: 3xTF32 on mma.sync in the per-op kernels, fp16
+ * hi + lo/4096 two-term split on tcgen05 in the persistent engine; both 2^-22 relative), 2 = single-pass TF32 */
 int surfd_unet_set_precision(surfd_unet* u, int mode);
 size_t surfd_unet_packed_floats(void);
 /* one model evaluation x0_hat = model(x_t, t, context/labels): teacher-forced parity entry.
