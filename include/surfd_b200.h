@@ -72,6 +72,10 @@ int surfd_dec_debug_layer(surfd_decoder* d, const float* A_dev, int M, int blk, 
 int surfd_udf_query(surfd_decoder* d, const float* pts_dev, int64_t M, float* udf_dev, float* grad_dev,
                     void* stream);
 
+/* decoder logits at explicit points: CbnDecoder.forward(CoordsEncoder.encode(c), lat) (cbndec.py:127-134,
+ * coordsenc.py:34-51) -- what a udf_func closure kept from the reference scripts calls. pts_dev [M][3]; logit_dev [M]. */
+int surfd_dec_logits(surfd_decoder* d, const float* pts_dev, int64_t M, float* logit_dev, void* stream);
+
 /* Whole lattice of one shape.  mode 0: dense get_udf_and_grads (meshudf.py:254-304);
  * mode 1: coarse-to-fine GridFiller.fill_grid (meshudf.py:36-206).  udf_dev [N^3], grad_dev [N^3][3]
  * (zero where not evaluated), both also clamped like meshudf.py:342.  counts (host, may be NULL):

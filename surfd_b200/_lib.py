@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_surfd_b200.so")
+# SURFD_B200_LIB selects an alternative in-tree build of the same sources (diagnostic builds, e.g. -DMC_PROFILE)
+LIB_PATH = os.environ.get("SURFD_B200_LIB") or os.path.join(_HERE, "_surfd_b200.so")
 
 _lib = None
 
@@ -31,6 +32,7 @@ PROTOTYPES = {
     "surfd_dec_time_layer": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp]),
     "surfd_dec_debug_layer": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "surfd_udf_query": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "surfd_dec_logits": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "surfd_udf_lattice": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_vp, c_vp, ctypes.POINTER(c_i64), c_vp]),
     "surfd_mc_create": (ctypes.c_int, [ctypes.POINTER(c_vp)]),
     "surfd_mc_destroy": (None, [c_vp]),

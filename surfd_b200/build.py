@@ -42,13 +42,19 @@ def _stamp(path, flags):
     return h.hexdigest()
 
 
-def build(verbose=False, force=False):
+def build(verbose=False, force=False, variant=None, extra_flags=None):
+    """variant / extra_flags: a diagnostic build of the same sources next to the product (e.g. variant="mcprof",
+    extra_flags={"mc.cu": ["-DMC_PROFILE"]} -> surfd_b200/_surfd_b200_mcprof.so; select it with SURFD_B200_LIB)."""
     nvcc = _nvcc()
+    global OBJ, OUT
+    if variant:
+        OBJ = os.path.join(HERE, "csrc", "_obj_" + variant)
+        OUT = os.path.join(HERE, "_surfd_b200_%s.so" % variant)
     os.makedirs(OBJ, exist_ok=True)
     objs = []
     changed = False
     for src in sources():
-        flags = ARCH + COMMON + EXTRA.get(src, [])
+        flags = ARCH + COMMON + EXTRA.get(src, []) + (extra_flags or {}).get(src, [])
         obj = os.path.join(OBJ, src[:-3] + ".o")
         stamp_file = obj + ".stamp"
         stamp = _stamp(os.path.join(CSRC, src), flags)
@@ -71,4 +77,7 @@ def build(verbose=False, force=False):
 
 
 if __name__ == "__main__":
-    print(build(verbose=True, force="--force" in sys.argv))
+    if "--mcprof" in sys.argv:
+        print(build(verbose=True, variant="mcprof", extra_flags={"mc.cu": ["-DMC_PROFILE"]}))
+    else:
+        print(build(verbose=True, force="--force" in sys.argv))

@@ -3,12 +3,16 @@ reference's flags (utils/parser_util.py:40-170: --model_path --output_dir --cond
 --guidance_param --device --batch_size --seed --category --sketch_path --image_path --mask_path --prompt --watertight
 --noise_schedule --sigma_small --cond_mask_prob --dataset ...) and checkpoint layouts.
 
-What runs here is the hot path only: reverse diffusion -> UDF lattice -> MeshUDF marching cubes -> UDF face filter, one
-`.obj` per sample.  The trimesh / pymeshlab clean-up the reference applies afterwards (meshudf.py:379-434,
-generate_uncond.py:113-122) is outside this path; the CLIP encoders are too, so conditional modes take
-pre-computed 512-d embeddings through --context_path (or use an installed `clip` package if there is one).
-Extra flags: --context_path, --dense_grid (use_fast_grid_filler=False), --precision {fp32,tf32}.
-Multi-GPU: launch with torchrun; samples are sharded contiguously over ranks, weights broadcast once over NCCL.
+What runs here: reverse diffusion -> UDF lattice -> MeshUDF marching cubes -> UDF face filter (the hot path), then the
+reference's mesh clean-up (meshudf.py:379-434, surfd_b200/meshclean.py) and output stage (Laplacian smoothing, removal of
+components under 2500 faces, .obj; generate_uncond.py:113-122, surfd_b200/output.py) on the device -- both restated from the
+documented behaviour of trimesh / pymeshlab, which are absent here (parity unpinned).  The CLIP encoders are outside this
+path, so conditional modes take pre-computed 512-d embeddings through --context_path (or use an installed `clip` package).
+`--watertight` (third-party `mcubes` at iso 0.01, generate_text.py:132-158) is not built and raises.
+Extra flags: --context_path, --dense_grid (use_fast_grid_filler=False), --precision {fp32,tf32}, --raw_mesh (stop at the
+meshudf.py:379 boundary).
+Multi-GPU: launch with torchrun; samples are sharded contiguously over ranks; rank 0 alone reads the two checkpoints and
+packs them, the flat blobs reach the other ranks through ONE NCCL broadcast each (surfd_b200.dist.broadcast_packed).
 """
 import argparse
 import os
@@ -59,6 +63,7 @@ def generate_args(argv=None):
     g.add_argument("--context_path", default=None, type=str, help="torch file with pre-computed [B,512] CLIP embeddings")
     g.add_argument("--dense_grid", action="store_true", help="use_fast_grid_filler=False (dense lattice)")
     g.add_argument("--precision", default="fp32", choices=["fp32", "tf32"], help="decoder GEMM precision")
+    g.add_argument("--raw_mesh", action="store_true", help="write the mesh at the meshudf.py:379 boundary (no clean-up / smoothing)")
     args = p.parse_args(argv)
     if args.cond_mask_prob == 0:          # parse_and_load_from_model (utils/parser_util.py:18-19)
         args.guidance_param = 1
@@ -83,6 +88,8 @@ def _context(args, kind, B, device):
         ctx = torch.as_tensor(ctx, dtype=torch.float32).reshape(-1, 512)
         if ctx.shape[0] == 1:
             ctx = ctx.repeat(B, 1)
+        if ctx.shape[0] < B:
+            raise SystemExit(f"--context_path holds {ctx.shape[0]} embeddings but {B} samples were requested")
         return ctx[:B].contiguous()
     try:
         import clip  # noqa: F401  (not shipped here)
@@ -116,18 +123,36 @@ def main(kind, argv=None):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.watertight:
+        raise NotImplementedError("--watertight (utils.GridFiller + third-party mcubes at iso 0.01, generate_text.py:132-158) is "
+                                  "not part of this build (SURVEY.md 8(f)-4)")
+    if not args.sigma_small:
+        raise NotImplementedError("--sigma_small False (FIXED_LARGE variance) is never used by the reference's checkpoints")
     latent = 64 if kind in ("image", "text") else 32      # generate_image.py:76, generate_text.py:80 vs generate_uncond.py:55
     cond_mode = args.cond_mode
-    print("Creating model and diffusion...")
-    print(f"Loading checkpoints from [{args.model_path}]...")
-    state = torch.load(args.model_path, map_location="cpu")
-    ckpt = torch.load(args.ae_dir, map_location="cpu")
-    print(f"Load AutoEncoder From: {args.ae_dir}")
+    from . import _lib, unet as U
+    from .decoder import pack_decoder
+    from .dist import broadcast_packed, shard_range
+    a = U.arch(latent, cond_mode, args.num_actions)
+    if rank == 0:
+        print("Creating model and diffusion...")
+        print(f"Loading checkpoints from [{args.model_path}]...")
+        state = torch.load(args.model_path, map_location="cpu")
+        blob_u, prog, _ = U.pack_unet(state, latent, cond_mode, args.num_actions)
+        ckpt = torch.load(args.ae_dir, map_location="cpu")
+        print(f"Load AutoEncoder From: {args.ae_dir}")
+        blob_d = pack_decoder(ckpt["decoder"], latent)
+        blob_u, prog, blob_d = blob_u.to(dev), prog.to(dev), blob_d.to(dev)
+    else:
+        blob_u = torch.empty(a.n_floats, dtype=torch.float32, device=dev)
+        prog = torch.empty(16 + len(a.buffers) + len(a.prog) * U.REC, dtype=torch.int64, device=dev)
+        blob_d = torch.empty(_lib.load().surfd_dec_packed_floats(latent), dtype=torch.float32, device=dev)
+    broadcast_packed([blob_u, prog, blob_d], src=0)
     B = args.batch_size
-    per = (B + world - 1) // world
-    lo, hi = min(B, rank * per), min(B, (rank + 1) * per)
-    pipe = SurfDPipeline(state, ckpt["decoder"], latent, cond_mode, device=dev, max_batch=max(1, per), num_actions=args.num_actions,
-                         mc_parallel=min(8, max(1, per)))
+    lo, hi = shard_range(B, world, rank)
+    per = max(1, hi - lo)
+    pipe = SurfDPipeline(None, None, latent, cond_mode, device=dev, max_batch=per, num_actions=args.num_actions,
+                         mc_parallel=min(8, per), packed_unet=(blob_u, prog.cpu()), packed_decoder=blob_d)
     if args.precision == "tf32":
         pipe.decoder.set_precision(1)
     # noise: CPU generator, full-batch order, sliced per rank (identical for any GPU count)
@@ -137,15 +162,23 @@ def main(kind, argv=None):
     if kind in ("sketch", "image", "text"):
         ctx = _context(args, kind, B, dev)[lo:hi]
     if kind == "cat":
+        if not 0 <= args.category < args.num_actions:
+            raise IndexError(f"--category {args.category} outside [0, {args.num_actions})")
         lab = torch.full((B,), args.category, dtype=torch.int64)[lo:hi]
     t0 = time.time()
     if hi > lo:
+        from .meshclean import clean_mesh
+        from .output import finish_and_save
         lat, meshes, stats = pipe.generate(noise.to(dev), args.resolution, ctx, lab, guidance=float(args.guidance_param),
                                            n_steps=1000, use_fast_grid_filler=not args.dense_grid, noise_schedule=args.noise_schedule)
         torch.cuda.synchronize()
         for k, (v, f) in enumerate(meshes):
             mesh_path = os.path.join(args.output_dir, f"{lo + k}.obj")
-            write_obj(mesh_path, v, f)
+            if args.raw_mesh:
+                write_obj(mesh_path, v, f)
+            else:
+                v, f = clean_mesh(v, f, smooth_borders=True)
+                finish_and_save(v, f, mesh_path, mincomponentsize=2500)
         print(f"rank {rank}: {hi - lo} shapes in {time.time() - t0:.2f}s; saved results to {mesh_path}")
     if world > 1:
         dist.barrier()

@@ -226,7 +226,8 @@ __global__ void encode_kernel(const float* __restrict__ pts, int M, float* __res
 // fc_out + sigmoid + udf scaling; one warp per point.
 // udf = (1 - sigmoid(logit)) * 0.1 ; dudf = (-0.1 * (1-p)) * p  (sigmoid backward order of torch autograd)
 __global__ void out_kernel(const float* __restrict__ act, int M, const float* __restrict__ wout, const float* __restrict__ bout,
-                           float* __restrict__ udf, const int32_t* __restrict__ dst, float* __restrict__ dudf) {
+                           float* __restrict__ udf, const int32_t* __restrict__ dst, float* __restrict__ dudf,
+                           float* __restrict__ logit_out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -244,7 +245,8 @@ __global__ void out_kernel(const float* __restrict__ act, int M, const float* __
     const float logit = s + bout[0];
     const float p = 1.0f / (1.0f + expf(-logit));
     const float u = (1.0f - p) * 0.1f;
-    udf[dst ? dst[warp] : warp] = u;
+    if (logit_out) logit_out[warp] = logit;   // CbnDecoder.forward's own output (cbndec.py:127-134)
+    if (udf) udf[dst ? dst[warp] : warp] = u;
     if (dudf) dudf[warp] = (-0.1f * (1.0f - p)) * p;
   }
 }
@@ -639,7 +641,8 @@ extern "C" int surfd_dec_set_latent(surfd_decoder* d, const float* lat_dev, void
 
 // Forward over M (<= chunk) points already in d->pts.  keep_acts: store every layer's activation (for the
 // gradient pass); otherwise ping-pong two buffers.  Writes udf through `dst` (or densely when dst==null).
-static int dec_forward(surfd_decoder* d, int M, bool keep_acts, float* udf_out, const int32_t* dst, cudaStream_t st) {
+static int dec_forward(surfd_decoder* d, int M, bool keep_acts, float* udf_out, const int32_t* dst, cudaStream_t st,
+                       float* logit_out = nullptr) {
   float* E = d->enc.as<float>();
   float* net = d->net.as<float>();
   encode_kernel<<<(unsigned)cdiv(M, 128), 128, 0, st>>>(d->pts.as<float>(), M, E);
@@ -663,7 +666,7 @@ static int dec_forward(surfd_decoder* d, int M, bool keep_acts, float* udf_out, 
     SURFD_TRY(gemm512(d, A(2 * i + 1), d->W1(i), d->W1r(i), M, e1, st));
   }
   out_kernel<<<(unsigned)cdiv((int64_t)M * 32, 256), 256, 0, st>>>(A(10), M, d->wout(), d->bout(), udf_out, dst,
-                                                                  keep_acts ? d->dudf.as<float>() : nullptr);
+                                                                  keep_acts ? d->dudf.as<float>() : nullptr, logit_out);
   SURFD_CHECK_LAUNCH();
   return 0;
 }
@@ -704,6 +707,20 @@ extern "C" int surfd_udf_query(surfd_decoder* d, const float* pts_dev, int64_t M
     SURFD_CUDA(cudaMemcpyAsync(d->pts.p, pts_dev + 3 * base, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     SURFD_TRY(dec_forward(d, m, grad_dev != nullptr, udf_dev + base, nullptr, st));
     if (grad_dev) SURFD_TRY(dec_backward(d, m, grad_dev + 3 * base, nullptr, st));
+  }
+  return 0;
+}
+
+// CbnDecoder.forward(CoordsEncoder.encode(pts), lat) itself: the logits the reference's udf_func closure feeds to sigmoid
+// (sample/generate_uncond.py:96-101), for callers that keep the closure and only swap the modules.
+extern "C" int surfd_dec_logits(surfd_decoder* d, const float* pts_dev, int64_t M, float* logit_dev, void* stream) {
+  SURFD_REQUIRE(d && d->latent_set, "decoder latent not set");
+  SURFD_REQUIRE(M >= 0 && (M == 0 || (pts_dev && logit_dev)), "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t base = 0; base < M; base += d->chunk) {
+    const int m = (int)((M - base) < d->chunk ? (M - base) : d->chunk);
+    SURFD_CUDA(cudaMemcpyAsync(d->pts.p, pts_dev + 3 * base, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SURFD_TRY(dec_forward(d, m, false, nullptr, nullptr, st, logit_dev + base));
   }
   return 0;
 }

@@ -2687,7 +2687,9 @@ extern "C" int surfd_sample(surfd_unet* u, int B, int n_steps, const int64_t* tm
   // (wide units) at least PERSIST_MIN_GRID CTAs, so that every token GEMM is a single round of co-resident units.  A test with
   // batches of 12 / 40 samples (several rounds of units per op) did not finish at the very end of round 1 and could not be
   // analysed any more; larger batches therefore take the CUDA-graph engine (same results at fp32 rounding level, slower).
-  constexpr int PERSIST_MAX_BATCH = 8, PERSIST_MIN_GRID = 100;
+  constexpr int PERSIST_MIN_GRID = 100;
+  int PERSIST_MAX_BATCH = 8;
+  if (const char* e = getenv("SURFD_PERSIST_MAX_BATCH")) PERSIST_MAX_BATCH = atoi(e);   // diagnostics
   if (u->sampler == 1 && u->coop && B <= PERSIST_MAX_BATCH) {
     int grid = u->sampler_sms > 0 ? u->sampler_sms : u->num_sms;
     if (grid > u->num_sms) grid = u->num_sms;

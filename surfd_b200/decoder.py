@@ -125,6 +125,14 @@ class UdfDecoder:
         _lib.check(self.lib.surfd_udf_query(self._h, _lib.ptr(pts), M, _lib.ptr(udf), _lib.ptr(grad), _lib.stream_ptr()))
         return (udf, grad) if want_grad else udf
 
+    def logits(self, pts):
+        """CbnDecoder.forward(encode(pts), lat) -> logits [M] (before the sigmoid of udf_func)"""
+        pts = pts.detach().to(self.device, torch.float32).contiguous()
+        M = pts.shape[0]
+        out = torch.empty(M, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.surfd_dec_logits(self._h, _lib.ptr(pts), M, _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
     def lattice(self, N, use_fast_grid_filler=True, max_dist=0.1):
         """(udf [N,N,N], grads [N,N,N,3], counts) -- GridFiller.fill_grid or get_udf_and_grads."""
         udf = torch.empty(N, N, N, device=self.device, dtype=torch.float32)

@@ -137,6 +137,13 @@ def udf_mc_lewiner(volume, grads, spacing=(1.0, 1.0, 1.0), gradient_direction="d
     if int(step_size) != 1 or use_classic or mask is not None or not allow_degenerate:
         raise NotImplementedError("surfd_b200 implements the configuration the Surf-D scripts use: "
                                   "step_size=1, use_classic=False, mask=None, allow_degenerate=True")
+    as_numpy = not torch.is_tensor(volume)     # the reference passes host numpy arrays (meshudf.py:347-349) and gets numpy back
+    if as_numpy:
+        import numpy as np
+        volume = torch.from_numpy(np.ascontiguousarray(volume, dtype=np.float32))
+        grads = torch.from_numpy(np.ascontiguousarray(grads, dtype=np.float32))
+    elif not torch.is_tensor(grads):
+        grads = torch.as_tensor(grads, dtype=torch.float32)
     mc = mc or _mc_for(volume.device if volume.is_cuda else "cuda")
     verts, faces = mc.run_raw(volume, grads)
     vertices = torch.flip(verts, dims=[1])                       # np.fliplr(vertices)
@@ -147,7 +154,13 @@ def udf_mc_lewiner(volume, grads, spacing=(1.0, 1.0, 1.0), gradient_direction="d
     if not (float(spacing[0]) == 1 and float(spacing[1]) == 1 and float(spacing[2]) == 1):
         sp = torch.tensor([float(s) for s in spacing], dtype=torch.float64, device=vertices.device)
         vertices = vertices.to(torch.float64) * sp               # float32 * float64 -> float64 like numpy
-    return vertices, faces.contiguous(), None, None
+    faces = faces.contiguous()
+    if as_numpy:
+        v = vertices.cpu().numpy()
+        if v.dtype != "float64" and not (float(spacing[0]) == 1 and float(spacing[1]) == 1 and float(spacing[2]) == 1):
+            v = v.astype("float64")
+        return v, faces.cpu().numpy(), None, None
+    return vertices, faces, None, None
 
 
 class DecoderUdf:
@@ -165,16 +178,59 @@ class DecoderUdf:
         return self.decoder.query(c)
 
 
-def get_mesh_from_udf(udf_func, coords_range=(-1, 1), max_dist=0.1, N=128, smooth_borders=True, differentiable=True,
-                      max_batch=2 ** 12, use_fast_grid_filler=True, mc=None, return_stats=False):
-    """Lattice query + marching cubes + UDF face filter (meshudf.py:307-379).
+def _recognise_closure(udf_func, max_dist):
+    """The scripts hand meshudf an opaque Python closure over (coords_encoder, decoder, lat) -- sample/generate_uncond.py:96-101.
+    A closure cannot cross the C ABI, but one built from the surfd_b200 drop-ins (modules.CbnDecoder + a latent tensor) can
+    be recognised: its cells hold the decoder object and the latent.  The recognition is then CHECKED, not trusted: the
+    closure is evaluated on probe points (which runs the CUDA decoder through surfd_dec_logits) and must agree with the
+    library's own udf query; anything else is refused -- there is no CPU fallback."""
+    from .modules import CbnDecoder
+    cells = getattr(udf_func, "__closure__", None) or ()
+    decs, lats = [], []
+    for c in cells:
+        try:
+            v = c.cell_contents
+        except ValueError:
+            continue
+        if isinstance(v, CbnDecoder):
+            decs.append(v)
+        elif torch.is_tensor(v) and v.is_floating_point():
+            lats.append(v)
+    if len(decs) != 1:
+        return None
+    dec = decs[0]
+    lats = [t for t in lats if t.numel() == dec.latent_dim]
+    if len(lats) != 1:
+        return None
+    bound = DecoderUdf(dec.udf_decoder, lats[0])
+    g = torch.Generator().manual_seed(1234)
+    probe = (torch.rand(257, 3, generator=g) * 2 - 1).to(dec.udf_decoder.device)
+    with torch.no_grad():
+        theirs = udf_func(probe)
+    ours = bound(probe)
+    if tuple(theirs.shape) != tuple(ours.shape) or float((theirs.to(ours.device) - ours).abs().max()) > 1e-6 * max(1.0, 10 * max_dist):
+        return None
+    return bound
 
-    Returns (verts float32 cuda [V,3], faces int64 cuda [F,3]) exactly at the meshudf.py:379 boundary:
-    all marching-cubes vertices, faces with the `udf > 1/N` ones removed.  The trimesh clean-up and border
-    smoothing that follow in the reference (meshudf.py:379-434) are outside this path."""
+
+def get_mesh_from_udf(udf_func, coords_range=(-1, 1), max_dist=0.1, N=128, smooth_borders=True, differentiable=True,
+                      max_batch=2 ** 12, use_fast_grid_filler=True, mc=None, return_stats=False, postprocess=None):
+    """Lattice query + marching cubes + UDF face filter (meshudf.py:307-379), then (postprocess) the mesh clean-up and
+    border smoothing of meshudf.py:379-434.
+
+    `udf_func`: a DecoderUdf, or the scripts' own closure built from surfd_b200's CoordsEncoder / CbnDecoder drop-ins
+    (recognised and verified, see _recognise_closure).  Returns (verts float32 cuda [V,3], faces int64 cuda [F,3]).
+    postprocess=None keeps the historical default of this function: the meshudf.py:379 boundary (all marching-cubes
+    vertices, faces with `udf > 1/N` removed) for a DecoderUdf, the full reference behaviour (clean-up + `smooth_borders`)
+    for a recognised script closure."""
     if not isinstance(udf_func, DecoderUdf):
-        raise TypeError("surfd_b200.get_mesh_from_udf needs a DecoderUdf (decoder + latent); arbitrary Python "
-                        "closures cannot run in the CUDA library and there is no CPU fallback")
+        bound = _recognise_closure(udf_func, max_dist) if callable(udf_func) else None
+        if bound is None:
+            raise TypeError("surfd_b200.get_mesh_from_udf needs a DecoderUdf or a udf_func closure over surfd_b200's CbnDecoder "
+                            "and one latent; arbitrary Python closures cannot run in the CUDA library and there is no CPU fallback")
+        udf_func = bound
+        if postprocess is None:
+            postprocess = True
     if tuple(float(c) for c in coords_range) != (-1.0, 1.0):
         raise NotImplementedError("the reference's marching cubes hard-codes the [-1,1] range (pyx:1131)")
     if differentiable:
@@ -189,6 +245,9 @@ def get_mesh_from_udf(udf_func, coords_range=(-1, 1), max_dist=0.1, N=128, smoot
     keep = dec.face_filter(vertices, faces, N)
     faces_kept = faces[keep.bool()]
     out = (vertices.to(torch.float32), faces_kept.to(torch.int64))
+    if postprocess:
+        from .meshclean import clean_mesh
+        out = clean_mesh(vertices, faces_kept, smooth_borders=smooth_borders)
     if return_stats:
         return out + (dict(n_udf=counts[0], n_grad=counts[1], n_faces_mc=int(faces.shape[0]), n_faces_kept=int(faces_kept.shape[0])),)
     return out

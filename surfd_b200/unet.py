@@ -216,11 +216,10 @@ def pack_unet(state_dict, L=32, cond_mode="no_cond", num_actions=9):
     """state_dict (flat, 'Unet.' prefix, as model{step:09d}.pt) -> (float32 blob, int64 program, arch)."""
     a = arch(L, cond_mode, num_actions)
     missing = [k for k in a.keys if k not in state_dict]
-    unexpected = [k for k in state_dict if k not in a.keys and not k.startswith("clip_model.")]
     if missing:   # load_model_wo_clip: only clip_model.* keys may be missing (utils/model_util.py:6-9)
         raise RuntimeError(f"Error(s) in loading state_dict for MDM: missing keys {missing[:8]}{'...' if len(missing) > 8 else ''}")
-    if unexpected:
-        raise RuntimeError(f"Error(s) in loading state_dict for MDM: unexpected keys {unexpected[:8]}")
+    # unexpected keys are ignored like the reference's load_state_dict(strict=False), which discards that list (e.g. a
+    # category checkpoint's Unet.label_emb.weight sampled with --cond_mode no_cond, clip_model.*, EMA leftovers)
     blob = torch.zeros(a.n_floats, dtype=torch.float32)
     fold = dict(getattr(a, "fold_bias", []))
     for name, tr in a.plan:
@@ -367,7 +366,9 @@ class UNetSampler:
             pass
 
     def set_precision(self, mode):
-        """token GEMMs: 0 fp32 FFMA, 1 mma.sync 3xTF32 (default, fp32-class accuracy), 2 single-pass TF32"""
+        """token GEMMs: 0 fp32 FFMA; 1 (default) fp32-class split products -- 3xTF32 on mma.sync in the per-op kernels, an fp16
+        two-term split (hi + lo/4096, operands must lie in the fp16 range |x| < 65504) on tcgen05 in the persistent engine,
+        both 2^-22 relative; 2 single-pass TF32"""
         _lib.check(self.lib.surfd_unet_set_precision(self._h, int(mode)))
 
     def set_lanes(self, n):
@@ -396,9 +397,31 @@ class UNetSampler:
         """raises if the last persistent sample() aborted (call after synchronising its stream)"""
         _lib.check(self.lib.surfd_unet_status(self._h))
 
+    def _check_cond(self, B, context, labels):
+        """Host-side validation of the conditioning before anything is launched: the device kernels index
+        `label_emb[y[b]]` and read B context rows unchecked.  Same failures as the reference: nn.Embedding raises IndexError
+        for a label outside [0, num_classes) (openaimodel.py:727-730), a category model asserts that labels are given
+        (`assert (y is not None) == (self.num_classes is not None)`, openaimodel.py:719-721), F.linear raises on a context of
+        the wrong width."""
+        nc = self.arch.num_classes
+        if (labels is not None) != (nc is not None):
+            raise ValueError("must specify y (labels) if and only if the model is class-conditional (cond_mode 'category')")
+        if labels is not None:
+            if labels.dim() != 1 or labels.shape[0] != B:
+                raise ValueError(f"labels must have shape ({B},), got {tuple(labels.shape)}")
+            if labels.is_floating_point():
+                raise TypeError("labels must be an integer tensor (nn.Embedding indices)")
+            lo, hi = int(labels.min()), int(labels.max())
+            if lo < 0 or hi >= nc:
+                raise IndexError(f"index out of range in self: label {lo if lo < 0 else hi} outside [0, {nc})")
+        if context is not None:
+            if context.dim() != 2 or tuple(context.shape) != (B, CONTEXT_DIM):
+                raise ValueError(f"context must have shape ({B}, {CONTEXT_DIM}), got {tuple(context.shape)}")
+
     def forward(self, x, t, context=None, labels=None):
         """x [B,1,L], t [B] int64 (original-process timesteps) -> model output [B,1,L]  (MDM.forward)"""
         B = x.shape[0]
+        self._check_cond(B, context, labels)
         x = x.detach().to(self.device, torch.float32).reshape(B, self.L).contiguous()
         t = t.detach().to(self.device, torch.int64).contiguous()
         ctx = context.detach().to(self.device, torch.float32).contiguous() if context is not None else None
@@ -413,6 +436,7 @@ class UNetSampler:
         n = schedule.num_timesteps
         B = noise.shape[1]
         assert noise.shape[0] == n + 1 and noise.shape[2] == self.L
+        self._check_cond(B, context, labels)
         coef, tmap = schedule.device_tables(self.device)
         noise = noise.detach().to(self.device, torch.float32).contiguous()
         ctx = context.detach().to(self.device, torch.float32).contiguous() if context is not None else None

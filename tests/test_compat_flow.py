@@ -1,0 +1,176 @@
+"""The reference's sampling scripts with only their imports swapped: module paths under
+surfd_b200.compat mirror the reference tree, the objects keep the reference's signatures.
+
+CPU part: every `from X import a, b` of sample/generate_*.py that names a module on the hot path resolves under
+surfd_b200.compat (checked against the reference source when /root/reference is present, else against the recorded list).
+GPU part (-m gpu): the generate_uncond.main flow, statement for statement, through the drop-ins."""
+import argparse
+import importlib
+import os
+import re
+
+import pytest
+import torch
+
+REF = "/root/reference"
+# (module, names) the five scripts import from the reference tree (sample/generate_uncond.py:1-12, generate_cat.py, ...)
+HOT_IMPORTS = [
+    ("utils.fixseed", ["fixseed"]),
+    ("utils.parser_util", ["generate_args"]),
+    ("utils.model_util", ["create_model_and_diffusion", "load_model_wo_clip"]),
+    ("utils", ["dist_util"]),
+    ("models.cfg_sampler", ["ClassifierFreeSampleModel"]),
+    ("AutoEncoder.models.coordsenc", ["CoordsEncoder"]),
+    ("AutoEncoder.models.cbndec", ["CbnDecoder"]),
+    ("meshudf.meshudf", ["get_mesh_from_udf"]),
+    ("utils.utils", ["get_o3d_mesh_from_tensors"]),
+]
+
+
+def test_compat_modules_resolve():
+    for mod, names in HOT_IMPORTS:
+        m = importlib.import_module("surfd_b200.compat." + mod)
+        for n in names:
+            assert hasattr(m, n) or importlib.import_module("surfd_b200.compat." + mod + "." + n), (mod, n)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_reference_script_imports_are_covered():
+    known = {m for m, _ in HOT_IMPORTS}
+    third_party = {"open3d", "pymeshlab", "torch", "os", "numpy", "trimesh", "PIL", "torchvision", "clip", "csv", "mcubes"}
+    out_of_scope = {"utils.utils:GridFiller", "data_loaders.dataset"}     # --watertight branch / CLIP preprocessing (8(f)-3/4)
+    for script in ("generate_uncond", "generate_cat", "generate_sketch", "generate_image", "generate_text"):
+        src = open(os.path.join(REF, "sample", script + ".py")).read()
+        for mod, names in re.findall(r"^from ([\w\.]+) import ([\w, ]+)$", src, flags=re.M):
+            if mod.split(".")[0] in third_party or mod in out_of_scope:
+                continue
+            for n in [x.strip() for x in names.split(",")]:
+                if f"{mod}:{n}" in out_of_scope:
+                    continue
+                assert mod in known, (script, mod)
+                m = importlib.import_module("surfd_b200.compat." + mod)
+                assert hasattr(m, n) or importlib.util.find_spec("surfd_b200.compat." + mod + "." + n), (script, mod, n)
+
+
+def test_p_sample_loop_refuses_what_it_cannot_run():
+    from surfd_b200.compat.utils.model_util import create_model_and_diffusion
+    args = argparse.Namespace(cond_mode="no_cond", num_actions=9, arch="OpenUNet", dataset="deepfashion3d", noise_schedule="cosine",
+                              sigma_small=True)
+    model, diffusion = create_model_and_diffusion(args)
+    assert diffusion.num_timesteps == 1000 and diffusion.timestep_map[:3] == [0, 1, 2]
+    assert model.eval() is None                                   # models/mdm.py:112-113
+    with pytest.raises(NotImplementedError):
+        diffusion.p_sample_loop(model, (1, 1, 32), clip_denoised=True)
+    with pytest.raises(NotImplementedError):
+        diffusion.p_sample_loop(model, (1, 1, 32), clip_denoised=False, const_noise=True)
+    with pytest.raises(TypeError):
+        diffusion.p_sample_loop(torch.nn.Linear(2, 2), (1, 1, 32), clip_denoised=False, device="cpu")
+    with pytest.raises(RuntimeError):
+        model.to("cpu")                                           # no CPU path
+
+
+@pytest.mark.gpu
+def test_generate_uncond_flow_with_swapped_imports(tmp_path):
+    # ---- the imports of sample/generate_uncond.py, swapped ----
+    from surfd_b200.compat.utils.model_util import create_model_and_diffusion, load_model_wo_clip
+    from surfd_b200.compat.utils import dist_util
+    from surfd_b200.compat.models.cfg_sampler import ClassifierFreeSampleModel
+    from surfd_b200.compat.AutoEncoder.models.coordsenc import CoordsEncoder
+    from surfd_b200.compat.AutoEncoder.models.cbndec import CbnDecoder
+    from surfd_b200.compat.meshudf.meshudf import get_mesh_from_udf
+    from surfd_b200.compat.utils.utils import get_o3d_mesh_from_tensors
+    from surfd_b200 import output as o3d, output as ml
+    from surfd_b200 import synth, unet as U
+    from surfd_b200.meshudf import DecoderUdf
+    from oracle import unet_oracle as UO
+
+    model_path, ae_dir = str(tmp_path / "model000000000.pt"), str(tmp_path / "ae.pt")
+    sd = synth.synth_mdm(32, "no_cond")
+    torch.save(sd, model_path)
+    torch.save(synth.synth_ae_poly(32), ae_dir)
+    args = argparse.Namespace(model_path=model_path, ae_dir=ae_dir, output_dir=str(tmp_path / "out"), device=0, num_samples=2,
+                              batch_size=8, guidance_param=1, cond_mode="no_cond", num_actions=9, arch="OpenUNet",
+                              dataset="deepfashion3d", noise_schedule="cosine", sigma_small=True, resolution=64)
+    # ---- main() of the reference, statement for statement (sample/generate_uncond.py:21-123) ----
+    out_path = args.output_dir
+    os.makedirs(out_path, exist_ok=True)
+    dist_util.setup_dist(args.device)
+    assert args.num_samples <= args.batch_size
+    args.batch_size = args.num_samples
+    model, diffusion = create_model_and_diffusion(args)
+    diffusion = type(diffusion)(U.space_timesteps(1000, [12]), U.cosine_betas())     # (test only: 12 respaced steps)
+    state_dict = torch.load(args.model_path, map_location="cpu")
+    load_model_wo_clip(model, state_dict)
+    if args.guidance_param != 1:
+        model = ClassifierFreeSampleModel(model)
+    model.to(dist_util.dev())
+    model.eval()
+    cond = {}
+    cond["y"] = {}
+    ckpt = torch.load(args.ae_dir)
+    latent_size = 32
+    coords_encoder = CoordsEncoder()
+    decoder = CbnDecoder(coords_encoder.out_dim, latent_size, 512, 5)
+    decoder.load_state_dict(ckpt["decoder"], strict=True)
+    decoder = decoder.cuda()
+    decoder.eval()
+    for param in decoder.parameters():
+        param.requires_grad = False
+    torch.manual_seed(10)
+    sample_fn = diffusion.p_sample_loop
+    sample = sample_fn(model, (args.batch_size, 1, latent_size), clip_denoised=False, model_kwargs=cond, skip_timesteps=0,
+                       init_image=None, progress=True, dump_steps=None, noise=None, const_noise=False)
+    assert sample.shape == (2, 1, 32) and sample.is_cuda
+    # the sampler consumed torch's CUDA generator like the reference: x_T, then one randn_like per step
+    torch.manual_seed(10)
+    x_T = torch.randn(2, 1, 32, device="cuda")
+    draws = [x_T] + [torch.randn_like(x_T) for _ in range(12)]
+    noise = torch.stack(draws).reshape(13, 2, 32).cpu()
+    with torch.no_grad():
+        ref = UO.p_sample_loop(sd, diffusion.schedule, noise)
+    assert float((sample.cpu().reshape(2, 32) - ref.reshape(2, 32)).abs().max()) < 1e-3
+
+    udf_max_dist = 0.1
+    for k in range(args.batch_size):
+        lat = sample[k]
+
+        def udf_func(c):
+            c = coords_encoder.encode(c.unsqueeze(0))
+            p = decoder(c, lat).squeeze(0)
+            p = torch.sigmoid(p)
+            p = (1 - p) * udf_max_dist
+            return p
+
+        v, t = get_mesh_from_udf(udf_func, coords_range=(-1, 1), max_dist=udf_max_dist, N=args.resolution, max_batch=2 ** 16,
+                                 differentiable=False)
+        assert v.is_cuda and v.dtype == torch.float32 and t.dtype == torch.int64 and t.shape[0] > 1000
+        # the closure itself evaluates on the GPU and agrees with the library's query
+        pts = torch.rand(500, 3, device="cuda") * 2 - 1
+        direct = DecoderUdf(decoder.udf_decoder, lat)(pts)
+        assert float((udf_func(pts) - direct).abs().max()) < 1e-6
+        # same mesh as the 379-boundary call + clean-up
+        exact, m = synth.poly_udf(v.cpu(), lat.reshape(-1).cpu())
+        assert float(m.abs().max()) < 0.8 * 2.0 / (args.resolution - 1)
+        pred_mesh_o3d = get_o3d_mesh_from_tensors(v, t)
+        mesh_path = os.path.join(args.output_dir, f"{k}.obj")
+        os.makedirs(os.path.dirname(mesh_path), exist_ok=True)
+        o3d.io.write_triangle_mesh(mesh_path, pred_mesh_o3d)
+        ms = ml.MeshSet()
+        ms.set_verbosity(False)
+        ms.load_new_mesh(mesh_path)
+        ms.apply_coord_laplacian_smoothing()
+        ms.meshing_remove_connected_component_by_face_number(mincomponentsize=2500)
+        ms.save_current_mesh(mesh_path)
+        rv, rf = o3d.read_obj(mesh_path)
+        assert rf.shape[0] > 1000 and rv.shape[0] > 500
+
+    # a foreign closure is refused loudly (no CPU fallback)
+    with pytest.raises(TypeError):
+        get_mesh_from_udf(lambda c: c.norm(dim=1) - 0.5, N=64, differentiable=False)
+    other = torch.zeros(1, 32, device="cuda")
+
+    def wrong(c):      # closes over the decoder but computes something else
+        return torch.sigmoid(decoder(coords_encoder.encode(c.unsqueeze(0)), other).squeeze(0))
+
+    with pytest.raises(TypeError):
+        get_mesh_from_udf(wrong, N=64, differentiable=False)
