@@ -111,6 +111,9 @@ int surfd_mc_fetch(surfd_mc* m, float* verts_dev /* [n_v][3] */, int32_t* faces_
 int surfd_mc_classify(surfd_mc* m, const float* udf_dev, int N, uint32_t* bits_dev_or_null,
                       int64_t* n_cand_host, void* stream);
 
+/* measurement hook: average duration of the classification kernel alone (`iters` launches, CUDA events on `stream`) */
+int surfd_mc_time_classify(surfd_mc* m, const float* udf_dev, int N, int iters, float* ms_per_launch, void* stream);
+
 /* UDF face filter of get_mesh_from_udf (meshudf.py:356-379): the reference evaluates the decoder at both end
  * points and the midpoint of every directed face edge (9 points per face, float64 positions rounded to float32
  * like `torch.from_numpy(points).float()`), keep[f] = 0 if any udf > 1/N.  Same decisions here with every vertex

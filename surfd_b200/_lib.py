@@ -42,6 +42,7 @@ PROTOTYPES = {
     "surfd_mc_finish": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "surfd_mc_fetch": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "surfd_mc_classify": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_vp, ctypes.POINTER(c_i64), c_vp]),
+    "surfd_mc_time_classify": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), c_vp]),
     "surfd_face_filter": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, ctypes.c_int, c_vp, c_vp]),
     "surfd_unet_create": (ctypes.c_int, [c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "surfd_unet_destroy": (None, [c_vp]),

@@ -172,6 +172,34 @@ extern "C" int surfd_mc_classify(surfd_mc* m, const float* udf_dev, int N, uint3
   return 0;
 }
 
+// Measurement hook (bench.py): `iters` back-to-back launches of classify_kernel alone over a resident lattice, CUDA events on
+// `stream`; the kernel's algorithmic traffic is 4 bytes per lattice point read + 1 bit written.
+extern "C" int surfd_mc_time_classify(surfd_mc* m, const float* udf_dev, int N, int iters, float* ms_per_launch, void* stream) {
+  SURFD_REQUIRE(m && udf_dev && ms_per_launch && iters >= 1, "null argument");
+  SURFD_REQUIRE(N >= 2 && N <= 1024, "Input array must be at least 2x2x2.");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t words = cdiv((int64_t)N * N * N, 32);
+  SURFD_TRY(m->bits.reserve((size_t)(words + 1) * sizeof(uint32_t)));
+  SURFD_CUDA(cudaMemsetAsync(m->bits.p, 0, (size_t)(words + 1) * sizeof(uint32_t), st));
+  const double voxel = 2.0 / (N - 1);
+  const float avg_t = (float)(1.05 * voxel), max_t = (float)(1.74 * voxel);
+  const int xsegs = (N + 31) / 32;
+  dim3 grid((unsigned)cdiv((int64_t)xsegs * (N - 1), 8), (unsigned)cdiv(N - 1, kZChunk));
+  cudaEvent_t e0, e1;
+  SURFD_CUDA(cudaEventCreate(&e0));
+  SURFD_CUDA(cudaEventCreate(&e1));
+  for (int i = 0; i < 2; ++i) { classify_kernel<<<grid, 256, 0, st>>>(udf_dev, N, avg_t, max_t, m->bits.as<uint32_t>(), (N % 32) == 0 ? 1 : 0); SURFD_CHECK_LAUNCH(); }
+  SURFD_CUDA(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) { classify_kernel<<<grid, 256, 0, st>>>(udf_dev, N, avg_t, max_t, m->bits.as<uint32_t>(), (N % 32) == 0 ? 1 : 0); SURFD_CHECK_LAUNCH(); }
+  SURFD_CUDA(cudaEventRecord(e1, st));
+  SURFD_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  SURFD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_launch = ms / iters;
+  return 0;
+}
+
 // Enqueue classification + compaction + ordered replay on `stream` without any host synchronisation: the
 // candidate count stays on the device and every buffer is sized from a per-handle capacity (grown on retry).
 extern "C" int surfd_mc_launch(surfd_mc* m, const float* udf_dev, const float* grad_dev, int N, void* stream) {

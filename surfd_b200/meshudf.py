@@ -107,6 +107,14 @@ class MarchingCubes:
         self._inputs = None
         return verts, faces
 
+    def time_classify(self, volume, iters=20):
+        """ms per launch of the classification kernel alone on a resident lattice (CUDA events) -- measurement hook"""
+        N = volume.shape[0]
+        assert volume.is_cuda and volume.dtype == torch.float32 and volume.is_contiguous()
+        ms = ctypes.c_float()
+        _lib.check(self.lib.surfd_mc_time_classify(self._h, _lib.ptr(volume), N, int(iters), ctypes.byref(ms), _lib.stream_ptr()))
+        return float(ms.value)
+
     def classify(self, volume):
         """candidate-cube count and bit mask (one bit per lattice index)."""
         N = volume.shape[0]

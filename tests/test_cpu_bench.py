@@ -14,18 +14,30 @@ def _run(*args, timeout=600):
 
 
 def test_reference_arm_emits_one_json_line():
-    p = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
+    # (the real arm runs the whole 1000-step sampler once, ~2 min; the contract is checked on a shortened schedule at C2)
+    p = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--config", "C2", "--ddpm-steps", "20")
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "shapes/s" and d["higher_is_better"] is True
-    assert d["metric"].startswith("shapes/sec end-to-end")
+    assert d["metric"] == "shapes/sec end-to-end (1000-step sample + 512\u00b3 UDF extract) at 1/2/4/8 B200"     # BASELINE.json, verbatim
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
     assert d["e2e"] == {"value": d["value"], "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["cores"] >= 1 and cb["kind"] in ("port", "port+reference-mc", "reference") and cb["sample"]
-    assert d["config"]["resolution"] == 256 and d["config"]["ddpm_steps"] == 1000 and d["config"]["batch_per_gpu"] == 8
+    assert d["config"]["resolution"] == 256 and d["config"]["ddpm_steps"] == 20 and d["config"]["batch_per_gpu"] == 8
+    assert d["config"]["name"] == "C2" and "measured once" in d["config"]["workload"]
+
+
+def test_default_configuration_is_the_metric():
+    sys.path.insert(0, ROOT)
+    import importlib
+    b = importlib.import_module("bench")
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert b.METRIC == base["metric"]
+    assert b.CONFIGS["C3"]["res"] == 512 and b.CONFIGS["C3"]["batch"] == 8 and b.CONFIG == "C3" and b.RES == 512
+    assert b.CONFIGS["C5"]["guidance"] == 4.0 and b.CONFIGS["C4"]["latent"] == 64 and b.CONFIGS["C4"]["batch"] == 4
 
 
 def test_product_arm_has_no_cpu_fallback():
