@@ -86,6 +86,8 @@ struct Compactor {
   // scatter(): must follow count() on the same bits; writes the first `cap` positions (total > cap = truncated).
   int count(const uint32_t* bits, int64_t n_words, cudaStream_t st);
   int scatter(const uint32_t* bits, int64_t n_words, int32_t* out_list, int64_t cap, cudaStream_t st);
+  // word_prefix(): must follow count() on the same bits; number of set bits before each word
+  int word_prefix(const uint32_t* bits, int64_t n_words, int32_t* prefix, cudaStream_t st);
   // copies d_total to host and synchronises the stream
   int read_total(int64_t* total, cudaStream_t st);
 };

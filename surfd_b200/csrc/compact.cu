@@ -94,6 +94,17 @@ __global__ void __launch_bounds__(kThreads) scatter_bits_kernel(const uint32_t* 
   }
 }
 
+// set bits before each 32-bit word (rank structure: rank(i) = prefix[i >> 5] + popc(bits[i >> 5] & low_mask(i)))
+__global__ void __launch_bounds__(kThreads) word_prefix_kernel(const uint32_t* __restrict__ bits, int64_t n_words,
+                                                               const int32_t* __restrict__ block_offsets,
+                                                               int32_t* __restrict__ prefix) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int c = i < n_words ? __popc(bits[i]) : 0;
+  int total;
+  const int inc = block_incl_scan(c, &total);
+  if (i < n_words) prefix[i] = block_offsets[blockIdx.x] + (inc - c);
+}
+
 }  // namespace
 
 int Compactor::init() {
@@ -134,6 +145,14 @@ int Compactor::scatter(const uint32_t* bits, int64_t n_words, int32_t* out_list,
   const int64_t nb = cdiv(n_words, kThreads);
   if (nb == 0) return 0;
   scatter_bits_kernel<<<(unsigned)nb, kThreads, 0, st>>>(bits, n_words, block_counts.as<int32_t>(), out_list, cap);
+  SURFD_CHECK_LAUNCH();
+  return 0;
+}
+
+int Compactor::word_prefix(const uint32_t* bits, int64_t n_words, int32_t* prefix, cudaStream_t st) {
+  const int64_t nb = cdiv(n_words, kThreads);
+  if (nb == 0) return 0;
+  word_prefix_kernel<<<(unsigned)nb, kThreads, 0, st>>>(bits, n_words, block_counts.as<int32_t>(), prefix);
   SURFD_CHECK_LAUNCH();
   return 0;
 }

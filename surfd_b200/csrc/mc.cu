@@ -11,7 +11,8 @@
 // raster-sorted candidate list == the order in which the reference's scan meets the candidates.
 // Stage 2 (replay_kernel): mc_core.h, O(surface).
 #include "common.cuh"
-#include "mc_core.h"
+#include <algorithm>
+#include "mc_chain.h"
 
 namespace surfd {
 
@@ -73,26 +74,63 @@ classify_kernel(const float* __restrict__ im, int N, float avg_t, float max_t, u
   }
 }
 
-// One warp per shape: all 32 lanes run replay_w() on a private copy of the bookkeeping (identical control flow, same-value
-// stores) and split the neighbourhood fetch / edge votes of each visit (mc_core.h, "warp-cooperative variant").
-// n_cand comes from the device-side compaction total, so the host never has to read it before the launch.
-__global__ void __launch_bounds__(32) replay_kernel(surfd_mccore::Grid* gp, surfd_mccore::Grid* result_host,
-                                                    const int64_t* __restrict__ n_cand_dev, int64_t cap_cand) {
-  __shared__ surfd_mccore::CubeCache cc;
+// ---- O(surface) replay (mc_chain.h): records -> one-warp chain -> parallel emission ----
+
+// lattice vertices that are a corner of a candidate cube
+__global__ void __launch_bounds__(256) mark_vertices_kernel(const int32_t* __restrict__ list, const int64_t* __restrict__ n_cand_dev,
+                                                            int64_t cap, int N, uint32_t* __restrict__ vbits) {
+  const int64_t n = min(*n_cand_dev, cap);
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = list[k];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int64_t v = i + (int64_t)MC_CZ(c) * N * N + (int64_t)MC_CY(c) * N + MC_CX(c);
+      atomicOr(&vbits[v >> 5], 1u << (v & 31));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) build_records_kernel(const surfd_mccore::Chain* __restrict__ gp, const int64_t* __restrict__ n_cand_dev,
+                                                            const int64_t* __restrict__ n_vtx_dev, int64_t cap_cand) {
+  const int64_t n = *n_cand_dev;
+  if (n > cap_cand || *n_vtx_dev > gp->cap_vtx) return;   // the chain reports MC_CAPACITY
+  surfd_mccore::Chain g = *gp;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    surfd_mccore::build_record(g, k);
+}
+
+// One warp per shape: all 32 lanes run replay_r() on a private copy of the counters (identical control flow, same-value
+// stores) and split the two gathers of each visit.  The candidate / vertex counts come from the device-side compaction
+// totals, so the host never has to read them before the launch.
+__global__ void __launch_bounds__(32) chain_kernel(surfd_mccore::Chain* gp, surfd_mccore::Chain* result_host,
+                                                   const int64_t* __restrict__ n_cand_dev, const int64_t* __restrict__ n_vtx_dev,
+                                                   int64_t cap_cand) {
+  __shared__ surfd_mccore::ChainCache cc;
   surfd_mccore::mc_lut_load();
-  surfd_mccore::Grid g = *gp;
+  surfd_mccore::Chain g = *gp;
   const int64_t n = *n_cand_dev;
   g.n_cand = n < cap_cand ? n : cap_cand;
   g.n_cand_total = n;
+  g.n_vtx = *n_vtx_dev;
+  g.n_v = 0; g.n_f3 = 0; g.n_accept = 0; g.n_seed = 0; g.n_unsure_push = 0; g.n_nontrivial_push = 0;
   if (n == 0) {
-    g.n_v = 0; g.n_f3 = 0; g.status = surfd_mccore::MC_EMPTY;
+    g.status = surfd_mccore::MC_EMPTY;
+  } else if (n > cap_cand || g.n_vtx > g.cap_vtx) {
+    g.status = surfd_mccore::MC_CAPACITY;   // candidate list truncated / vertex state too small: caller retries with more room
   } else {
-    surfd_mccore::replay_w(g, cc, gp);
-    if (n > cap_cand) g.status = surfd_mccore::MC_CAPACITY;   // candidate list truncated: caller retries with more room
+    surfd_mccore::replay_r(g, cc, gp);
   }
   __syncwarp();
   // results go straight to mapped pinned host memory: no device->host copy has to be queued behind this long kernel
   if (threadIdx.x == 0) { *gp = g; *result_host = g; }
+}
+
+__global__ void __launch_bounds__(128) emit_kernel(const surfd_mccore::Chain* __restrict__ gp) {
+  surfd_mccore::mc_lut_load();
+  if (gp->status != surfd_mccore::MC_OK) return;
+  surfd_mccore::Chain g = *gp;
+  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < g.n_accept; a += (int64_t)gridDim.x * blockDim.x)
+    surfd_mccore::emit_cube(g, a);
 }
 
 }  // namespace surfd
@@ -100,13 +138,14 @@ __global__ void __launch_bounds__(32) replay_kernel(surfd_mccore::Grid* gp, surf
 using namespace surfd;
 
 struct surfd_mc {
-  DevBuf bits, list, sgn, flg, face_layer, verts, faces, queues, grid_dev;
-  surfd_mccore::Grid* grid_host = nullptr;   // mapped pinned: the kernel writes the results here
-  surfd_mccore::Grid* grid_host_dev = nullptr;
-  surfd_mccore::Grid* grid_stage = nullptr;  // pinned: launch parameters
-  Compactor comp;
+  DevBuf bits, list, cand_prefix, vbits, vtx_prefix, recs, vs, done, slot, acc, verts, faces, queues, grid_dev;
+  surfd_mccore::Chain* grid_host = nullptr;   // mapped pinned: the kernel writes the results here
+  surfd_mccore::Chain* grid_host_dev = nullptr;
+  surfd_mccore::Chain* grid_stage = nullptr;  // pinned: launch parameters
+  Compactor comp, comp_v;
   int64_t n_v = 0, n_f3 = 0;
   int64_t cap_cand = 0;
+  int q_shift = 0;     // extra doublings of the queue capacity after a queue overflow
   int N = 0;
   bool pending = false;
   cudaStream_t pending_stream = nullptr;
@@ -116,28 +155,31 @@ extern "C" int surfd_mc_create(surfd_mc** out) {
   SURFD_REQUIRE(out != nullptr, "null argument");
   surfd_mc* m = new surfd_mc();
   int st = m->comp.init();
+  if (!st) st = m->comp_v.init();
   if (st) { delete m; return st; }
-  cudaError_t e = cudaHostAlloc(&m->grid_host, sizeof(surfd_mccore::Grid), cudaHostAllocMapped);
+  cudaError_t e = cudaHostAlloc(&m->grid_host, sizeof(surfd_mccore::Chain), cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaHostGetDevicePointer(&m->grid_host_dev, m->grid_host, 0);
-  if (e == cudaSuccess) e = cudaMallocHost(&m->grid_stage, sizeof(surfd_mccore::Grid));
-  if (e != cudaSuccess) { m->comp.destroy(); delete m; return set_error(-(int)e, cudaGetErrorString(e), __FILE__, __LINE__); }
-  st = m->grid_dev.reserve(sizeof(surfd_mccore::Grid));
+  if (e == cudaSuccess) e = cudaMallocHost(&m->grid_stage, sizeof(surfd_mccore::Chain));
+  if (e != cudaSuccess) { m->comp.destroy(); m->comp_v.destroy(); delete m; return set_error(-(int)e, cudaGetErrorString(e), __FILE__, __LINE__); }
+  st = m->grid_dev.reserve(sizeof(surfd_mccore::Chain));
   if (st) { surfd_mc_destroy(m); return st; }
-  // The replay is a single long-running warp that shares the GPU with the decoder's persistent tcgen05 kernel (one 215 KB
+  // The chain is a single long-running warp that shares the GPU with the decoder's persistent tcgen05 kernel (one 215 KB
   // CTA per SM).  An SM can only host both if they agree on the L1/shared split, so ask for the same max-shared carve-out;
-  // otherwise every SM holding a replay is lost to the GEMM and its 148-CTA grid needs a second wave (measured ~2x).
-  cudaFuncSetAttribute(replay_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  // otherwise every SM holding a chain is lost to the GEMM and its 148-CTA grid needs a second wave (measured ~2x).
+  cudaFuncSetAttribute(chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   *out = m;
   return 0;
 }
 
 extern "C" void surfd_mc_destroy(surfd_mc* m) {
   if (!m) return;
-  m->bits.release(); m->list.release(); m->sgn.release(); m->flg.release(); m->face_layer.release();
-  m->verts.release(); m->faces.release(); m->queues.release(); m->grid_dev.release();
+  DevBuf* all[] = {&m->bits, &m->list, &m->cand_prefix, &m->vbits, &m->vtx_prefix, &m->recs, &m->vs, &m->done, &m->slot, &m->acc,
+                   &m->verts, &m->faces, &m->queues, &m->grid_dev};
+  for (DevBuf* b : all) b->release();
   if (m->grid_host) cudaFreeHost(m->grid_host);
   if (m->grid_stage) cudaFreeHost(m->grid_stage);
   m->comp.destroy();
+  m->comp_v.destroy();
   delete m;
 }
 
@@ -200,8 +242,8 @@ extern "C" int surfd_mc_time_classify(surfd_mc* m, const float* udf_dev, int N, 
   return 0;
 }
 
-// Enqueue classification + compaction + ordered replay on `stream` without any host synchronisation: the
-// candidate count stays on the device and every buffer is sized from a per-handle capacity (grown on retry).
+// Enqueue classification + compaction + records + ordered chain + emission on `stream` without any host synchronisation:
+// the candidate / vertex counts stay on the device and every buffer is sized from a per-handle capacity (grown on retry).
 extern "C" int surfd_mc_launch(surfd_mc* m, const float* udf_dev, const float* grad_dev, int N, void* stream) {
   SURFD_REQUIRE(m && udf_dev && grad_dev, "null argument");
   SURFD_REQUIRE(N >= 2 && N <= 1024, "Input array must be at least 2x2x2.");
@@ -210,40 +252,66 @@ extern "C" int surfd_mc_launch(surfd_mc* m, const float* udf_dev, const float* g
   const int64_t words = cdiv(n3, 32);
   m->N = N;
   SURFD_TRY(run_classify(m, udf_dev, N, st));
-  // capacity: candidates live in a thin shell around the surface, O(N^2); start at 8*N^2 (a sphere of radius 0.5
+  // capacity: candidates live in a thin shell around the surface, O(N^2); start at 3*N^2 (a sphere of radius 0.5
   // gives ~1.55*N^2) and let surfd_mc_finish() report SURFD_CAPACITY so the wrapper can grow it.
-  int64_t cap = m->cap_cand > 0 ? m->cap_cand : 8ll * N * N;
+  int64_t cap = m->cap_cand > 0 ? m->cap_cand : std::max<int64_t>(3ll * N * N, 4096);
   if (cap > n3) cap = n3;
   m->cap_cand = cap;
+  // a vertex is shared by up to 8 candidate cubes; a shell 2-3 cubes thick has ~1.3 vertices per cube
+  int64_t cap_vtx = 4 * cap;
+  if (cap_vtx > n3) cap_vtx = n3;
   SURFD_TRY(m->list.reserve((size_t)cap * sizeof(int32_t)));
   SURFD_TRY(m->comp.scatter(m->bits.as<uint32_t>(), words, m->list.as<int32_t>(), cap, st));
-  SURFD_TRY(m->sgn.reserve((size_t)n3));
-  SURFD_TRY(m->flg.reserve((size_t)n3));
-  SURFD_TRY(m->face_layer.reserve((size_t)n3 * 4 * sizeof(int32_t)));
-  SURFD_CUDA(cudaMemsetAsync(m->sgn.p, 0, (size_t)n3, st));
-  SURFD_CUDA(cudaMemsetAsync(m->flg.p, 0, (size_t)n3, st));
-  SURFD_CUDA(cudaMemsetAsync(m->face_layer.p, 0xFF, (size_t)n3 * 4 * sizeof(int32_t), st));
+  SURFD_TRY(m->cand_prefix.reserve((size_t)(words + 1) * sizeof(int32_t)));
+  SURFD_TRY(m->comp.word_prefix(m->bits.as<uint32_t>(), words, m->cand_prefix.as<int32_t>(), st));
+  // vertex set + its rank structure
+  SURFD_TRY(m->vbits.reserve((size_t)(words + 1) * sizeof(uint32_t)));
+  SURFD_TRY(m->vtx_prefix.reserve((size_t)(words + 1) * sizeof(int32_t)));
+  SURFD_CUDA(cudaMemsetAsync(m->vbits.p, 0, (size_t)(words + 1) * sizeof(uint32_t), st));
+  mark_vertices_kernel<<<592, 256, 0, st>>>(m->list.as<int32_t>(), m->comp.d_total, cap, N, m->vbits.as<uint32_t>());
+  SURFD_CHECK_LAUNCH();
+  SURFD_TRY(m->comp_v.count(m->vbits.as<uint32_t>(), words, st));
+  SURFD_TRY(m->comp_v.word_prefix(m->vbits.as<uint32_t>(), words, m->vtx_prefix.as<int32_t>(), st));
+  // O(surface) state
+  SURFD_TRY(m->recs.reserve((size_t)cap * sizeof(surfd_mccore::Rec)));
+  SURFD_TRY(m->vs.reserve((size_t)cap_vtx));
+  SURFD_TRY(m->done.reserve((size_t)cap));
+  SURFD_TRY(m->slot.reserve((size_t)cap_vtx * 4 * sizeof(int32_t)));
+  SURFD_TRY(m->acc.reserve((size_t)cap * sizeof(surfd_mccore::Accept)));
+  SURFD_CUDA(cudaMemsetAsync(m->vs.p, 0, (size_t)cap_vtx, st));
+  SURFD_CUDA(cudaMemsetAsync(m->done.p, 0, (size_t)cap, st));
+  SURFD_CUDA(cudaMemsetAsync(m->slot.p, 0xFF, (size_t)cap_vtx * 4 * sizeof(int32_t), st));
   // observed V ~ 0.8 n_cand, 3F ~ 4.7 n_cand on closed surfaces; 3x / 12x leaves room for noisy fields
   const int64_t cap_v = 3 * cap + 64;
   const int64_t cap_f3 = 12 * cap + 64;
   SURFD_TRY(m->verts.reserve((size_t)cap_v * 3 * sizeof(float)));
   SURFD_TRY(m->faces.reserve((size_t)cap_f3 * sizeof(int32_t)));
-  uint32_t qcap = 1024;
-  while ((int64_t)qcap < 16 * cap + 1024) qcap <<= 1;
-  SURFD_TRY(m->queues.reserve((size_t)qcap * 3 * sizeof(int32_t)));
+  // every accepted cube pushes <= 6 entries and is accepted once: 6*cap bounds the BFS queue's lifetime traffic, hence its
+  // occupancy; the two priority queues hold cubes waiting for a second look (grown on MC_QUEUE_OVERFLOW)
+  uint32_t qcap = 1024, qcap2 = 1024;
+  while ((int64_t)qcap < 6 * cap + 1024) qcap <<= 1;
+  while ((int64_t)qcap2 < cap + 1024) qcap2 <<= 1;
+  qcap <<= m->q_shift; qcap2 <<= m->q_shift;
+  SURFD_TRY(m->queues.reserve(((size_t)qcap + 2 * (size_t)qcap2) * sizeof(int32_t)));
 
-  surfd_mccore::Grid& g = *m->grid_host;
+  surfd_mccore::Chain& g = *m->grid_stage;
   memset(&g, 0, sizeof(g));
   g.N = N; g.im = udf_dev; g.grads = grad_dev;
-  g.cand_bits = m->bits.as<uint32_t>(); g.cand_list = m->list.as<int32_t>(); g.n_cand = 0;
-  g.sgn = m->sgn.as<int8_t>(); g.flg = m->flg.as<uint8_t>(); g.face_layer = m->face_layer.as<int32_t>();
+  g.cand_bits = m->bits.as<uint32_t>(); g.cand_prefix = m->cand_prefix.as<int32_t>();
+  g.vtx_bits = m->vbits.as<uint32_t>(); g.vtx_prefix = m->vtx_prefix.as<int32_t>();
+  g.cand_list = m->list.as<int32_t>(); g.n_cand = 0; g.cap_vtx = cap_vtx;
+  g.recs = m->recs.as<surfd_mccore::Rec>(); g.vs = m->vs.as<uint8_t>(); g.done = m->done.as<uint8_t>();
+  g.slot = m->slot.as<int32_t>(); g.acc = m->acc.as<surfd_mccore::Accept>();
   g.verts = m->verts.as<float>(); g.cap_v = cap_v; g.faces = m->faces.as<int32_t>(); g.cap_f3 = cap_f3;
-  g.q.buf = m->queues.as<int32_t>(); g.q_unsure.buf = g.q.buf + qcap; g.q_nontrivial.buf = g.q.buf + 2 * (size_t)qcap;
-  g.q.mask = g.q_unsure.mask = g.q_nontrivial.mask = qcap - 1;
-  // the launch struct is staged through a second pinned copy so grid_host can receive the results
-  memcpy(m->grid_stage, &g, sizeof(g));
+  g.q.buf = m->queues.as<int32_t>(); g.q_unsure.buf = g.q.buf + qcap; g.q_nontrivial.buf = g.q_unsure.buf + qcap2;
+  g.q.mask = qcap - 1; g.q_unsure.mask = g.q_nontrivial.mask = qcap2 - 1;
   SURFD_CUDA(cudaMemcpyAsync(m->grid_dev.p, m->grid_stage, sizeof(g), cudaMemcpyHostToDevice, st));
-  replay_kernel<<<1, 32, 0, st>>>(m->grid_dev.as<surfd_mccore::Grid>(), m->grid_host_dev, m->comp.d_total, cap);
+  surfd_mccore::Chain* gd = m->grid_dev.as<surfd_mccore::Chain>();
+  build_records_kernel<<<592, 128, 0, st>>>(gd, m->comp.d_total, m->comp_v.d_total, cap);
+  SURFD_CHECK_LAUNCH();
+  chain_kernel<<<1, 32, 0, st>>>(gd, m->grid_host_dev, m->comp.d_total, m->comp_v.d_total, cap);
+  SURFD_CHECK_LAUNCH();
+  emit_kernel<<<592, 128, 0, st>>>(gd);
   SURFD_CHECK_LAUNCH();
   m->pending_stream = st;
   m->pending = true;
@@ -256,7 +324,7 @@ extern "C" int surfd_mc_finish(surfd_mc* m, int64_t* n_v, int64_t* n_f, int64_t*
   SURFD_REQUIRE(m->pending, "surfd_mc_finish without surfd_mc_launch");
   SURFD_CUDA(cudaStreamSynchronize(m->pending_stream));
   m->pending = false;
-  surfd_mccore::Grid g;
+  surfd_mccore::Chain g;
   memcpy(&g, m->grid_host, sizeof(g));   // written by the kernel into mapped pinned memory; the stream sync above orders it
   m->n_v = g.n_v; m->n_f3 = g.n_f3;
   *n_v = g.n_v; *n_f = g.n_f3 / 3;
@@ -268,11 +336,19 @@ extern "C" int surfd_mc_finish(surfd_mc* m, int64_t* n_v, int64_t* n_f, int64_t*
   if (g.status == surfd_mccore::MC_CAPACITY) {
     // grow for the retry: enough for the whole candidate set, or double when vertices/faces overflowed
     int64_t want = g.n_cand_total > m->cap_cand ? g.n_cand_total + g.n_cand_total / 8 : 2 * m->cap_cand;
+    if (g.n_vtx > g.cap_vtx) want = std::max<int64_t>(g.n_cand_total + g.n_cand_total / 8, g.n_vtx / 4 + g.n_vtx / 32);
     m->cap_cand = want;
     m->n_v = m->n_f3 = 0;
     return set_error(SURFD_CAPACITY, "marching cubes capacity exceeded; call again (buffers were grown)", __FILE__, __LINE__);
   }
-  if (g.status == surfd_mccore::MC_QUEUE_OVERFLOW) return set_error(SURFD_QUEUE_OVERFLOW, "marching cubes BFS queue overflow", __FILE__, __LINE__);
+  if (g.status == surfd_mccore::MC_QUEUE_OVERFLOW) {
+    if (m->q_shift < 4) {   // retry with larger queues (same path as a capacity miss)
+      ++m->q_shift;
+      m->n_v = m->n_f3 = 0;
+      return set_error(SURFD_CAPACITY, "marching cubes queue capacity exceeded; call again (queues were grown)", __FILE__, __LINE__);
+    }
+    return set_error(SURFD_QUEUE_OVERFLOW, "marching cubes BFS queue overflow", __FILE__, __LINE__);
+  }
   return 0;
 }
 

@@ -88,7 +88,7 @@ class MarchingCubes:
         """cycle counters of the last replay (zeros unless built with -DMC_PROFILE) -- diagnostics"""
         prof = (ctypes.c_int64 * 8)()
         _lib.check(self.lib.surfd_mc_profile(self._h, prof))
-        return dict(zip(("total", "fetch", "sign", "tiling", "emit", "visits", "refills"), list(prof)[:7]))
+        return dict(zip(("total", "fetch", "sign", "tiling", "emit", "visits", "refills", "generic"), list(prof)[:8]))
 
     def finish(self):
         """wait for launch(); returns (verts float32 [V,3], faces int32 [F,3]) or None when the buffers had to grow

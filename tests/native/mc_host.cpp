@@ -4,7 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
-#include "mc_core.h"
+#include "mc_chain.h"
 using namespace surfd_mccore;
 
 static int run_impl(const float* im, const float* grads, int N, float* verts, int64_t cap_v, int32_t* faces, int64_t cap_f3,
@@ -14,8 +14,9 @@ extern "C" int mc_host_run(const float* im, const float* grads, int N, float* ve
                            int32_t* faces, int64_t cap_f3, int64_t* n_v, int64_t* n_f3, int64_t* stats) {
   return run_impl(im, grads, N, verts, cap_v, faces, cap_f3, n_v, n_f3, stats, 0);
 }
-// the warp-cooperative variant with its lane loops run sequentially (what the kernel executes, emulated)
-extern "C" int mc_host_run_w(const float* im, const float* grads, int N, float* verts, int64_t cap_v,
+// the device pipeline (records -> compact-state chain -> parallel emission, mc_chain.h) with the chain warp's lane loops run
+// sequentially: what mc.cu executes, emulated
+extern "C" int mc_host_run_r(const float* im, const float* grads, int N, float* verts, int64_t cap_v,
                              int32_t* faces, int64_t cap_f3, int64_t* n_v, int64_t* n_f3, int64_t* stats) {
   return run_impl(im, grads, N, verts, cap_v, faces, cap_f3, n_v, n_f3, stats, 1);
 }
@@ -41,6 +42,40 @@ static int run_impl(const float* im, const float* grads, int N, float* verts, in
         m = v6 > m ? v6 : m; m = v5 > m ? v5 : m; m = v4 > m ? v4 : m; m = v3 > m ? v3 : m; m = v2 > m ? v2 : m; m = v1 > m ? v1 : m;
         if (avg < avg_t && m <= max_t) { bits[i >> 5] |= 1u << (i & 31); list.push_back((int32_t)i); }
       }
+  if (warp_variant) {
+    const int64_t n_words = (n3 + 31) / 32;
+    std::vector<uint32_t> vbits(n_words, 0u);
+    for (int32_t i : list)
+      for (int c = 0; c < 8; ++c) {
+        const int64_t v = i + (int64_t)MC_CZ(c) * N * N + (int64_t)MC_CY(c) * N + MC_CX(c);
+        vbits[v >> 5] |= 1u << (v & 31);
+      }
+    std::vector<int32_t> cpre(n_words), vpre(n_words);
+    int64_t nc = 0, nv = 0;
+    for (int64_t w = 0; w < n_words; ++w) { cpre[w] = (int32_t)nc; vpre[w] = (int32_t)nv; nc += __builtin_popcount(bits[w]); nv += __builtin_popcount(vbits[w]); }
+    Chain g;
+    memset(&g, 0, sizeof(g));
+    g.N = N; g.im = im; g.grads = grads; g.cand_bits = bits.data(); g.cand_prefix = cpre.data(); g.vtx_bits = vbits.data(); g.vtx_prefix = vpre.data();
+    g.cand_list = list.data(); g.n_cand = g.n_cand_total = (int64_t)list.size(); g.n_vtx = g.cap_vtx = nv;
+    std::vector<Rec> recs(list.size() + 1);
+    std::vector<uint8_t> vs(nv + 1, 0), done(list.size() + 1, 0);
+    std::vector<int32_t> slot(4 * nv + 4, -1);
+    std::vector<Accept> acc(list.size() + 1);
+    g.recs = recs.data(); g.vs = vs.data(); g.done = done.data(); g.slot = slot.data(); g.acc = acc.data();
+    g.verts = verts; g.cap_v = cap_v; g.faces = faces; g.cap_f3 = cap_f3;
+    uint32_t cap = 1024; while (cap < 8u * list.size() + 1024u) cap <<= 1;
+    std::vector<int32_t> b0(cap), b1(cap), b2(cap);
+    g.q.buf = b0.data(); g.q_unsure.buf = b1.data(); g.q_nontrivial.buf = b2.data();
+    g.q.mask = g.q_unsure.mask = g.q_nontrivial.mask = cap - 1;
+    for (int64_t k = 0; k < g.n_cand; ++k) build_record(g, k);
+    ChainCache cc;
+    const Chain home = g;
+    replay_r(g, cc, &home);
+    for (int64_t a = 0; a < g.n_accept; ++a) emit_cube(g, a);
+    *n_v = g.n_v; *n_f3 = g.n_f3;
+    if (stats) { stats[0] = g.n_cand; stats[1] = g.n_seed; stats[2] = g.n_accept; stats[3] = g.n_unsure_push; stats[4] = g.n_nontrivial_push; }
+    return g.status;
+  }
   Grid g;
   memset(&g, 0, sizeof(g));
   g.N = N; g.im = im; g.grads = grads; g.cand_bits = bits.data(); g.cand_list = list.data(); g.n_cand = (int64_t)list.size();
@@ -51,7 +86,7 @@ static int run_impl(const float* im, const float* grads, int N, float* verts, in
   std::vector<int32_t> b0(cap), b1(cap), b2(cap);
   g.q.buf = b0.data(); g.q_unsure.buf = b1.data(); g.q_nontrivial.buf = b2.data();
   g.q.mask = g.q_unsure.mask = g.q_nontrivial.mask = cap - 1;
-  if (warp_variant) { CubeCache cc; const Grid home = g; replay_w(g, cc, &home); } else replay(g);
+  replay(g);
   *n_v = g.n_v; *n_f3 = g.n_f3;
   if (stats) { stats[0] = g.n_cand; stats[1] = g.n_seed; stats[2] = g.n_accept; stats[3] = g.n_unsure_push; stats[4] = g.n_nontrivial_push; }
   return g.status;

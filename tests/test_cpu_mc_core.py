@@ -21,8 +21,8 @@ def host_mc():
                                src, "-o", so])
     lib = ctypes.CDLL(so)
 
-    def run(udf, g, fn="mc_host_run_w"):
-        """fn: mc_host_run = scalar replay; mc_host_run_w = the warp-cooperative variant the kernel runs (lanes emulated)"""
+    def run(udf, g, fn="mc_host_run_r"):
+        """fn: mc_host_run = scalar replay; mc_host_run_r = the warp-cooperative variant the kernel runs (lanes emulated)"""
         N = udf.shape[0]
         cap_v, cap_f = 600_000, 3_600_000
         v = np.empty((cap_v, 3), np.float32); f = np.empty(cap_f, np.int32)
@@ -41,7 +41,7 @@ def test_core_matches_reference_golden_bit_exact(host_mc, case):
     g = np.load(os.path.join(GOLDEN, "mc_fields.npz"))
     udf, grads = analytic_field(kind, N, noise, seed=N)
     key = f"{kind}_{N}_{noise}"
-    for fn in ("mc_host_run", "mc_host_run_w"):
+    for fn in ("mc_host_run", "mc_host_run_r"):
         rc, v, f, st = host_mc(udf, grads, fn)
         assert rc == 0
         assert np.array_equal(v, g[key + "_v"])      # vertex positions and numbering, bit for bit
@@ -65,7 +65,7 @@ def test_core_exact_zero_udf_extension_rule(host_mc, ref_mc):
         udf, grads = analytic_field(kind, N, noise, seed=7)
         udf = udf.copy(); udf[udf < zf * 2 / (N - 1)] = 0.0
         rv, rf = ref_mc(udf, grads)
-        for fn in ("mc_host_run", "mc_host_run_w"):
+        for fn in ("mc_host_run", "mc_host_run_r"):
             rc, v, f, st = host_mc(udf, grads, fn)
             assert rc == 0 and np.array_equal(v, rv) and np.array_equal(f, rf), (kind, fn)
 
