@@ -285,13 +285,17 @@ MC_HD void decode_index(int32_t c, int N, int& z, int& y, int& x) { x = c % N; y
 #if defined(__CUDA_ARCH__)
 // every lane executes the "loop" body once: a vote collects the predicate of all lanes
 #define MC_VOTE(mask, l, pred) mask = __ballot_sync(0xffffffffu, (pred))
+// a per-lane register (one slot on the device, an array over the emulated lanes on the host)
+#define MC_LANE_SLOTS 1
+#define MC_LANE_SLOT(l) 0
 #else
 #define MC_VOTE(mask, l, pred) mask |= ((pred) ? (1u << (l)) : 0u)
+#define MC_LANE_SLOTS 32
+#define MC_LANE_SLOT(l) (l)
 #endif
 
 // record copy global -> shared: asynchronous on the device (no registers; MC_COPY_WAIT() completes all copies in flight)
-MC_HD void copy_record(Rec* dst, const Rec* src, int l) {
-  if (l >= 25) return;
+MC_HD void copy_record(Rec* dst, const Rec* src, int l) {   // 16-byte piece l of the 25
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(reinterpret_cast<U4*>(dst) + l)),
                "l"(reinterpret_cast<const U4*>(src) + l) : "memory");
@@ -560,7 +564,7 @@ MC_HD void push_neighbours_r(Chain& g, int32_t cid) {
 // a visit outside the BFS window (raster seed, priority queues): fetch the record first
 MC_HD bool visit_direct_r(Chain& g, ChainCache& cc, const Chain* home, int32_t cid, int mode, bool& done_set) {
   MC_WARP_SYNC();
-  MC_LANE_LOOP(l) { copy_record(&cc.rec, g.recs + cid, l); }
+  MC_LANE_LOOP(l) { if (l < 25) copy_record(&cc.rec, g.recs + cid, l); }
   MC_COPY_WAIT();
   MC_WARP_SYNC();
   return visit_r(g, cc.rec, home, cid, mode, done_set);
@@ -581,6 +585,9 @@ MC_HD void replay_r(Chain& g, ChainCache& cc, const Chain* home) {
   MC_LANE_LOOP(l) { cc.qw_cur[l] = -1; }
   MC_WARP_SYNC();
   uint32_t qw_base = 0, qw_n = 0, qw_valid = 0;   // window [qw_base, qw_base + qw_n) of queue positions; bit = may be visited
+  int32_t nx_c[MC_LANE_SLOTS];                    // per lane: the entry of the window after this one, requested early
+  uint32_t nx_base = 0xffffffffu, nx_n = 0;
+  for (int i = 0; i < MC_LANE_SLOTS; ++i) nx_c[i] = -1;
   bool done_set = false;
   for (int64_t sw_base = 0; sw_base < g.n_cand; sw_base += 32) {
     // raster window: 32 consecutive candidate ids; bit = not visited yet
@@ -615,24 +622,29 @@ MC_HD void replay_r(Chain& g, ChainCache& cc, const Chain* home) {
           if (g.done[cur]) continue;
         } else {
           if (g.q.head - qw_base >= qw_n) {
+            // refill: the entries were requested one window ahead (nx_c), so one memory latency covers the visited flags,
+            // the records (copied for every real entry: waiting for the flags first would cost a second latency) and the
+            // request for the following window's entries
             qw_base = g.q.head;
             const uint32_t avail = g.q.tail - g.q.head;
             qw_n = avail < 32u ? avail : 32u;
             MC_PROF_INC(6);
             qw_valid = 0;
+            const bool have = nx_base == qw_base;
+            const uint32_t more = avail - qw_n < 32u ? avail - qw_n : 32u;
             MC_WARP_SYNC();
             MC_LANE_LOOP(l) {
               int32_t c = -1;
-              if ((uint32_t)l < qw_n) c = g.q.buf[(qw_base + (uint32_t)l) & g.q.mask];
+              if ((uint32_t)l < qw_n) c = (have && (uint32_t)l < nx_n) ? nx_c[MC_LANE_SLOT(l)] : g.q.buf[(qw_base + (uint32_t)l) & g.q.mask];
+              if (c >= 0) {
+                MC_UNROLL
+                for (int k = 0; k < 25; ++k) copy_record(&cc.wrec[l], g.recs + c, k);
+              }
+              nx_c[MC_LANE_SLOT(l)] = (uint32_t)l < more ? g.q.buf[(qw_base + 32u + (uint32_t)l) & g.q.mask] : -1;
               MC_VOTE(qw_valid, l, c >= 0 && !g.done[c]);
               cc.qw_cur[l] = c;
             }
-            MC_WARP_SYNC();
-            for (uint32_t m = qw_valid; m; m &= m - 1u) {
-              const int e = MC_POPC((m & (0u - m)) - 1u);
-              const int32_t c = cc.qw_cur[e];
-              MC_LANE_LOOP(l) { copy_record(&cc.wrec[e], g.recs + c, l); }
-            }
+            nx_base = qw_base + 32u; nx_n = more;
             MC_COPY_WAIT();
             MC_WARP_SYNC();
           }

@@ -696,7 +696,22 @@ struct PersistArgs {
   int use_tc;                 // precision mode 1: wide units run on tcgen05 (ops with wide == 2); the kernel holds 64 TMEM columns
   unsigned* sync;             // [0] barrier counter, [1] abort flag
   long long* prof;            // diagnostics (may be null): [cta 0 | cta G-1][op type][body cycles, barrier cycles, count]
+  const struct WJob* wjobs;   // weight stream (use_tma): one entry per token-GEMM op of a pass, in program order
+  int n_wjobs;
+  int use_tma;                // tcgen05 units take their weights from the packed stream through cp.async.bulk (see WJob)
 };
+
+// Weight stream of the tcgen05 units.  The weights of a unit are immutable and the op list is static, so they do not have
+// to wait for the op chain: at load time every (op, output tile, K slice) gets its chunk pairs packed as ready-made 32 KB
+// shared-memory images (fp16 hi plane | lo plane, 128 rows x 128 B each, SWIZZLE_128B applied), and one thread of each CTA
+// walks the CTA's future units in program order and copies the next images into a ring with cp.async.bulk (TMA, completion
+// on an mbarrier) whenever a stage is free -- across grid barriers, GroupNorm and attention ops.  HBM keeps streaming while
+// the dependent chain synchronises, and a token GEMM finds its first pairs already resident.
+struct WJob {
+  const uint8_t* base;        // [tiles_n * ks][pairs_max][32 KB]
+  int tiles_n, tiles_m, ks, n_chunks, pairs_max, pad;
+};
+constexpr int WJOB_MAX = 96;
 
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -721,7 +736,8 @@ __device__ __forceinline__ void grid_arrive(unsigned* sync) {   // call after a 
   if (threadIdx.x == 0) red_release_add(sync, 1u);
 }
 // returns false when the run was aborted (a CTA waited > ~1 s: never expected)
-__device__ __forceinline__ bool grid_wait(unsigned* sync, unsigned& target, unsigned G, int* s_ok) {
+template <typename Idle>
+__device__ __forceinline__ bool grid_wait(unsigned* sync, unsigned& target, unsigned G, int* s_ok, Idle idle) {
   if (threadIdx.x == 0) {
     target += G;
     int ok = 1;
@@ -730,6 +746,7 @@ __device__ __forceinline__ bool grid_wait(unsigned* sync, unsigned& target, unsi
     for (;;) {
       const unsigned v = ld_acquire(sync);
       if ((int)(v - target) >= 0) break;
+      idle();   // the weight stream keeps issuing while this CTA waits
       if ((++spins & 1023u) == 0u) {
         if (*(volatile unsigned*)(sync + 1) != 0u || clock64() - t0 > 2000000000LL) {
           atomicExch(sync + 1, 1u);
@@ -1370,6 +1387,13 @@ constexpr int TC_OP_BYTES = (WN + CT) * 128 * 2;               // hi + lo planes
 constexpr int TC_W_LO = WN * 128, TC_A_HI = 2 * WN * 128, TC_A_LO = 2 * WN * 128 + CT * 128;
 constexpr int TC_ASTG = 2 * CT * CT;                            // floats per fp32 token-row stage (2 chunks x 32 rows x 32)
 constexpr int TC_SMEM = 1024 + TC_STAGES * TC_OP_BYTES + TC_STAGES * TC_ASTG * 4;
+// weight-stream layout (use_tma): [W ring: TC_STAGES x 32 KB, written by cp.async.bulk only][A operand tiles: TC_STAGES x 8 KB]
+// [fp32 token-row staging: TC_STAGES x 8 KB -- also the scratch of the attention / embedding ops, which run between GEMMs]
+constexpr int TCX_W_BYTES = 2 * WN * 128;                       // one chunk pair of weights: hi + lo planes
+constexpr int TCX_A_BYTES = 2 * CT * 128;
+constexpr int TCX_A_OFF = TC_STAGES * TCX_W_BYTES;
+constexpr int TCX_STG_OFF = TCX_A_OFF + TC_STAGES * TCX_A_BYTES;
+static_assert(TCX_STG_OFF + TC_STAGES * TC_ASTG * 4 + 1024 == TC_SMEM, "both layouts use the same dynamic shared memory");
 __device__ __forceinline__ uint8_t* tc_ops(float* smem) {   // operand ring: first 1024-byte boundary of the dynamic shared memory
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
 }
@@ -1432,13 +1456,66 @@ __device__ __forceinline__ void tcw_ld32(uint32_t taddr, uint32_t* r) {
 // per-CTA state of the tcgen05 path (static shared memory of the persistent kernel)
 struct TcState {
   uint64_t stage_free[TC_STAGES];   // the MMAs that read operand stage s have completed
+  uint64_t full[TC_STAGES];         // weight stream: the image of ring stage s has landed (complete_tx)
   uint64_t done;                    // all MMAs of the unit have completed
   uint32_t tmem_base;
   uint32_t pad;
 };
 // thread-local, uniform: commits issued so far per barrier (a wait targets the phase of the latest commit; waiting twice for
 // the same phase is harmless, so no wait is ever "owed")
-struct TcPhase { uint32_t stage[TC_STAGES]; uint32_t done; };
+struct TcPhase { uint32_t stage[TC_STAGES]; uint32_t done; uint32_t pairs; };   // pairs: chunk pairs consumed so far (weight stream: ring position)
+
+// ---- weight-stream producer (thread 0 of every CTA) ----
+__device__ __forceinline__ bool tcw_mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(tcw_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+struct WCursor {
+  int ji, u, p, np;        // job, unit, pair within the unit, pairs of the unit
+  int reps;                // passes over the job list still to stream (this one included)
+  uint32_t issued;         // images issued so far
+  int n_jobs, cta, G;
+};
+__device__ __forceinline__ int wjob_pairs(const WJob& j, int u) {
+  const int crank = u % j.ks;
+  const int f_begin = (crank * j.n_chunks) / j.ks, f_end = ((crank + 1) * j.n_chunks) / j.ks;
+  return (f_end - f_begin + 1) >> 1;
+}
+// position the cursor on the first unit at or after (ji, u) that exists; reps == 0: stream finished
+__device__ __forceinline__ void wcursor_settle(WCursor& c, const WJob* jobs) {
+  while (c.reps > 0) {
+    if (c.ji >= c.n_jobs) { c.ji = 0; c.u = c.cta; --c.reps; continue; }
+    const WJob& j = jobs[c.ji];
+    if (c.u >= j.tiles_n * j.tiles_m * j.ks) { ++c.ji; c.u = c.cta; continue; }
+    c.np = wjob_pairs(j, c.u);
+    return;
+  }
+}
+// issue as many images as the ring takes (never blocks)
+__device__ __forceinline__ void wstream_pump(WCursor& c, const WJob* jobs, TcState* ts, uint8_t* ring) {
+  while (c.reps > 0) {
+    const uint32_t s = c.issued & (TC_STAGES - 1), k = c.issued / TC_STAGES;
+    // use k of stage s overwrites use k-1: its MMAs must have completed (commit -> stage_free phase k-1)
+    if (k > 0 && !tcw_mbar_test(&ts->stage_free[s], (k - 1u) & 1u)) return;
+    const WJob& j = jobs[c.ji];
+    const int crank = c.u % j.ks, tn = (c.u / j.ks) % j.tiles_n;
+    const uint8_t* src = j.base + ((size_t)(tn * j.ks + crank) * j.pairs_max + c.p) * TCX_W_BYTES;
+    const uint32_t bar = tcw_smem_u32(&ts->full[s]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TCX_W_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tcw_smem_u32(ring + s * TCX_W_BYTES)), "l"(src), "r"((uint32_t)TCX_W_BYTES), "r"(bar) : "memory");
+    ++c.issued;
+    if (++c.p >= c.np) { c.p = 0; c.u += c.G; wcursor_settle(c, jobs); }
+  }
+}
+
 
 // load-time split of a weight tensor: block of 32 floats -> [32 x hi | 32 x lo] halves in the same 128 bytes
 __global__ void split_weights_kernel(const float* __restrict__ W, float* __restrict__ Wh, size_t n_blocks) {
@@ -1452,6 +1529,36 @@ __global__ void split_weights_kernel(const float* __restrict__ W, float* __restr
   uint32_t* dst = reinterpret_cast<uint32_t*>(Wh + blk * 32);
   dst[j] = hi;
   dst[16 + j] = lo;
+}
+
+// load-time packing of the weight stream: block (weight unit = tile_n * ks + slice, pair) writes one 32 KB image, same
+// thread -> 16-byte piece mapping and the same swizzle as tc_issue()'s shared-memory destination
+__global__ void __launch_bounds__(256) pack_wstream_kernel(ConvArgs a, int ks, int n_chunks0, int n_chunks, int pairs_max, uint8_t* dst) {
+  const int wu = (int)blockIdx.x, pair = (int)blockIdx.y;
+  const int crank = wu % ks, tn = wu / ks;
+  const int n0 = tn * WN;
+  const int f_begin = (crank * n_chunks) / ks, f_end = ((crank + 1) * n_chunks) / ks;
+  uint8_t* img = dst + ((size_t)wu * pairs_max + pair) * TCX_W_BYTES;
+  const int tid = (int)threadIdx.x, lp = tid & 7, cr = tid >> 3;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int f = f_begin + 2 * pair + g;
+    const bool have = f < f_end;
+    const int s = (have && f >= n_chunks0) ? 1 : 0;
+    const Seg& sg = a.seg[s];
+    const int q = have ? (s ? f - n_chunks0 : f) : 0;
+    const int cb = q / sg.taps, tap = q - cb * sg.taps;
+    const float* wbase = sg.Wh + (size_t)tap * a.N * sg.Cin + cb * CT + 4 * lp;
+    const int plane = lp >> 2, p16 = 4 * g + (lp & 3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rr = cr + 32 * j;
+      const int n = n0 + rr;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (have && n < a.N) v = *reinterpret_cast<const uint4*>(wbase + (size_t)n * sg.Cin);
+      *reinterpret_cast<uint4*>(img + (plane ? TC_W_LO : 0) + rr * 128 + ((p16 ^ (rr & 7)) << 4)) = v;
+    }
+  }
 }
 
 // cp.async copies of chunk pair `pair` of a tcgen05 unit: what & 1 = split weight rows straight into the swizzled operand
@@ -1520,8 +1627,9 @@ __device__ __forceinline__ void tc_preissue(const POp& o, float* smem, int cta) 
 }
 
 // returns false when a wait timed out (the caller aborts the run)
+// tma: the weights arrive through the weight stream (wstream_pump) instead of this CTA's cp.async copies
 __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* partials, unsigned* sems, unsigned* abort_flag, bool pre_issued,
-                                          int cta, int G, long long* prof, TcState* ts, TcPhase& ph) {
+                                          int cta, int G, long long* prof, TcState* ts, TcPhase& ph, bool tma, WCursor& wc, const WJob* jobs) {
   const bool pf = prof != nullptr && cta == 0 && threadIdx.x == 0;
   const ConvArgs& a = o.conv;
   const int ks = o.ks;
@@ -1531,7 +1639,10 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
   const int n_chunks0 = a.seg[0].taps * (a.seg[0].Cin / CT);
   const int n_chunks = n_chunks0 + (a.nseg > 1 ? a.seg[1].taps * (a.seg[1].Cin / CT) : 0);
   uint8_t* ops = tc_ops(smem);
-  float* astg = tc_astage(smem);
+  float* astg = tma ? reinterpret_cast<float*>(ops + TCX_STG_OFF) : tc_astage(smem);
+  // operand tiles of ring stage s: weights (hi plane, lo plane at + TC_W_LO) and token rows (hi, lo at + CT * 128)
+  auto w_tile = [&](int st) { return tma ? ops + st * TCX_W_BYTES : ops + st * TC_OP_BYTES; };
+  auto a_tile = [&](int st) { return tma ? ops + TCX_A_OFF + st * TCX_A_BYTES : ops + st * TC_OP_BYTES + TC_A_HI; };
   const uint32_t idesc = tcw_idesc();
   const uint32_t tmem = ts->tmem_base;
   bool ok = true;
@@ -1547,22 +1658,25 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
     const int n0 = tn * WN, m0 = tm * CT;
     const int f_begin = (crank * n_chunks) / ks, f_end = ((crank + 1) * n_chunks) / ks;
     const int n_pairs = (f_end - f_begin + 1) >> 1;
+    // ring stage of the unit's pair: the weight stream numbers the pairs of the whole run, the local ring restarts per unit
+    const uint32_t gp0 = tma ? ph.pairs : 0u;
+    auto stage_of = [&](int pair) { return (int)((gp0 + (uint32_t)pair) & (TC_STAGES - 1)); };
     auto issue_pair = [&](int pair, int what) {
-      const int s = pair & (TC_STAGES - 1);
-      tc_issue(a, n_chunks0, f_begin, f_end, n0, m0, pair, ops + s * TC_OP_BYTES, astg + s * TC_ASTG, what);
+      const int s = stage_of(pair);
+      tc_issue(a, n_chunks0, f_begin, f_end, n0, m0, pair, w_tile(s), astg + s * TC_ASTG, tma ? (what & 2) : what);
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     // (every MMA of the previous unit / op has completed: its `done` wait; stages 0 and 1 are free)
-    const int first_what = (pre_issued && u == cta) ? 2 : 3;
+    const int first_what = (tma || (pre_issued && u == cta)) ? 2 : 3;
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       if (p < n_pairs) issue_pair(p, first_what);
       else asm volatile("cp.async.commit_group;" ::: "memory");
     }
     for (int p = 0; p < n_pairs; ++p) {
-      const int s = p & (TC_STAGES - 1);
+      const int s = stage_of(p);
       if (p + 2 < n_pairs) {
-        wait_stage((p + 2) & (TC_STAGES - 1));   // read by the MMAs of pair p - 2 (issued one iteration ago at the latest)
+        wait_stage(stage_of(p + 2));   // read by the MMAs of pair p - 2 (issued one iteration ago at the latest)
         issue_pair(p + 2, 3);
       } else {
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1581,18 +1695,27 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
         split_f16x2(make_float2(x0.z, x0.w), hi.y, lo.y);
         split_f16x2(make_float2(x1.x, x1.y), hi.z, lo.z);
         split_f16x2(make_float2(x1.z, x1.w), hi.w, lo.w);
-        uint8_t* ob = ops + s * TC_OP_BYTES;
+        uint8_t* at = a_tile(s);
         const int off = rr * 128 + ((pc ^ (rr & 7)) << 4);
-        *reinterpret_cast<uint4*>(ob + TC_A_HI + off) = hi;
-        *reinterpret_cast<uint4*>(ob + TC_A_LO + off) = lo;
+        *reinterpret_cast<uint4*>(at + off) = hi;
+        *reinterpret_cast<uint4*>(at + CT * 128 + off) = lo;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (copies, split) -> tensor core reads
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
       if (tid == 0) {
+        if (tma) {   // this pair's weight image: issued by the stream long ago in the steady state
+          const uint32_t par = ((gp0 + (uint32_t)p) / TC_STAGES) & 1u;
+          uint32_t spins = 0;
+          wstream_pump(wc, jobs, ts, ops);
+          while (!tcw_mbar_test(&ts->full[s], par)) {
+            wstream_pump(wc, jobs, ts, ops);
+            if (++spins > (1u << 24)) { ok = false; break; }
+          }
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = tcw_smem_u32(ops + s * TC_OP_BYTES);
-        const uint64_t whi = tcw_desc(sa), wlo = tcw_desc(sa + TC_W_LO), ahi = tcw_desc(sa + TC_A_HI), alo = tcw_desc(sa + TC_A_LO);
+        const uint32_t sw = tcw_smem_u32(w_tile(s)), sa = tcw_smem_u32(a_tile(s));
+        const uint64_t whi = tcw_desc(sw), wlo = tcw_desc(sw + TC_W_LO), ahi = tcw_desc(sa), alo = tcw_desc(sa + CT * 128);
         const bool has2 = f_begin + 2 * p + 1 < f_end;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {   // 16 halves = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
@@ -1607,6 +1730,7 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
       }
       ph.stage[s] += 1u;
     }
+    ph.pairs += (uint32_t)n_pairs;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     ph.done += 1u;
     if (!tcw_mbar_wait(&ts->done, (ph.done - 1u) & 1u)) ok = false;
@@ -1858,11 +1982,23 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
   static_assert(sizeof(POp) <= 256 * sizeof(int), "descriptor must fit one word per thread");
   fetch_op(0, 0);
   __shared__ TcState tcs;
+  __shared__ WJob s_jobs[MODE == 1 ? WJOB_MAX : 1];
   TcPhase tph{};
   const bool use_tc = MODE == 1 && pa.use_tc != 0;
+  const bool use_tma = use_tc && pa.use_tma != 0;
+  WCursor wcur{};
+  if (use_tma) {
+    for (int i = tid; i < pa.n_wjobs * (int)(sizeof(WJob) / sizeof(int)); i += 256)
+      reinterpret_cast<int*>(s_jobs)[i] = reinterpret_cast<const int*>(pa.wjobs)[i];
+    wcur.n_jobs = pa.n_wjobs; wcur.cta = cta; wcur.G = G; wcur.u = cta; wcur.reps = pa.n_steps * pa.n_pass;
+  }
+  // scratch of the attention / embedding ops: behind the weight ring when the stream owns the front of the shared memory
+  float* const scr = use_tma ? reinterpret_cast<float*>(tc_ops(smem) + TCX_STG_OFF) : smem;
+  auto pump = [&]() { if (MODE == 1 && use_tma) wstream_pump(wcur, s_jobs, &tcs, tc_ops(smem)); };   // thread 0 only
   if (use_tc) {   // tcgen05 path: mbarriers + 64 TMEM columns (two 128 x 32 fp32 accumulators), held for the whole run
     if (tid == 0) {
       for (int i = 0; i < TC_STAGES; ++i) tcw_mbar_init(&tcs.stage_free[i], 1);
+      for (int i = 0; i < TC_STAGES; ++i) tcw_mbar_init(&tcs.full[i], 1);
       tcw_mbar_init(&tcs.done, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1874,6 +2010,7 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
   }
   __syncthreads();
   if (use_tc) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (use_tma && tid == 0) { wcursor_settle(wcur, s_jobs); pump(); }
   int slot = 0;
   [&]() {   // the op loop; `return` leaves it early when the run is aborted (TMEM is released below in every case)
   for (int iter = 0; iter < pa.n_steps; ++iter) {
@@ -1895,6 +2032,7 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
         const bool profiled = pa.prof != nullptr && tid == 0 && (cta == 0 || cta == G - 1);
         long long t_op0 = 0;
         if (profiled) t_op0 = clock64();
+        if (tid == 0) pump();
         switch (o.type) {
           case P_EMB1: {   // timestep embedding (temb_kernel) + first time_embed linear with SiLU
             const int B = pa.B;
@@ -1907,11 +2045,11 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
                 const float c = -9.210340371976184f;
                 const float f = expf(__fdiv_rn(__fmul_rn(c, (float)k), 112.0f));
                 const float arg = __fmul_rn(tf, f);
-                smem[r * TCH + k] = cosf(arg);
-                smem[r * TCH + TCH / 2 + k] = sinf(arg);
+                scr[r * TCH + k] = cosf(arg);
+                scr[r * TCH + TCH / 2 + k] = sinf(arg);
               }
               __syncthreads();
-              p_lin_cols(o, smem, mb, rows, cta, G);
+              p_lin_cols(o, scr, mb, rows, cta, G);
             }
             break;
           }
@@ -1931,12 +2069,12 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
                   if (i < rows * K) {
                     float x = xv[q];
                     if (in_silu) x = x / (1.0f + expf(-x));
-                    smem[i] = x;
+                    scr[i] = x;
                   }
                 }
               }
               __syncthreads();
-              p_lin_cols(o, smem, mb, rows, cta, G);
+              p_lin_cols(o, scr, mb, rows, cta, G);
             }
             break;
           }
@@ -1962,7 +2100,7 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
           case P_CONV:
             if (MODE == 1 && o.wide == 2) {
               unsigned* bank = pa.sems + (size_t)(seq & 1u) * pa.sem_bank;
-              if (!p_conv_tc(o, smem, pa.partials, bank, pa.sync + 1, pre_issued, cta, G, pa.prof, &tcs, tph)) {
+              if (!p_conv_tc(o, smem, pa.partials, bank, pa.sync + 1, pre_issued, cta, G, pa.prof, &tcs, tph, use_tma, wcur, s_jobs)) {
                 if (tid == 0) atomicExch(pa.sync + 1, 1u);   // a tensor-core wait timed out: abort the run (reported by surfd_unet_status)
               }
             } else if (MODE != 0 && o.wide) {
@@ -1979,10 +2117,10 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
             const int n_units = pa.B * heads;
             for (int u = cta; u < n_units; u += G)
               if (o.ps.ks > 0)
-                attn_unit(o.in0, o.i0, o.i1, heads, o.f0, o.out0, u / heads, u % heads, smem, tid, 256, [] { __syncthreads(); },
+                attn_unit(o.in0, o.i0, o.i1, heads, o.f0, o.out0, u / heads, u % heads, scr, tid, 256, [] { __syncthreads(); },
                           [&](const float*, int m, int c) { return part_value(o.ps, o.i1, m, c); });
               else
-                attn_unit(o.in0, o.i0, o.i1, heads, o.f0, o.out0, u / heads, u % heads, smem, tid, 256, [] { __syncthreads(); },
+                attn_unit(o.in0, o.i0, o.i1, heads, o.f0, o.out0, u / heads, u % heads, scr, tid, 256, [] { __syncthreads(); },
                           [](const float* p, int, int) { return *p; });
             break;
           }
@@ -2035,12 +2173,13 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
         if (profiled) t_op1 = clock64();
         grid_arrive(pa.sync);
         pre_issued = false;
-        if (MODE != 0 && has_next && sop[slot ^ 1].type == P_CONV && sop[slot ^ 1].wide) {
+        if (tid == 0) pump();
+        if (MODE != 0 && !use_tma && has_next && sop[slot ^ 1].type == P_CONV && sop[slot ^ 1].wide) {
           if (sop[slot ^ 1].wide == 2) tc_preissue(sop[slot ^ 1], smem, cta);
           else wide_preissue<WTP, W_STAGE, W_STAGES>(sop[slot ^ 1], smem, cta);
           pre_issued = true;
         }
-        if (!grid_wait(pa.sync, target, (unsigned)G, &s_ok)) return;
+        if (!grid_wait(pa.sync, target, (unsigned)G, &s_ok, pump)) return;
         if (profiled) {
           long long* pr = pa.prof + ((cta == 0 ? 0 : 8) + sop[slot].type) * 3;
           pr[0] += t_op1 - t_op0;
@@ -2094,7 +2233,8 @@ static_assert(8 * CONV_STAGES * 2 * CT * CTP >= 8 * CT * 33 + CT * CT, "reductio
 struct Lane {
   DevBuf pool, emb_all, temb, e1, emb, t_cur, x0a, x0b, xcur, state;
   // persistent sampler: op descriptors, K-slice scratch, semaphores, barrier word + abort flag
-  DevBuf emb_silu, ctxv, p_ops, p_partials, p_sems, p_sync, p_prof;
+  DevBuf emb_silu, ctxv, p_ops, p_partials, p_sems, p_sync, p_prof, p_wjobs, p_wstream;
+  int p_n_wjobs = 0, p_use_tma = 0;
   int p_B = -1, p_n_emb = 0, p_n_prog = 0, p_smem = 0, p_grid = 0, p_split = -1, p_wide = -1, p_sem_bank = 0, p_use_tc = 0;
   const float* p_ctx = nullptr;
   const int64_t* p_lab = nullptr;
@@ -2119,6 +2259,7 @@ struct Lane {
     pool.release(); emb_all.release(); temb.release(); e1.release(); emb.release(); t_cur.release(); x0a.release(); x0b.release();
     xcur.release(); state.release();
     emb_silu.release(); ctxv.release(); p_ops.release(); p_partials.release(); p_sems.release(); p_sync.release(); p_prof.release();
+    p_wjobs.release(); p_wstream.release();
     p_B = -1;
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
@@ -2619,6 +2760,51 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
       nx.ps.ks = c.ks; nx.ps.tiles_n = c.tiles_n; nx.ps.emb_ld = c.conv.emb_ld; nx.ps.N = c.conv.N;
     }
   }
+  // weight stream (tcgen05 units): packed 32 KB images per (op, output tile, K slice, chunk pair) + the job table
+  ln.p_use_tma = 0; ln.p_n_wjobs = 0;
+  if (use_tc && !(dbg & (4 | 128))) {
+    std::vector<WJob> jobs;
+    std::vector<size_t> offs;
+    size_t total = 0;
+    bool all_tc = true;
+    for (const auto& o : ops) {
+      if (o.type != P_CONV) continue;
+      if (o.wide != 2) { all_tc = false; break; }
+      const ConvArgs& a = o.conv;
+      const int n_chunks0 = a.seg[0].taps * (a.seg[0].Cin / CT);
+      const int n_chunks = n_chunks0 + (a.nseg > 1 ? a.seg[1].taps * (a.seg[1].Cin / CT) : 0);
+      int pairs_max = 0;
+      for (int c = 0; c < o.ks; ++c) {
+        const int fb = (c * n_chunks) / o.ks, fe = ((c + 1) * n_chunks) / o.ks;
+        pairs_max = std::max(pairs_max, (fe - fb + 1) >> 1);
+      }
+      WJob j{};
+      j.tiles_n = o.tiles_n; j.tiles_m = o.tiles_m; j.ks = o.ks; j.n_chunks = n_chunks; j.pairs_max = pairs_max;
+      offs.push_back(total);
+      total += (size_t)o.tiles_n * o.ks * pairs_max * TCX_W_BYTES;
+      jobs.push_back(j);
+    }
+    if (all_tc && !jobs.empty() && (int)jobs.size() <= WJOB_MAX) {
+      SURFD_TRY(ln.p_wstream.reserve(total));
+      size_t ji = 0;
+      for (const auto& o : ops) {
+        if (o.type != P_CONV) continue;
+        WJob& j = jobs[ji];
+        j.base = ln.p_wstream.as<uint8_t>() + offs[ji];
+        const ConvArgs& a = o.conv;
+        const int n_chunks0 = a.seg[0].taps * (a.seg[0].Cin / CT);
+        pack_wstream_kernel<<<dim3((unsigned)(o.tiles_n * o.ks), (unsigned)j.pairs_max), 256>>>(a, o.ks, n_chunks0, j.n_chunks, j.pairs_max,
+                                                                                                  ln.p_wstream.as<uint8_t>() + offs[ji]);
+        SURFD_CHECK_LAUNCH();
+        ++ji;
+      }
+      SURFD_CUDA(cudaDeviceSynchronize());
+      SURFD_TRY(ln.p_wjobs.reserve(jobs.size() * sizeof(WJob)));
+      SURFD_CUDA(cudaMemcpy(ln.p_wjobs.p, jobs.data(), jobs.size() * sizeof(WJob), cudaMemcpyHostToDevice));
+      ln.p_n_wjobs = (int)jobs.size();
+      ln.p_use_tma = 1;
+    }
+  }
   if (dbg & 4) for (auto& o : ops) o.type = 0;
   SURFD_TRY(ln.p_partials.reserve((max_partial_tiles ? max_partial_tiles : 1) * CT * CT * sizeof(float)));
   for (auto& o : ops) if (o.ps.ks > 0) o.ps.part = ln.p_partials.as<float>();
@@ -2664,6 +2850,7 @@ static int sample_persistent(surfd_unet* u, int B, int n_steps, const int64_t* t
   pa.tmap = tmap_dev; pa.coef = coef_dev; pa.noise = noise_dev; pa.noise_stride = (long long)B * L; pa.guidance = guidance;
   pa.x = ln.xcur.as<float>(); pa.x0a = ln.x0a.as<float>();
   pa.partials = ln.p_partials.as<float>(); pa.sems = ln.p_sems.as<unsigned>(); pa.sem_bank = ln.p_sem_bank; pa.use_tc = ln.p_use_tc; pa.sync = ln.p_sync.as<unsigned>();
+  pa.wjobs = ln.p_wjobs.as<WJob>(); pa.n_wjobs = ln.p_n_wjobs; pa.use_tma = ln.p_use_tma;
   pa.prof = nullptr;
   if (u->profile) {
     SURFD_CUDA(cudaMemsetAsync(ln.p_prof.p, 0, 48 * sizeof(long long), st));
