@@ -696,8 +696,9 @@ struct PersistArgs {
   int use_tc;                 // precision mode 1: wide units run on tcgen05 (ops with wide == 2); the kernel holds 64 TMEM columns
   unsigned* sync;             // [0] barrier counter, [1] abort flag
   long long* prof;            // diagnostics (may be null): [cta 0 | cta G-1][op type][body cycles, barrier cycles, count]
-  const struct WJob* wjobs;   // weight stream (use_tma): one entry per token-GEMM op of a pass, in program order
-  int n_wjobs;
+  const uint8_t* const* wlist;   // weight stream (use_tma): image pointers of one pass, per CTA in consumption order
+  const int* wl_start;           // [grid] first entry of the CTA's list
+  const int* wl_count;           // [grid] its length
   int use_tma;                // tcgen05 units take their weights from the packed stream through cp.async.bulk (see WJob)
 };
 
@@ -1477,45 +1478,47 @@ __device__ __forceinline__ bool tcw_mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// The CTA's images of one pass over the op list, in consumption order, are listed at load time (persist_build): the producer
+// only walks a pointer list -- a single thread runs this code, and every dependent scalar instruction costs it 5-8 cycles
+// (a first version that derived unit / slice / pair from the op table with integer divisions spent 1.8 us per unit here).
 struct WCursor {
-  int ji, u, p, np;        // job, unit, pair within the unit, pairs of the unit
-  int reps;                // passes over the job list still to stream (this one included)
-  uint32_t issued;         // images issued so far
-  int n_jobs, cta, G;
+  const uint8_t* const* list;   // this CTA's image pointers of one pass
+  uint32_t n, idx, reps;        // images per pass, position, passes still to stream (this one included)
+  uint32_t issued;              // images issued so far
 };
-__device__ __forceinline__ int wjob_pairs(const WJob& j, int u) {
-  const int crank = u % j.ks;
-  const int f_begin = (crank * j.n_chunks) / j.ks, f_end = ((crank + 1) * j.n_chunks) / j.ks;
-  return (f_end - f_begin + 1) >> 1;
-}
-// position the cursor on the first unit at or after (ji, u) that exists; reps == 0: stream finished
-__device__ __forceinline__ void wcursor_settle(WCursor& c, const WJob* jobs) {
-  while (c.reps > 0) {
-    if (c.ji >= c.n_jobs) { c.ji = 0; c.u = c.cta; --c.reps; continue; }
-    const WJob& j = jobs[c.ji];
-    if (c.u >= j.tiles_n * j.tiles_m * j.ks) { ++c.ji; c.u = c.cta; continue; }
-    c.np = wjob_pairs(j, c.u);
-    return;
-  }
-}
-// issue as many images as the ring takes (never blocks)
-__device__ __forceinline__ void wstream_pump(WCursor& c, const WJob* jobs, TcState* ts, uint8_t* ring) {
-  while (c.reps > 0) {
+// issue as many images as the ring takes (never blocks).  The pointers of the next TC_STAGES images are requested together
+// up front: one L2 round trip per call instead of one per image.
+__device__ __forceinline__ void wstream_pump(WCursor& c, TcState* ts, uint8_t* ring) {
+  if (c.reps == 0) return;
+  {   // anything to do at all?  (the common case in the grid-barrier spin loop: the ring is full)
     const uint32_t s = c.issued & (TC_STAGES - 1), k = c.issued / TC_STAGES;
-    // use k of stage s overwrites use k-1: its MMAs must have completed (commit -> stage_free phase k-1)
     if (k > 0 && !tcw_mbar_test(&ts->stage_free[s], (k - 1u) & 1u)) return;
-    const WJob& j = jobs[c.ji];
-    const int crank = c.u % j.ks, tn = (c.u / j.ks) % j.tiles_n;
-    const uint8_t* src = j.base + ((size_t)(tn * j.ks + crank) * j.pairs_max + c.p) * TCX_W_BYTES;
+  }
+  uint32_t idx = c.idx, reps = c.reps, issued = c.issued;
+  const uint8_t* ptr[TC_STAGES];
+  {
+    uint32_t j = idx;
+#pragma unroll
+    for (int i = 0; i < TC_STAGES; ++i) {
+      ptr[i] = c.list[j];
+      if (++j == c.n) j = 0;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TC_STAGES; ++i) {
+    if (reps == 0) break;
+    const uint32_t s = issued & (TC_STAGES - 1), k = issued / TC_STAGES;
+    // use k of stage s overwrites use k-1: its MMAs must have completed (commit -> stage_free phase k-1)
+    if (k > 0 && !tcw_mbar_test(&ts->stage_free[s], (k - 1u) & 1u)) break;
     const uint32_t bar = tcw_smem_u32(&ts->full[s]);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TCX_W_BYTES) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(tcw_smem_u32(ring + s * TCX_W_BYTES)), "l"(src), "r"((uint32_t)TCX_W_BYTES), "r"(bar) : "memory");
-    ++c.issued;
-    if (++c.p >= c.np) { c.p = 0; c.u += c.G; wcursor_settle(c, jobs); }
+                 ::"r"(tcw_smem_u32(ring + s * TCX_W_BYTES)), "l"(ptr[i]), "r"((uint32_t)TCX_W_BYTES), "r"(bar) : "memory");
+    ++issued;
+    if (++idx == c.n) { idx = 0; --reps; }
   }
+  c.idx = idx; c.reps = reps; c.issued = issued;
 }
-
 
 // load-time split of a weight tensor: block of 32 floats -> [32 x hi | 32 x lo] halves in the same 128 bytes
 __global__ void split_weights_kernel(const float* __restrict__ W, float* __restrict__ Wh, size_t n_blocks) {
@@ -1609,6 +1612,51 @@ __device__ __forceinline__ void tc_issue(const ConvArgs& a, int n_chunks0, int f
   }
 }
 
+// Token rows of chunk pair `pair` of a weight-stream unit (the `what & 2` part of tc_issue).  One thread runs ~30 of these
+// per op on the critical path, so the segment descriptors are read into registers before the first copy (every cp.async
+// carries a memory clobber: interleaved with the copies, each field was re-read from shared memory behind a dependent
+// address computation -- measured 1.3 us per unit for issuing 0.17 us worth of loads), the row -> (sample, token) division
+// is done once per unit by the caller, and the chunk -> (channel block, tap) division is by a constant.
+__device__ __forceinline__ void tc_issue_rows(const ConvArgs& a, int n_chunks0, int f_begin, int f_end, int pair, float* astg,
+                                              int rb, int rl, bool rok) {
+  const int tid = (int)threadIdx.x;
+  const int lp = tid & 7, cr = tid >> 3;
+  const Seg s0 = a.seg[0];
+  const Seg s1 = a.seg[1];
+  const float* src[2];
+  int bytes[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int f = f_begin + 2 * pair + g;
+    const bool have = f < f_end;
+    const bool one = f >= n_chunks0;
+    const int taps = one ? s1.taps : s0.taps, stride = one ? s1.stride : s0.stride, up = one ? s1.up : s0.up;
+    const int T_in = one ? s1.T_in : s0.T_in, C1 = one ? s1.C1 : s0.C1, Cin = one ? s1.Cin : s0.Cin;
+    const float* A = one ? s1.A : s0.A;
+    const float* A2 = one ? s1.A2 : s0.A2;
+    const int q = one ? f - n_chunks0 : f;
+    const int cb = taps == 3 ? q / 3 : (taps == 1 ? q : q / taps);
+    const int tap = q - cb * taps;
+    const int T_eff = up ? 2 * T_in : T_in;
+    const int sr = rl * stride + tap - (taps >> 1);
+    const bool ok = have && rok && sr >= 0 && sr < T_eff;
+    const int st = up ? (sr >> 1) : sr;
+    const bool second = cb * CT >= C1;
+    const float* base = second ? A2 : A;
+    const int ld = second ? Cin - C1 : C1;
+    const int coff = second ? cb * CT - C1 : cb * CT;
+    src[g] = base + (ok ? ((size_t)rb * T_in + st) * ld : (size_t)0) + (have ? coff : 0) + 4 * lp;
+    bytes[g] = ok ? 16 : 0;
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    if (f_begin + 2 * pair + g < f_end) {
+      const uint32_t da = tcw_smem_u32(astg + (g * CT + cr) * CT + 4 * lp);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(src[g]), "r"(bytes[g]) : "memory");
+    }
+  }
+}
+
 // weight copies of the first two chunk pairs of this CTA's first unit, issued before the barrier in front of the op
 __device__ __forceinline__ void tc_preissue(const POp& o, float* smem, int cta) {
   const ConvArgs& a = o.conv;
@@ -1629,7 +1677,7 @@ __device__ __forceinline__ void tc_preissue(const POp& o, float* smem, int cta) 
 // returns false when a wait timed out (the caller aborts the run)
 // tma: the weights arrive through the weight stream (wstream_pump) instead of this CTA's cp.async copies
 __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* partials, unsigned* sems, unsigned* abort_flag, bool pre_issued,
-                                          int cta, int G, long long* prof, TcState* ts, TcPhase& ph, bool tma, WCursor& wc, const WJob* jobs) {
+                                          int cta, int G, long long* prof, TcState* ts, TcPhase& ph, bool tma, WCursor& wc) {
   const bool pf = prof != nullptr && cta == 0 && threadIdx.x == 0;
   const ConvArgs& a = o.conv;
   const int ks = o.ks;
@@ -1660,87 +1708,199 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
     const int n_pairs = (f_end - f_begin + 1) >> 1;
     // ring stage of the unit's pair: the weight stream numbers the pairs of the whole run, the local ring restarts per unit
     const uint32_t gp0 = tma ? ph.pairs : 0u;
+    const int m_row = m0 + (tid >> 3);   // this thread's token row of the tile -> (sample, token)
+    const bool row_ok = m_row < M;
+    const int row_b = m_row / a.T_out, row_l = m_row - row_b * a.T_out;
     auto stage_of = [&](int pair) { return (int)((gp0 + (uint32_t)pair) & (TC_STAGES - 1)); };
     auto issue_pair = [&](int pair, int what) {
       const int s = stage_of(pair);
       tc_issue(a, n_chunks0, f_begin, f_end, n0, m0, pair, w_tile(s), astg + s * TC_ASTG, tma ? (what & 2) : what);
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // (every MMA of the previous unit / op has completed: its `done` wait; stages 0 and 1 are free)
-    const int first_what = (tma || (pre_issued && u == cta)) ? 2 : 3;
+    // split one pair's token rows (fp32 staging -> fp16 hi / lo operand tiles): thread -> 8 consecutive channels (one 16-byte
+    // piece of halves) of one row
+    auto split_pair = [&](int p, int s) {
+      const int rr = tid >> 3, pc = tid & 7;
+      const int g = pc >> 2, kk0 = (pc & 3) * 8;
+      const float* src = astg + s * TC_ASTG + (g * CT + rr) * CT + kk0;
+      float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
+      if (g == 1 && !(f_begin + 2 * p + 1 < f_end)) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }   // odd chunk count
+      uint4 hi, lo;
+      split_f16x2(make_float2(x0.x, x0.y), hi.x, lo.x);
+      split_f16x2(make_float2(x0.z, x0.w), hi.y, lo.y);
+      split_f16x2(make_float2(x1.x, x1.y), hi.z, lo.z);
+      split_f16x2(make_float2(x1.z, x1.w), hi.w, lo.w);
+      uint8_t* at = a_tile(s);
+      const int off = rr * 128 + ((pc ^ (rr & 7)) << 4);
+      *reinterpret_cast<uint4*>(at + off) = hi;
+      *reinterpret_cast<uint4*>(at + CT * 128 + off) = lo;
+    };
+    // thread 0: the pair's 12 (6) MMAs + the commits that free the stage / complete the unit
+    auto mma_pair = [&](int p, int s) {
+      if (tma) {   // this pair's weight image: issued by the stream long ago in the steady state
+        const uint32_t par = ((gp0 + (uint32_t)p) / TC_STAGES) & 1u;
+        uint32_t spins = 0;
+        const long long tw0 = pf ? clock64() : 0;
+        while (!tcw_mbar_test(&ts->full[s], par)) {
+          wstream_pump(wc, ts, ops);
+          if (++spins > (1u << 24)) { ok = false; break; }
+        }
+        if (pf) { prof[48] += clock64() - tw0; prof[51] += spins ? 1 : 0; }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      const uint32_t sw = tcw_smem_u32(w_tile(s)), sa = tcw_smem_u32(a_tile(s));
+      const uint64_t whi = tcw_desc(sw), wlo = tcw_desc(sw + TC_W_LO), ahi = tcw_desc(sa), alo = tcw_desc(sa + CT * 128);
+      const bool has2 = f_begin + 2 * p + 1 < f_end;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      if (p < n_pairs) issue_pair(p, first_what);
+      for (int k = 0; k < 4; ++k) {   // 16 halves = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+        if (k >= 2 && !has2) break;    // odd chunk count: the second half of the K row is absent
+        // Six independent accumulators (set = k & 1; W_hi A_hi | W_lo A_hi | W_hi A_lo): an MMA with 32 token columns is far
+        // shorter than the tensor pipe's accumulate latency, so back-to-back MMAs into ONE accumulator ran at ~226 cycles each
+        // (measured: 12 MMAs = 1.3 us per pair, the bound of the pair loop); now an accumulator is revisited every 6th MMA.
+        const uint32_t acc = (p != 0 || k >= 2) ? 1u : 0u;
+        const uint32_t set = tmem + (uint32_t)((k & 1) * 3 * CT);
+        tcw_mma(set + CT, wlo + (uint64_t)(2 * k), ahi + (uint64_t)(2 * k), idesc, acc);
+        tcw_mma(set, whi + (uint64_t)(2 * k), ahi + (uint64_t)(2 * k), idesc, acc);
+        tcw_mma(set + 2 * CT, whi + (uint64_t)(2 * k), alo + (uint64_t)(2 * k), idesc, acc);
+      }
+      tcw_commit(&ts->stage_free[s]);
+      if (p == n_pairs - 1) tcw_commit(&ts->done);
+    };
+    // Weight-stream flow: the MMAs of a pair are issued by TWO threads (a single thread pays ~110 cycles per tcgen05.mma: 12 per
+    // pair were 1.9 us per unit).  Thread 0: W_hi x [A_hi ; A_lo] as ONE MMA with 64 token columns (the two token planes are
+    // adjacent 32-row tiles) -> columns [0, 64) of the set; thread 32: W_lo x A_hi -> columns [64, 96).  4 + 4 instead of 12
+    // instructions per pair; the accumulators are disjoint, both threads commit to the stage / unit barriers (count 2).
+    auto full_wait = [&](int p, int s, int which) {   // the pair's weight image has landed (issued long ago in the steady state)
+      const uint32_t par = ((gp0 + (uint32_t)p) / TC_STAGES) & 1u;
+      uint32_t spins = 0;
+      while (!tcw_mbar_test(&ts->full[s], par)) {
+        if (which == 0) wstream_pump(wc, ts, ops);
+        if (++spins > (1u << 24)) { ok = false; break; }
+      }
+      if (pf) prof[51] += spins ? 1 : 0;
+    };
+    auto mma_pair2 = [&](int p, int s, int which) {
+      const uint32_t sw = tcw_smem_u32(w_tile(s)), sa = tcw_smem_u32(a_tile(s));
+      const uint64_t wd = tcw_desc(sw + (which ? TC_W_LO : 0)), ad = tcw_desc(sa);
+      const uint32_t id = which ? idesc : ((1u << 4) | ((uint32_t)((2 * CT) >> 3) << 17) | ((uint32_t)(WN >> 4) << 24));
+      const bool has2 = f_begin + 2 * p + 1 < f_end;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k >= 2 && !has2) break;
+        const uint32_t acc = (p != 0 || k >= 2) ? 1u : 0u;
+        const uint32_t set = tmem + (uint32_t)((k & 1) * 3 * CT) + (which ? 2u * CT : 0u);
+        tcw_mma(set, wd + (uint64_t)(2 * k), ad + (uint64_t)(2 * k), id, acc);
+      }
+      tcw_commit(&ts->stage_free[s]);
+      if (p == n_pairs - 1) tcw_commit(&ts->done);
+    };
+    if (tma) {
+      // Weight stream: the only generic-proxy writes to the operand tiles are the split token rows, so a unit needs ONE
+      // proxy fence per batch of up to TC_STAGES pairs instead of one per pair.  (Measured: with a fence behind every pair
+      // the pair loop cost 1.3-2 us per pair although no weight image was ever late -- the fence waits for the copies that
+      // are still in flight for the following pairs, which serialises the ring.)  All token rows of the batch are requested
+      // at once: one L2 round trip per batch.
+      for (int b0 = 0; b0 < n_pairs; b0 += TC_STAGES) {
+        const int nb = n_pairs - b0 < TC_STAGES ? n_pairs - b0 : TC_STAGES;
+        if (b0 > 0) {   // the stages' previous users are this unit's previous batch
+          const long long ts0 = pf ? clock64() : 0;
+          for (int i = 0; i < nb; ++i) wait_stage(stage_of(b0 + i));
+          if (pf) prof[49] += clock64() - ts0;
+        }
+        for (int i = 0; i < nb; ++i) tc_issue_rows(a, n_chunks0, f_begin, f_end, b0 + i, astg + stage_of(b0 + i) * TC_ASTG, row_b, row_l, row_ok);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const long long ti1 = pf ? clock64() : 0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const long long ti2 = pf ? clock64() : 0;
+        __syncthreads();   // the batch's token rows have landed for every thread
+        if (pf && b0 == 0) { prof[56] += ti1 - t0; prof[57] += ti2 - ti1; }
+        if (pf && b0 == 0) { prof[27] += clock64() - t0; prof[26] += n_pairs; }
+        const long long tq0 = pf ? clock64() : 0;
+        for (int i = 0; i < nb; ++i) split_pair(b0 + i, stage_of(b0 + i));
+        const long long tq1 = pf ? clock64() : 0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (split) -> tensor core reads
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        const long long tq2 = pf ? clock64() : 0;
+        __syncthreads();
+        if (tid == 0 || tid == 32) {
+          const int which = tid == 32 ? 1 : 0;
+          const long long tq3 = pf ? clock64() : 0;
+          for (int i = 0; i < nb; ++i) full_wait(b0 + i, stage_of(b0 + i), which);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (pf) prof[48] += clock64() - tq3;
+          for (int i = 0; i < nb; ++i) mma_pair2(b0 + i, stage_of(b0 + i), which);
+          const long long tq4 = pf ? clock64() : 0;
+          if (pf) { prof[52] += tq1 - tq0; prof[53] += tq2 - tq1; prof[54] += tq3 - tq2; prof[55] += tq4 - tq3; }
+        }
+        for (int i = 0; i < nb; ++i) ph.stage[stage_of(b0 + i)] += 1u;
+      }
+    } else {
+    // (every MMA of the previous unit / op has completed: its `done` wait; stages 0 and 1 are free)
+    // Token rows are requested three pairs ahead; pair p + 3 reuses the stage of pair p - 1, whose MMAs were committed one
+    // iteration ago.
+    const bool w_pre = pre_issued && u == cta;   // local ring: the weights of pairs 0 and 1 were copied before the barrier
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      if (p < n_pairs) issue_pair(p, (w_pre && p < 2) ? 2 : 3);
       else asm volatile("cp.async.commit_group;" ::: "memory");
     }
     for (int p = 0; p < n_pairs; ++p) {
       const int s = stage_of(p);
-      if (p + 2 < n_pairs) {
-        wait_stage(stage_of(p + 2));   // read by the MMAs of pair p - 2 (issued one iteration ago at the latest)
-        issue_pair(p + 2, 3);
+      if (p + 3 < n_pairs) {
+        const long long ts0 = pf ? clock64() : 0;
+        wait_stage(stage_of(p + 3));   // read by the MMAs of pair p - 1 (issued one iteration ago)
+        if (pf) prof[49] += clock64() - ts0;
+        issue_pair(p + 3, 3);
       } else {
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      asm volatile("cp.async.wait_group 3;" ::: "memory");
       __syncthreads();   // pair p has landed for every thread
       if (pf && p == 0) { prof[27] += clock64() - t0; prof[26] += n_pairs; }
-      {   // split this pair's token rows: thread -> 8 consecutive channels (one 16-byte piece of halves) of one row
-        const int rr = tid >> 3, pc = tid & 7;
-        const int g = pc >> 2, kk0 = (pc & 3) * 8;
-        const float* src = astg + s * TC_ASTG + (g * CT + rr) * CT + kk0;
-        float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
-        if (g == 1 && !(f_begin + 2 * p + 1 < f_end)) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }   // odd chunk count
-        uint4 hi, lo;
-        split_f16x2(make_float2(x0.x, x0.y), hi.x, lo.x);
-        split_f16x2(make_float2(x0.z, x0.w), hi.y, lo.y);
-        split_f16x2(make_float2(x1.x, x1.y), hi.z, lo.z);
-        split_f16x2(make_float2(x1.z, x1.w), hi.w, lo.w);
-        uint8_t* at = a_tile(s);
-        const int off = rr * 128 + ((pc ^ (rr & 7)) << 4);
-        *reinterpret_cast<uint4*>(at + off) = hi;
-        *reinterpret_cast<uint4*>(at + CT * 128 + off) = lo;
-      }
+      split_pair(p, s);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (copies, split) -> tensor core reads
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
       if (tid == 0) {
-        if (tma) {   // this pair's weight image: issued by the stream long ago in the steady state
-          const uint32_t par = ((gp0 + (uint32_t)p) / TC_STAGES) & 1u;
-          uint32_t spins = 0;
-          wstream_pump(wc, jobs, ts, ops);
-          while (!tcw_mbar_test(&ts->full[s], par)) {
-            wstream_pump(wc, jobs, ts, ops);
-            if (++spins > (1u << 24)) { ok = false; break; }
-          }
-        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sw = tcw_smem_u32(w_tile(s)), sa = tcw_smem_u32(a_tile(s));
-        const uint64_t whi = tcw_desc(sw), wlo = tcw_desc(sw + TC_W_LO), ahi = tcw_desc(sa), alo = tcw_desc(sa + CT * 128);
-        const bool has2 = f_begin + 2 * p + 1 < f_end;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {   // 16 halves = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-          if (k >= 2 && !has2) break;    // odd chunk count: the second half of the K row is absent
-          const uint32_t acc = (p | k) != 0 ? 1u : 0u;
-          tcw_mma(tmem + CT, wlo + (uint64_t)(2 * k), ahi + (uint64_t)(2 * k), idesc, acc);
-          tcw_mma(tmem, whi + (uint64_t)(2 * k), ahi + (uint64_t)(2 * k), idesc, acc);
-          tcw_mma(tmem + CT, whi + (uint64_t)(2 * k), alo + (uint64_t)(2 * k), idesc, 1u);
-        }
-        tcw_commit(&ts->stage_free[s]);
-        if (p == n_pairs - 1) tcw_commit(&ts->done);
+        mma_pair(p, s);
       }
       ph.stage[s] += 1u;
+    }
     }
     ph.pairs += (uint32_t)n_pairs;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     ph.done += 1u;
-    if (!tcw_mbar_wait(&ts->done, (ph.done - 1u) & 1u)) ok = false;
+    const long long td0 = pf ? clock64() : 0;
+    // one thread polls the mbarrier, the others sleep at the CTA barrier (255 threads spinning on try_wait slowed the MMA
+    // issuer's own shared-memory operations down)
+    if (tid == 0 && !tcw_mbar_wait(&ts->done, (ph.done - 1u) & 1u)) ok = false;
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (pf) t1 = clock64();
+    if (pf) prof[50] += t1 - td0;
+    if (tma && tid == 128) wstream_pump(wc, ts, ops);   // the unit's stages are free: refill them while warps 0-3 read the accumulators
     float* mine = partials + ((size_t)tile * ks + crank) * (CT * WN);
     if (warp < 4) {
       uint32_t r1[32], r2[32];
-      tcw_ld32(tmem + ((uint32_t)(warp * 32) << 16), r1);
-      tcw_ld32(tmem + ((uint32_t)(warp * 32) << 16) + CT, r2);
+      {   // sum the two accumulator sets: r1 = W_hi A_hi, r2 = W_lo A_hi + W_hi A_lo (scaled by 4096)
+        const uint32_t row = tmem + ((uint32_t)(warp * 32) << 16);
+        uint32_t t[32];
+        tcw_ld32(row, r1);
+        tcw_ld32(row + 3 * CT, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(t[j]));
+        tcw_ld32(row + CT, r2);
+        tcw_ld32(row + 2 * CT, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r2[j] = __float_as_uint(__uint_as_float(r2[j]) + __uint_as_float(t[j]));
+        tcw_ld32(row + 4 * CT, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r2[j] = __float_as_uint(__uint_as_float(r2[j]) + __uint_as_float(t[j]));
+        tcw_ld32(row + 5 * CT, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r2[j] = __float_as_uint(__uint_as_float(r2[j]) + __uint_as_float(t[j]));
+      }
       const int n = n0 + warp * 32 + lane;
       if (ks == 1) {
         if (n < a.N) {
@@ -1982,35 +2142,38 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
   static_assert(sizeof(POp) <= 256 * sizeof(int), "descriptor must fit one word per thread");
   fetch_op(0, 0);
   __shared__ TcState tcs;
-  __shared__ WJob s_jobs[MODE == 1 ? WJOB_MAX : 1];
+  __shared__ WCursor s_wcur;   // weight-stream position: advanced by thread 0 (op start, grid barrier) and, inside a token
+                               // GEMM, by thread 128 (a warp that has no part in the accumulator read-out); CTA barriers separate them
   TcPhase tph{};
   const bool use_tc = MODE == 1 && pa.use_tc != 0;
   const bool use_tma = use_tc && pa.use_tma != 0;
-  WCursor wcur{};
-  if (use_tma) {
-    for (int i = tid; i < pa.n_wjobs * (int)(sizeof(WJob) / sizeof(int)); i += 256)
-      reinterpret_cast<int*>(s_jobs)[i] = reinterpret_cast<const int*>(pa.wjobs)[i];
-    wcur.n_jobs = pa.n_wjobs; wcur.cta = cta; wcur.G = G; wcur.u = cta; wcur.reps = pa.n_steps * pa.n_pass;
+  if (use_tma && tid == 0) {
+    WCursor c{};
+    c.n = pa.wl_count[cta];
+    c.list = pa.wlist + pa.wl_start[cta];
+    c.reps = c.n ? (uint32_t)(pa.n_steps * pa.n_pass) : 0u;
+    s_wcur = c;
   }
   // scratch of the attention / embedding ops: behind the weight ring when the stream owns the front of the shared memory
   float* const scr = use_tma ? reinterpret_cast<float*>(tc_ops(smem) + TCX_STG_OFF) : smem;
-  auto pump = [&]() { if (MODE == 1 && use_tma) wstream_pump(wcur, s_jobs, &tcs, tc_ops(smem)); };   // thread 0 only
+  auto pump = [&]() { if (MODE == 1 && use_tma) wstream_pump(s_wcur, &tcs, tc_ops(smem)); };   // thread 0 only
   if (use_tc) {   // tcgen05 path: mbarriers + 64 TMEM columns (two 128 x 32 fp32 accumulators), held for the whole run
     if (tid == 0) {
-      for (int i = 0; i < TC_STAGES; ++i) tcw_mbar_init(&tcs.stage_free[i], 1);
+      // weight-stream flow: two MMA-issuing threads commit to the stage / unit barriers
+      for (int i = 0; i < TC_STAGES; ++i) tcw_mbar_init(&tcs.stage_free[i], use_tma ? 2 : 1);
       for (int i = 0; i < TC_STAGES; ++i) tcw_mbar_init(&tcs.full[i], 1);
-      tcw_mbar_init(&tcs.done, 1);
+      tcw_mbar_init(&tcs.done, use_tma ? 2 : 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(tcw_smem_u32(&tcs.tmem_base)) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tcw_smem_u32(&tcs.tmem_base)) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (use_tc) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (use_tma && tid == 0) { wcursor_settle(wcur, s_jobs); pump(); }
+  if (use_tma && tid == 0) pump();
   int slot = 0;
   [&]() {   // the op loop; `return` leaves it early when the run is aborted (TMEM is released below in every case)
   for (int iter = 0; iter < pa.n_steps; ++iter) {
@@ -2100,7 +2263,7 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
           case P_CONV:
             if (MODE == 1 && o.wide == 2) {
               unsigned* bank = pa.sems + (size_t)(seq & 1u) * pa.sem_bank;
-              if (!p_conv_tc(o, smem, pa.partials, bank, pa.sync + 1, pre_issued, cta, G, pa.prof, &tcs, tph, use_tma, wcur, s_jobs)) {
+              if (!p_conv_tc(o, smem, pa.partials, bank, pa.sync + 1, pre_issued, cta, G, pa.prof, &tcs, tph, use_tma, s_wcur)) {
                 if (tid == 0) atomicExch(pa.sync + 1, 1u);   // a tensor-core wait timed out: abort the run (reported by surfd_unet_status)
               }
             } else if (MODE != 0 && o.wide) {
@@ -2193,7 +2356,7 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
   }();
   if (use_tc) {
     __syncthreads();
-    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tcs.tmem_base) : "memory");
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tcs.tmem_base) : "memory");
   }
 }
 
@@ -2233,8 +2396,8 @@ static_assert(8 * CONV_STAGES * 2 * CT * CTP >= 8 * CT * 33 + CT * CT, "reductio
 struct Lane {
   DevBuf pool, emb_all, temb, e1, emb, t_cur, x0a, x0b, xcur, state;
   // persistent sampler: op descriptors, K-slice scratch, semaphores, barrier word + abort flag
-  DevBuf emb_silu, ctxv, p_ops, p_partials, p_sems, p_sync, p_prof, p_wjobs, p_wstream;
-  int p_n_wjobs = 0, p_use_tma = 0;
+  DevBuf emb_silu, ctxv, p_ops, p_partials, p_sems, p_sync, p_prof, p_wlist, p_wlidx, p_wstream;
+  int p_use_tma = 0;
   int p_B = -1, p_n_emb = 0, p_n_prog = 0, p_smem = 0, p_grid = 0, p_split = -1, p_wide = -1, p_sem_bank = 0, p_use_tc = 0;
   const float* p_ctx = nullptr;
   const int64_t* p_lab = nullptr;
@@ -2259,7 +2422,7 @@ struct Lane {
     pool.release(); emb_all.release(); temb.release(); e1.release(); emb.release(); t_cur.release(); x0a.release(); x0b.release();
     xcur.release(); state.release();
     emb_silu.release(); ctxv.release(); p_ops.release(); p_partials.release(); p_sems.release(); p_sync.release(); p_prof.release();
-    p_wjobs.release(); p_wstream.release();
+    p_wlist.release(); p_wlidx.release(); p_wstream.release();
     p_B = -1;
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
@@ -2516,8 +2679,8 @@ extern "C" int surfd_unet_profile(surfd_unet* u, int on, int64_t* out) {
   SURFD_REQUIRE(u != nullptr, "null argument");
   if (!out) { u->profile = on != 0; return 0; }
   SURFD_CUDA(cudaDeviceSynchronize());
-  for (int i = 0; i < 48; ++i) out[i] = 0;
-  if (u->lanes[0].p_prof.p) SURFD_CUDA(cudaMemcpy(out, u->lanes[0].p_prof.p, 48 * sizeof(long long), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 64; ++i) out[i] = 0;
+  if (u->lanes[0].p_prof.p) SURFD_CUDA(cudaMemcpy(out, u->lanes[0].p_prof.p, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -2761,7 +2924,7 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
     }
   }
   // weight stream (tcgen05 units): packed 32 KB images per (op, output tile, K slice, chunk pair) + the job table
-  ln.p_use_tma = 0; ln.p_n_wjobs = 0;
+  ln.p_use_tma = 0;
   if (use_tc && !(dbg & (4 | 128))) {
     std::vector<WJob> jobs;
     std::vector<size_t> offs;
@@ -2784,7 +2947,7 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
       total += (size_t)o.tiles_n * o.ks * pairs_max * TCX_W_BYTES;
       jobs.push_back(j);
     }
-    if (all_tc && !jobs.empty() && (int)jobs.size() <= WJOB_MAX) {
+    if (all_tc && !jobs.empty()) {
       SURFD_TRY(ln.p_wstream.reserve(total));
       size_t ji = 0;
       for (const auto& o : ops) {
@@ -2799,9 +2962,28 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
         ++ji;
       }
       SURFD_CUDA(cudaDeviceSynchronize());
-      SURFD_TRY(ln.p_wjobs.reserve(jobs.size() * sizeof(WJob)));
-      SURFD_CUDA(cudaMemcpy(ln.p_wjobs.p, jobs.data(), jobs.size() * sizeof(WJob), cudaMemcpyHostToDevice));
-      ln.p_n_wjobs = (int)jobs.size();
+      // per-CTA image lists of one pass, in the order p_conv_tc consumes them: ops in program order, units u = cta, cta + grid,
+      // ..., pairs in order
+      std::vector<const uint8_t*> list;
+      std::vector<int> idx(2 * (size_t)grid);
+      for (int c = 0; c < grid; ++c) {
+        idx[(size_t)c] = (int)list.size();
+        for (const WJob& j : jobs) {
+          const int n_units = j.tiles_n * j.tiles_m * j.ks;
+          for (int uu = c; uu < n_units; uu += grid) {
+            const int crank = uu % j.ks, tn = (uu / j.ks) % j.tiles_n;
+            const int fb = (crank * j.n_chunks) / j.ks, fe = ((crank + 1) * j.n_chunks) / j.ks;
+            const int np = (fe - fb + 1) >> 1;
+            for (int pp = 0; pp < np; ++pp) list.push_back(j.base + ((size_t)(tn * j.ks + crank) * j.pairs_max + pp) * TCX_W_BYTES);
+          }
+        }
+        idx[(size_t)grid + c] = (int)list.size() - idx[(size_t)c];
+      }
+      if (list.empty()) list.push_back(nullptr);
+      SURFD_TRY(ln.p_wlist.reserve(list.size() * sizeof(void*)));
+      SURFD_TRY(ln.p_wlidx.reserve(idx.size() * sizeof(int)));
+      SURFD_CUDA(cudaMemcpy(ln.p_wlist.p, list.data(), list.size() * sizeof(void*), cudaMemcpyHostToDevice));
+      SURFD_CUDA(cudaMemcpy(ln.p_wlidx.p, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
       ln.p_use_tma = 1;
     }
   }
@@ -2813,7 +2995,7 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
   max_tiles = (max_tiles + 63) / 64 * 64;
   SURFD_TRY(ln.p_sems.reserve(3 * max_tiles * sizeof(unsigned)));
   SURFD_TRY(ln.p_sync.reserve(P_SYNC_WORDS * sizeof(unsigned)));
-  SURFD_TRY(ln.p_prof.reserve(48 * sizeof(long long)));
+  SURFD_TRY(ln.p_prof.reserve(64 * sizeof(long long)));
   ln.p_sem_bank = (int)max_tiles;
   ln.p_n_emb = n_emb; ln.p_n_prog = (int)ops.size() - n_emb; ln.p_smem = smem_floats * (int)sizeof(float);
   ln.p_wide = (int)wide + (int)use_tc;
@@ -2850,10 +3032,11 @@ static int sample_persistent(surfd_unet* u, int B, int n_steps, const int64_t* t
   pa.tmap = tmap_dev; pa.coef = coef_dev; pa.noise = noise_dev; pa.noise_stride = (long long)B * L; pa.guidance = guidance;
   pa.x = ln.xcur.as<float>(); pa.x0a = ln.x0a.as<float>();
   pa.partials = ln.p_partials.as<float>(); pa.sems = ln.p_sems.as<unsigned>(); pa.sem_bank = ln.p_sem_bank; pa.use_tc = ln.p_use_tc; pa.sync = ln.p_sync.as<unsigned>();
-  pa.wjobs = ln.p_wjobs.as<WJob>(); pa.n_wjobs = ln.p_n_wjobs; pa.use_tma = ln.p_use_tma;
+  pa.wlist = ln.p_wlist.as<const uint8_t*>(); pa.wl_start = ln.p_wlidx.as<int>(); pa.wl_count = ln.p_wlidx.as<int>() + grid;
+  pa.use_tma = ln.p_use_tma;
   pa.prof = nullptr;
   if (u->profile) {
-    SURFD_CUDA(cudaMemsetAsync(ln.p_prof.p, 0, 48 * sizeof(long long), st));
+    SURFD_CUDA(cudaMemsetAsync(ln.p_prof.p, 0, 64 * sizeof(long long), st));
     pa.prof = ln.p_prof.as<long long>();
   }
   if (u->precision == 0) SURFD_TRY(persist_launch<0>(pa, grid, ln.p_smem, st));

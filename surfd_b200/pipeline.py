@@ -5,6 +5,7 @@ Shapes are independent.  The decoder work (lattice, face filter) runs on the mai
 marching-cubes replay (a single-CTA, latency-bound kernel) runs on a side stream with its own workspace, so up to
 `mc_parallel` replays overlap with each other and with the next shapes' lattices.
 """
+import contextlib
 import time
 
 import torch
@@ -12,6 +13,16 @@ import torch
 from . import unet as U
 from .decoder import UdfDecoder
 from .meshudf import MarchingCubes, finish_mesh
+
+
+@contextlib.contextmanager
+def _nvtx(name):
+    """NVTX range around a stage (sample / lattice / mc / filter): shows up in Nsight timelines, free otherwise"""
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 class SurfDPipeline:
@@ -47,7 +58,8 @@ class SurfDPipeline:
         return self.schedule_cache[key]
 
     def sample_latents(self, noise, context=None, labels=None, guidance=1.0, n_steps=1000, noise_schedule="cosine"):
-        return self.sampler.sample(self.schedule(n_steps, noise_schedule), noise, context, labels, guidance)
+        with _nvtx("surfd.sample"):
+            return self.sampler.sample(self.schedule(n_steps, noise_schedule), noise, context, labels, guidance)
 
     def _launch_fields(self, wave, latents, N, use_fast_grid_filler, max_dist, marks):
         """lattice of every shape of `wave` on the current stream; each shape's marching cubes starts on its side stream
@@ -58,14 +70,16 @@ class SurfDPipeline:
         for j, k in enumerate(wave):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(main)
-            dec.set_latent(latents[k])
-            udf, grads, counts = dec.lattice(N, use_fast_grid_filler=use_fast_grid_filler, max_dist=max_dist)
-            udf.clamp_(min=0)                                    # udf[udf < 0] = 0  (meshudf.py:342)
+            with _nvtx("surfd.lattice"):
+                dec.set_latent(latents[k])
+                udf, grads, counts = dec.lattice(N, use_fast_grid_filler=use_fast_grid_filler, max_dist=max_dist)
+                udf.clamp_(min=0)                                # udf[udf < 0] = 0  (meshudf.py:342)
             e1.record(main)
             marks.append((e0, e1))
             fields[k] = (udf, grads, counts)
             self.streams[j].wait_event(e1)
-            self.mcs[j].launch(udf, grads, self.streams[j])
+            with _nvtx("surfd.mc.launch"):
+                self.mcs[j].launch(udf, grads, self.streams[j])
         return fields
 
     def _finish_fields(self, wave, latents, N, fields, meshes, stats, marks):
@@ -74,17 +88,28 @@ class SurfDPipeline:
         main = torch.cuda.current_stream(self.device)
         for j, k in enumerate(wave):
             udf, grads, counts = fields[k]
-            res = self.mcs[j].finish()
-            while res is None:                                   # buffers were grown: run this shape again
-                self.mcs[j].launch(udf, grads, self.streams[j])
+            try:
                 res = self.mcs[j].finish()
+                while res is None:                               # buffers were grown: run this shape again
+                    self.mcs[j].launch(udf, grads, self.streams[j])
+                    res = self.mcs[j].finish()
+            except Exception:
+                # e.g. "No surface found": the other replays of the wave are still in flight on their streams and read
+                # lattices this frame owns -- drain them before the error unwinds
+                for jj in range(j + 1, len(wave)):
+                    try:
+                        self.mcs[jj].finish()
+                    except Exception:
+                        pass
+                raise
             verts_raw, faces_raw = res
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(main)
-            vertices, faces = finish_mesh(verts_raw, faces_raw, N)
-            dec.set_latent(latents[k])
-            keep = dec.face_filter(vertices, faces, N)
-            faces_kept = faces[keep.bool()]
+            with _nvtx("surfd.filter"):
+                vertices, faces = finish_mesh(verts_raw, faces_raw, N)
+                dec.set_latent(latents[k])
+                keep = dec.face_filter(vertices, faces, N)
+                faces_kept = faces[keep.bool()]
             e1.record(main)
             marks.append((e0, e1, "f"))
             meshes[k] = (vertices.to(torch.float32), faces_kept.to(torch.int64))
