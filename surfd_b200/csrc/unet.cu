@@ -674,6 +674,7 @@ struct POp {
   float* out1;
   int i0, i1, i2, i3, i4, i5;
   float f0;
+  float inv_ks, inv_tn, inv_T; // P_CONV: 1 / ks, 1 / tiles_n, 1 / T_out (unit decoding without integer divisions, see div_small)
   int wide;                   // P_CONV: 1 = wide unit (32 x 128 tile, distributed slice reduction), 0 = narrow unit
   int defer;                  // P_CONV (wide, ks > 1): leave the K-slice partial tiles to the next op (no exchange inside this op)
   PartSrc ps;                 // P_GN / P_ATTN: the first input is a deferred token-GEMM output
@@ -1174,10 +1175,12 @@ __device__ __forceinline__ void p_conv_wide(const POp& o, float* smem, float* pa
   for (int u = cta; u < n_units; u += G) {
     long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     if (pf) t0 = clock64();
-    const int crank = u % ks, tile = u / ks;
-    const int tn = tile % o.tiles_n, tm = tile / o.tiles_n;
+    // unit -> (tile, slice) -> chunk range: integer divisions by run-time values cost a lone warp ~35 dependent instructions
+    // each (seven of them were 0.7 us at the head of every unit); the divisors' reciprocals come with the descriptor
+    const int tile = div_small(u, ks, o.inv_ks), crank = u - tile * ks;
+    const int tm = div_small(tile, o.tiles_n, o.inv_tn), tn = tile - tm * o.tiles_n;
     const int n0 = tn * WN, m0 = tm * CT;
-    const int f_begin = (crank * n_chunks) / ks, f_end = ((crank + 1) * n_chunks) / ks;
+    const int f_begin = div_small(crank * n_chunks, ks, o.inv_ks), f_end = div_small((crank + 1) * n_chunks, ks, o.inv_ks);
     const int n_pairs = (f_end - f_begin + 1) >> 1;
 
     auto issue_pair = [&](int pair, float* stg, int what) {
@@ -1617,12 +1620,12 @@ __device__ __forceinline__ void tc_issue(const ConvArgs& a, int n_chunks0, int f
 // carries a memory clobber: interleaved with the copies, each field was re-read from shared memory behind a dependent
 // address computation -- measured 1.3 us per unit for issuing 0.17 us worth of loads), the row -> (sample, token) division
 // is done once per unit by the caller, and the chunk -> (channel block, tap) division is by a constant.
-__device__ __forceinline__ void tc_issue_rows(const ConvArgs& a, int n_chunks0, int f_begin, int f_end, int pair, float* astg,
+struct SegRows { const float* A; const float* A2; int Cin, taps, stride, up, T_in, C1; };   // what the token-row copies need of a Seg
+__device__ __forceinline__ SegRows seg_rows(const Seg& g) { return SegRows{g.A, g.A2, g.Cin, g.taps, g.stride, g.up, g.T_in, g.C1}; }
+__device__ __forceinline__ void tc_issue_rows(const SegRows& s0, const SegRows& s1, int n_chunks0, int f_begin, int f_end, int pair, float* astg,
                                               int rb, int rl, bool rok) {
   const int tid = (int)threadIdx.x;
   const int lp = tid & 7, cr = tid >> 3;
-  const Seg s0 = a.seg[0];
-  const Seg s1 = a.seg[1];
   const float* src[2];
   int bytes[2];
 #pragma unroll
@@ -1701,16 +1704,18 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
   for (int u = cta; u < n_units; u += G) {
     long long t0 = 0, t1 = 0, t3 = 0;
     if (pf) t0 = clock64();
-    const int crank = u % ks, tile = u / ks;
-    const int tn = tile % o.tiles_n, tm = tile / o.tiles_n;
+    // unit -> (tile, slice) -> chunk range without integer divisions (see p_conv_wide)
+    const int tile = div_small(u, ks, o.inv_ks), crank = u - tile * ks;
+    const int tm = div_small(tile, o.tiles_n, o.inv_tn), tn = tile - tm * o.tiles_n;
     const int n0 = tn * WN, m0 = tm * CT;
-    const int f_begin = (crank * n_chunks) / ks, f_end = ((crank + 1) * n_chunks) / ks;
+    const int f_begin = div_small(crank * n_chunks, ks, o.inv_ks), f_end = div_small((crank + 1) * n_chunks, ks, o.inv_ks);
     const int n_pairs = (f_end - f_begin + 1) >> 1;
     // ring stage of the unit's pair: the weight stream numbers the pairs of the whole run, the local ring restarts per unit
     const uint32_t gp0 = tma ? ph.pairs : 0u;
     const int m_row = m0 + (tid >> 3);   // this thread's token row of the tile -> (sample, token)
     const bool row_ok = m_row < M;
-    const int row_b = m_row / a.T_out, row_l = m_row - row_b * a.T_out;
+    const int row_b = div_small(m_row, a.T_out, o.inv_T), row_l = m_row - row_b * a.T_out;
+    const SegRows sr0 = seg_rows(a.seg[0]), sr1 = seg_rows(a.seg[1]);   // into registers once per unit (see tc_issue_rows)
     auto stage_of = [&](int pair) { return (int)((gp0 + (uint32_t)pair) & (TC_STAGES - 1)); };
     auto issue_pair = [&](int pair, int what) {
       const int s = stage_of(pair);
@@ -1806,8 +1811,9 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
           const long long ts0 = pf ? clock64() : 0;
           for (int i = 0; i < nb; ++i) wait_stage(stage_of(b0 + i));
           if (pf) prof[49] += clock64() - ts0;
+          if (tid == 128) wstream_pump(wc, ts, ops);   // the previous batch's stages are free: request this batch's images now
         }
-        for (int i = 0; i < nb; ++i) tc_issue_rows(a, n_chunks0, f_begin, f_end, b0 + i, astg + stage_of(b0 + i) * TC_ASTG, row_b, row_l, row_ok);
+        for (int i = 0; i < nb; ++i) tc_issue_rows(sr0, sr1, n_chunks0, f_begin, f_end, b0 + i, astg + stage_of(b0 + i) * TC_ASTG, row_b, row_l, row_ok);
         asm volatile("cp.async.commit_group;" ::: "memory");
         const long long ti1 = pf ? clock64() : 0;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1825,7 +1831,13 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
         if (tid == 0 || tid == 32) {
           const int which = tid == 32 ? 1 : 0;
           const long long tq3 = pf ? clock64() : 0;
-          for (int i = 0; i < nb; ++i) full_wait(b0 + i, stage_of(b0 + i), which);
+          {   // the batch's weight images: the tests are independent (their latencies overlap); waiting is the rare path
+            uint32_t landed = 1u;
+            for (int i = 0; i < nb; ++i)
+              landed &= tcw_mbar_test(&ts->full[stage_of(b0 + i)], ((gp0 + (uint32_t)(b0 + i)) / TC_STAGES) & 1u) ? 1u : 0u;
+            if (!landed)
+              for (int i = 0; i < nb; ++i) full_wait(b0 + i, stage_of(b0 + i), which);
+          }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (pf) prof[48] += clock64() - tq3;
           for (int i = 0; i < nb; ++i) mma_pair2(b0 + i, stage_of(b0 + i), which);
@@ -2810,6 +2822,7 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
           if (ksplit > P_MAX_KS_WIDE) ksplit = P_MAX_KS_WIDE;
           if (ksplit < 1) ksplit = 1;
           o.ks = ksplit;
+          o.inv_ks = 1.0f / (float)o.ks; o.inv_tn = 1.0f / (float)o.tiles_n; o.inv_T = 1.0f / (float)a.T_out;
           if (nt > max_tiles) max_tiles = nt;
           if (ksplit > 1 && nt * ksplit * (WN / CT) > max_partial_tiles) max_partial_tiles = nt * ksplit * (WN / CT);
           ops.push_back(o);
