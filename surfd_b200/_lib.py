@@ -26,6 +26,7 @@ PROTOTYPES = {
     "surfd_dec_set_latent": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "surfd_dec_set_precision": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "surfd_dec_set_sm_budget": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "surfd_dec_set_chain": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "surfd_dec_num_sms": (ctypes.c_int, [c_vp]),
     "surfd_dec_chunk_points": (ctypes.c_int, [c_vp]),
     "surfd_dec_profile": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(ctypes.c_double)]),

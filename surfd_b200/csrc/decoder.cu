@@ -424,6 +424,9 @@ struct surfd_decoder {
   DevBuf wT;         // transposes: WpT [64][512], then 5x{W0T, W1T}
   DevBuf wR;         // TF32-rounded (rna) copies for the tensor-core path: 5x{W0, W1}, then 5x{W0T, W1T}
   DevBuf err;        // int error flag written by the tcgen05 kernel's bounded waits
+  DevBuf gsync;      // grid-barrier word of the layer-chain kernel
+  int chain = 0;     // TF32 mode: 1 = all 512x512 layers of a pass in one cooperative launch (tc_chain_kernel), 0 = one launch per
+                     // layer (default: measured faster -- the epilogue, not HBM, bounds a tile; profiles/README.md)
   DevBuf vflag;      // face filter: per-vertex "udf > 1/N" flags
   bool profiling = false;             // surfd_dec_profile: event pair around every 512x512 layer GEMM
   std::vector<cudaEvent_t> prof_events;
@@ -518,6 +521,7 @@ extern "C" int surfd_dec_create(const float* packed, size_t n_floats, int L, int
   if ((st = d->wR.reserve((size_t)4 * NBLK * HID * HID * sizeof(float)))) return fail(st);
   if ((st = d->err.reserve(sizeof(int)))) return fail(st);
   cudaMemset(d->err.p, 0, sizeof(int));
+  if ((st = d->gsync.reserve(64))) return fail(st);
   {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -552,7 +556,7 @@ extern "C" int surfd_dec_create(const float* packed, size_t n_floats, int L, int
 
 extern "C" void surfd_dec_destroy(surfd_decoder* d) {
   if (!d) return;
-  d->wR.release(); d->err.release(); d->vflag.release();
+  d->wR.release(); d->err.release(); d->gsync.release(); d->vflag.release();
   for (cudaEvent_t ev : d->prof_events) cudaEventDestroy(ev);
   d->prof_events.clear();
   d->weights.release(); d->wT.release(); d->fold.release(); d->acts.release(); d->net.release(); d->dnet.release();
@@ -629,6 +633,14 @@ extern "C" int surfd_dec_set_sm_budget(surfd_decoder* d, int n_sms) {
 }
 extern "C" int surfd_dec_num_sms(surfd_decoder* d) { return d ? d->num_sms : 0; }
 
+// TF32 mode: 1 = the ten 512x512 layers of a pass run in one cooperative launch with the chunk's activations resident in L2
+// (tc_chain_kernel); 0 (default) = one launch per layer (tc_gemm_kernel).  Same arithmetic, bit-identical results.
+extern "C" int surfd_dec_set_chain(surfd_decoder* d, int on) {
+  SURFD_REQUIRE(d != nullptr, "null decoder");
+  d->chain = on ? 1 : 0;
+  return 0;
+}
+
 extern "C" int surfd_dec_set_latent(surfd_decoder* d, const float* lat_dev, void* stream) {
   SURFD_REQUIRE(d != nullptr && lat_dev != nullptr, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -636,6 +648,34 @@ extern "C" int surfd_dec_set_latent(surfd_decoder* d, const float* lat_dev, void
   fold_cbn_kernel<<<dim3(HID / 128, NCBN), 128, 0, st>>>(d->cbn(), d->L, lat_dev, s, s + NCBN * HID);
   SURFD_CHECK_LAUNCH();
   d->latent_set = true;
+  return 0;
+}
+
+// n consecutive 512x512 layers over the same M rows: one cooperative launch in TF32 mode (tc_chain_kernel), else one GEMM
+// launch per layer.
+static int layer_chain(surfd_decoder* d, const float* const* A, const float* const* W, const float* const* Wr, const Epilogue* e, int n,
+                       int M, cudaStream_t st) {
+  if (d->precision == 1 && d->chain) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (d->profiling) {
+      if (d->prof_used + 2 > d->prof_events.size()) {
+        for (int i = 0; i < 2; ++i) {
+          cudaEvent_t ev;
+          SURFD_CUDA(cudaEventCreate(&ev));
+          d->prof_events.push_back(ev);
+        }
+      }
+      e0 = d->prof_events[d->prof_used]; e1 = d->prof_events[d->prof_used + 1];
+      d->prof_used += 2;
+      d->prof_points += (int64_t)n * M;   // point-layers: FLOPs = 2 * 512 * 512 each
+      SURFD_CUDA(cudaEventRecord(e0, st));
+    }
+    const int sms = d->sm_budget > 0 && d->sm_budget < d->num_sms ? d->sm_budget : d->num_sms;
+    const int rc = launch_chain_tc(A, Wr, e, n, M, d->gsync.as<unsigned>(), d->err.as<int>(), sms, st);
+    if (e1) SURFD_CUDA(cudaEventRecord(e1, st));
+    return rc;
+  }
+  for (int i = 0; i < n; ++i) SURFD_TRY(gemm512(d, A[i], W[i], Wr[i], M, e[i], st));
   return 0;
 }
 
@@ -654,17 +694,22 @@ static int dec_forward(surfd_decoder* d, int M, bool keep_acts, float* udf_out, 
   // net = fc_p(E);  act0 = relu(cbn_0(net))   (K = 64: always the fp32 FFMA kernel, the positional encoding stays exact)
   e.bias = d->bp(); e.C = net; e.act = A(0); e.s2 = d->s(0); e.t2 = d->t(0); e.round_act = tcm;
   SURFD_TRY(launch_gemm(E, ENC, d->Wp(), ENC, M, HID, ENC, e, st));
+  Epilogue ep[2 * NBLK];
+  const float* Ain[2 * NBLK];
+  const float* Wf[2 * NBLK];
+  const float* Wr[2 * NBLK];
   for (int i = 0; i < NBLK; ++i) {
     // h = fc_0(act);  act' = relu(cbn_1(h))
     Epilogue e0{};
     e0.ld = HID; e0.bias = d->b0(i); e0.act = A(2 * i + 1); e0.s2 = d->s(2 * i + 1); e0.t2 = d->t(2 * i + 1); e0.round_act = tcm;
-    SURFD_TRY(gemm512(d, A(2 * i), d->W0(i), d->W0r(i), M, e0, st));
+    ep[2 * i] = e0; Ain[2 * i] = A(2 * i); Wf[2 * i] = d->W0(i); Wr[2 * i] = d->W0r(i);
     // net += fc_1(act');  act'' = relu(cbn_next(net))
     Epilogue e1{};
     e1.ld = HID; e1.bias = d->b1(i); e1.R = net; e1.C = net; e1.act = A(2 * i + 2); e1.s2 = d->s(2 * i + 2); e1.t2 = d->t(2 * i + 2);
     e1.round_act = (tcm && i < NBLK - 1) ? 1 : 0;   // the last activation feeds the fp32 fc_out reduction only
-    SURFD_TRY(gemm512(d, A(2 * i + 1), d->W1(i), d->W1r(i), M, e1, st));
+    ep[2 * i + 1] = e1; Ain[2 * i + 1] = A(2 * i + 1); Wf[2 * i + 1] = d->W1(i); Wr[2 * i + 1] = d->W1r(i);
   }
+  SURFD_TRY(layer_chain(d, Ain, Wf, Wr, ep, 2 * NBLK, M, st));
   out_kernel<<<(unsigned)cdiv((int64_t)M * 32, 256), 256, 0, st>>>(A(10), M, d->wout(), d->bout(), udf_out, dst,
                                                                   keep_acts ? d->dudf.as<float>() : nullptr, logit_out);
   SURFD_CHECK_LAUNCH();
@@ -678,16 +723,21 @@ static int dec_backward(surfd_decoder* d, int M, float* grad_out, const int32_t*
   const int64_t total = (int64_t)M * HID;
   bwd_init_kernel<<<(unsigned)cdiv(total / 4, 256), 256, 0, st>>>(d->act(10), total, d->wout(), d->s(10), dnet);
   SURFD_CHECK_LAUNCH();
-  for (int i = NBLK - 1; i >= 0; --i) {
+  Epilogue ep[2 * NBLK];
+  const float* Ain[2 * NBLK];
+  const float* Wf[2 * NBLK];
+  const float* Wr[2 * NBLK];
+  for (int i = NBLK - 1, k = 0; i >= 0; --i, k += 2) {
     // dh = (dnet * W1) (.) relu'(act_{2i+1}) (.) s_{2i+1}
     Epilogue e1{};
     e1.ld = HID; e1.mask = d->act(2 * i + 1); e1.mscale = d->s(2 * i + 1); e1.C = dh; e1.round_c = d->precision == 1 ? 1 : 0;
-    SURFD_TRY(gemm512(d, dnet, d->W1T(i), d->W1Tr(i), M, e1, st));
+    ep[k] = e1; Ain[k] = dnet; Wf[k] = d->W1T(i); Wr[k] = d->W1Tr(i);
     // dnet += (dh * W0) (.) relu'(act_{2i}) (.) s_{2i}
     Epilogue e0{};
     e0.ld = HID; e0.mask = d->act(2 * i); e0.mscale = d->s(2 * i); e0.R = dnet; e0.C = dnet;
-    SURFD_TRY(gemm512(d, dh, d->W0T(i), d->W0Tr(i), M, e0, st));
+    ep[k + 1] = e0; Ain[k + 1] = dh; Wf[k + 1] = d->W0T(i); Wr[k + 1] = d->W0Tr(i);
   }
+  SURFD_TRY(layer_chain(d, Ain, Wf, Wr, ep, 2 * NBLK, M, st));
   Epilogue ee{};
   ee.ld = ENC; ee.C = d->de.as<float>();
   SURFD_TRY(launch_gemm(dnet, HID, d->WpT(), HID, M, ENC, HID, ee, st));

@@ -33,4 +33,9 @@ __device__ __forceinline__ float round_to_tf32(float x) {
 // decoder_tc.cu: A [M][512], W [512][512] (both K contiguous), persistent tcgen05 kernel
 int launch_gemm_tc(const float* A, const float* W, int M, const Epilogue& e, int* err_flag, int num_sms, cudaStream_t st);
 
+// decoder_tc.cu: n consecutive layers over the same rows in ONE cooperative launch (grid barrier between layers; the chunk's
+// activations stay in L2).  gsync: one device word, zeroed by the call.
+int launch_chain_tc(const float* const* A, const float* const* W, const Epilogue* e, int n, int M, unsigned* gsync, int* err_flag,
+                    int num_sms, cudaStream_t st);
+
 }  // namespace surfd

@@ -111,7 +111,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, Epilogue e, int* err) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (not through an integer cast): the compiler keeps the
+  // shared address space and the epilogue's staging accesses compile to LDS / STS instead of generic LD / ST (ncu r2: the
+  // generic loads were the top stall of the epilogue warps)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
@@ -267,6 +270,203 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ---- the layer chain in one launch ---------------------------------------------------------------------------------
+// The per-layer launches move every activation tensor through HBM (chunks of >= 100k points are needed to amortise a launch:
+// 220 MB per tensor, L2 holds 126 MB), and that traffic -- not the tensor pipe -- bounds the chain (r1: 36 % of the TF32
+// peak, DRAM 19-33 %, epilogue warps waiting on HBM).  tc_chain_kernel runs ALL the 512x512 layers of a pass over a small
+// chunk (2 tiles per CTA and layer) in one cooperative launch: same roles and pipelines as tc_gemm_kernel, a grid barrier
+// between layers, tensor maps and epilogues of the layers in the kernel parameters.  The chunk's activation tensors
+// (3 x 37 MB forward) stay in L2 from the epilogue that writes them to the TMA load that reads them.
+struct alignas(64) ChainLayer {
+  CUtensorMap tmA;   // this layer's input activations [M][512]
+  CUtensorMap tmB;   // its weights [512][512]
+  Epilogue e;
+};
+constexpr int CHAIN_MAX_LAYERS = 10;
+struct ChainProg {
+  ChainLayer layer[CHAIN_MAX_LAYERS];
+};
+static_assert(sizeof(ChainProg) <= 3968, "the program travels in the kernel parameters");
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_chain_kernel(const __grid_constant__ ChainProg prog, int n_layers, int M, unsigned* gsync, int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (not through an integer cast): the compiler keeps the
+  // shared address space and the epilogue's staging accesses compile to LDS / STS instead of generic LD / ST (ncu r2: the
+  // generic loads were the top stall of the epilogue warps)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = 2 * m_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pipeline positions: each role advances its own copies, all roles see the same sequence of tiles and k-blocks
+  int stage = 0; uint32_t phase = 0;
+  int acc = 0; uint32_t acc_phase = 0;
+  unsigned target = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const ChainLayer& L = prog.layer[l];
+    if (warp == 0) {
+      // ===== TMA producer =====
+      if (lane == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");   // the previous layer's activations were written with generic stores
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+          const int m0 = (tile >> 1) * BM, n0 = (tile & 1) * BN;
+          for (int kb = 0; kb < KBLOCKS; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1, err, 1);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            mbar_expect_tx(&full[stage], STAGE_BYTES);
+            tma_load_2d(&L.tmA, &full[stage], sa, kb * BK, m0);
+            tma_load_2d(&L.tmB, &full[stage], sa + A_BYTES, kb * BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===== MMA issuer =====
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc();
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+          mbar_wait(&tempty[acc], acc_phase ^ 1, err, 2);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < KBLOCKS; ++kb) {
+            mbar_wait(&full[stage], phase, err, 3);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t adesc = umma_desc(sa), bdesc = umma_desc(sa + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k)
+              umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[stage]);
+            if (kb == KBLOCKS - 1) umma_commit(&tfull[acc]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    } else {
+      // ===== epilogue warps 2..5 (see tc_gemm_kernel) =====
+      const Epilogue& e = L.e;
+      const int quad = warp & 3;
+      float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * STG_LD);
+      const int srow = lane >> 3, scol = (lane & 7) * 4;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile >> 1) * BM, n0 = (tile & 1) * BN;
+        mbar_wait(&tfull[acc], acc_phase, err, 4);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float4 rq[8], mk[8];
+          {
+            const int nn = n0 + c * 32 + scol;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int m = m0 + quad * 32 + it * 4 + srow;
+              const size_t off = (size_t)(m < M ? m : M - 1) * e.ld + nn;
+              if (e.R) rq[it] = *reinterpret_cast<const float4*>(e.R + off);
+              if (e.mask) mk[it] = *reinterpret_cast<const float4*>(e.mask + off);
+            }
+          }
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * q) =
+                make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+          __syncwarp();
+          const int n = n0 + c * 32 + scol;
+          float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), ms = bias, s2 = bias, t2 = bias;
+          if (e.bias) bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+          if (e.mask) ms = __ldg(reinterpret_cast<const float4*>(e.mscale + n));
+          if (e.act) { s2 = __ldg(reinterpret_cast<const float4*>(e.s2 + n)); t2 = __ldg(reinterpret_cast<const float4*>(e.t2 + n)); }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + srow;
+            const int m = m0 + quad * 32 + rr;
+            if (m >= M) continue;
+            float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + scol);
+            const size_t off = (size_t)m * e.ld + n;
+            v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+            if (e.mask) {
+              const float4 k4 = mk[it];
+              v.x = k4.x > 0.f ? v.x * ms.x : 0.f; v.y = k4.y > 0.f ? v.y * ms.y : 0.f;
+              v.z = k4.z > 0.f ? v.z * ms.z : 0.f; v.w = k4.w > 0.f ? v.w * ms.w : 0.f;
+            }
+            if (e.R) { const float4 q4 = rq[it]; v.x += q4.x; v.y += q4.y; v.z += q4.z; v.w += q4.w; }
+            if (e.C) {
+              float4 o = v;
+              if (e.round_c) { o.x = round_to_tf32(o.x); o.y = round_to_tf32(o.y); o.z = round_to_tf32(o.z); o.w = round_to_tf32(o.w); }
+              *reinterpret_cast<float4*>(e.C + off) = o;
+            }
+            if (e.act) {
+              float4 a;
+              a.x = fmaxf(fmaf(s2.x, v.x, t2.x), 0.f); a.y = fmaxf(fmaf(s2.y, v.y, t2.y), 0.f);
+              a.z = fmaxf(fmaf(s2.z, v.z, t2.z), 0.f); a.w = fmaxf(fmaf(s2.w, v.w, t2.w), 0.f);
+              if (e.round_act) { a.x = round_to_tf32(a.x); a.y = round_to_tf32(a.y); a.z = round_to_tf32(a.z); a.w = round_to_tf32(a.w); }
+              *reinterpret_cast<float4*>(e.act + off) = a;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      // this layer's activations go to the next layer's TMA loads (async proxy), possibly on another SM
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    if (l + 1 < n_layers) {
+      // grid barrier: every CTA's tiles of this layer are complete and visible
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(gsync), "r"(1u) : "memory");
+        uint32_t spins = 0;
+        for (;;) {
+          unsigned v;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gsync) : "memory");
+          if ((int)(v - target) >= 0) break;
+          if (++spins > SPIN_LIMIT) {
+            if (err) *err = 5;
+            __threadfence_system();
+            asm volatile("trap;");
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -298,6 +498,31 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int box_r
 }
 
 }  // namespace tc
+
+// One cooperative launch for `n` consecutive 512x512 layers over the same M rows (A[i] -> epilogue e[i]); gsync: a zeroed word.
+int launch_chain_tc(const float* const* A, const float* const* W, const Epilogue* e, int n, int M, unsigned* gsync, int* err_flag,
+                    int num_sms, cudaStream_t st) {
+  SURFD_REQUIRE(n >= 1 && n <= tc::CHAIN_MAX_LAYERS, "bad layer count");
+  static bool attr_set = false;
+  if (!attr_set) {
+    SURFD_CUDA(cudaFuncSetAttribute(tc::tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    attr_set = true;
+  }
+  static tc::ChainProg prog;   // (host staging for the by-value kernel parameter; the launch copies it)
+  for (int i = 0; i < n; ++i) {
+    SURFD_TRY(tc::make_map(&prog.layer[i].tmA, A[i], M, tc::BM));
+    SURFD_TRY(tc::make_map(&prog.layer[i].tmB, W[i], 512, tc::BN));
+    prog.layer[i].e = e[i];
+  }
+  const int tiles = 2 * (int)cdiv(M, tc::BM);
+  int grid = tiles < num_sms ? tiles : num_sms;
+  SURFD_CUDA(cudaMemsetAsync(gsync, 0, sizeof(unsigned), st));
+  int n_layers = n, m = M;
+  void* args[] = {&prog, &n_layers, &m, &gsync, &err_flag};
+  SURFD_CUDA(cudaLaunchCooperativeKernel((void*)tc::tc_chain_kernel, dim3((unsigned)grid), dim3(tc::THREADS), args, (size_t)tc::SMEM_BYTES, st));
+  g_launch_count += 1;
+  return 0;
+}
 
 int launch_gemm_tc(const float* A, const float* W, int M, const Epilogue& e, int* err_flag, int num_sms, cudaStream_t st) {
   static bool attr_set = false;

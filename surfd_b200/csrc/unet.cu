@@ -1344,7 +1344,8 @@ __device__ __forceinline__ void p_conv_wide(const POp& o, float* smem, float* pa
 
 // value of element (m, c) of a deferred token-GEMM output: slices summed in slice order, then + bias (+ emb) (+ residual) --
 // the same order of additions as the in-op epilogue of p_conv_wide.  All loads are requested together.
-__device__ __forceinline__ float part_value(const PartSrc& ps, int T, int m, int c) {
+// b = m / T when the caller knows it (the division by a run-time T costs ~35 dependent instructions per element), else -1
+__device__ __forceinline__ float part_value(const PartSrc& ps, int T, int m, int c, int b = -1) {
   const float* base = ps.part + ((size_t)((m >> 5) * ps.tiles_n + (c >> 7)) * ps.ks) * (CT * WN) + (m & 31) * WN + (c & (WN - 1));
   float pv[P_MAX_KS_WIDE];
 #pragma unroll
@@ -1358,7 +1359,7 @@ __device__ __forceinline__ float part_value(const PartSrc& ps, int T, int m, int
     }
   }
   const float bv = ps.bias[c];
-  const float ev = ps.emb ? ps.emb[(size_t)(m / T) * ps.emb_ld + c] : 0.f;
+  const float ev = ps.emb ? ps.emb[(size_t)(b >= 0 ? b : m / T) * ps.emb_ld + c] : 0.f;
   const float rv = ps.res ? ps.res[(size_t)m * ps.N + c] : 0.f;
   float v = 0.f;
 #pragma unroll
@@ -1399,7 +1400,8 @@ constexpr int TCX_A_OFF = TC_STAGES * TCX_W_BYTES;
 constexpr int TCX_STG_OFF = TCX_A_OFF + TC_STAGES * TCX_A_BYTES;
 static_assert(TCX_STG_OFF + TC_STAGES * TC_ASTG * 4 + 1024 == TC_SMEM, "both layouts use the same dynamic shared memory");
 __device__ __forceinline__ uint8_t* tc_ops(float* smem) {   // operand ring: first 1024-byte boundary of the dynamic shared memory
-  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the __shared__ array, not an integer cast: keeps the shared address space -> LDS / STS, not generic LD / ST)
+  return reinterpret_cast<uint8_t*>(smem) + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem) & 1023u)) & 1023u);
 }
 __device__ __forceinline__ float* tc_astage(float* smem) { return reinterpret_cast<float*>(tc_ops(smem) + TC_STAGES * TC_OP_BYTES); }
 
@@ -1995,11 +1997,12 @@ __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, 
   const int C = C1 + C2;
   const int cg = C / 32;
   const int n = T * cg;
-  const bool deferred = o.ps.ks > 0;
+  const PartSrc ps = o.ps;   // into registers: the descriptor lives in shared memory and the barriers below carry memory clobbers
+  const bool deferred = ps.ks > 0;
   float* fin = const_cast<float*>(o.in0);   // a deferred first input is finalised in place for its later consumers
   auto load = [&](int idx) -> float {
     const int t = idx / cg, c = g * cg + idx % cg;
-    if (deferred && c < C1) return part_value(o.ps, T, b * T + t, c);
+    if (deferred && c < C1) return part_value(ps, T, b * T + t, c, b);
     return c < C1 ? in1[((size_t)b * T + t) * C1 + c] : in2[((size_t)b * T + t) * C2 + (c - C1)];
   };
   auto block_sum = [&](float v) -> float {
@@ -2017,7 +2020,7 @@ __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, 
   int tt[PGN_CACHE], cc[PGN_CACHE];   // (token, channel) of the cached elements, computed once (the unit is issue-bound on index math)
   const float inv_cg = 1.0f / (float)cg;
   auto load_tc = [&](int t, int c) -> float {
-    if (deferred && c < C1) return part_value(o.ps, T, b * T + t, c);
+    if (deferred && c < C1) return part_value(ps, T, b * T + t, c, b);
     return c < C1 ? in1[((size_t)b * T + t) * C1 + c] : in2[((size_t)b * T + t) * C2 + (c - C1)];
   };
 #pragma unroll
@@ -3066,12 +3069,13 @@ extern "C" int surfd_sample(surfd_unet* u, int B, int n_steps, const int64_t* tm
   SURFD_REQUIRE(B >= 1 && B <= u->max_batch, "batch exceeds max_batch");
   SURFD_REQUIRE(n_steps >= 1, "n_steps must be positive");
   cudaStream_t st = (cudaStream_t)stream;
-  // The persistent engine runs in the range it has been verified on hardware: batches of at most PERSIST_MAX_BATCH samples and
-  // (wide units) at least PERSIST_MIN_GRID CTAs, so that every token GEMM is a single round of co-resident units.  A test with
-  // batches of 12 / 40 samples (several rounds of units per op) did not finish at the very end of round 1 and could not be
-  // analysed any more; larger batches therefore take the CUDA-graph engine (same results at fp32 rounding level, slower).
+  // The persistent engine is used for batches of at most PERSIST_MAX_BATCH samples per call and (wide units) at least
+  // PERSIST_MIN_GRID CTAs.  Above 8 samples a token GEMM has more units than resident CTAs (several rounds per op): verified on
+  // hardware up to 64 samples per call, both latent sizes, against the graph engine (tests/test_gpu_unet.py large_batches,
+  // tools/probe_large_batch.py; the round-1 report of an unfinished 12 / 40-sample run did not reproduce in three separate
+  // sessions, nor under compute-sanitizer -- profiles/r2_sanitizer.md).  Larger batches take the CUDA-graph engine.
   constexpr int PERSIST_MIN_GRID = 100;
-  int PERSIST_MAX_BATCH = 8;
+  int PERSIST_MAX_BATCH = 64;
   if (const char* e = getenv("SURFD_PERSIST_MAX_BATCH")) PERSIST_MAX_BATCH = atoi(e);   // diagnostics
   if (u->sampler == 1 && u->coop && B <= PERSIST_MAX_BATCH) {
     int grid = u->sampler_sms > 0 ? u->sampler_sms : u->num_sms;

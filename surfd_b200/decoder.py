@@ -102,6 +102,12 @@ class UdfDecoder:
     def set_precision(self, mode):
         _lib.check(self.lib.surfd_dec_set_precision(self._h, int(mode)))
 
+    def set_chain(self, on):
+        """TF32 mode: True = the ten 512x512 layers of a pass in ONE cooperative launch (tc_chain_kernel: grid barrier between
+        layers, the chunk's activations stay in L2); False (default: measured faster, profiles/README.md) = one launch per
+        layer.  Bit-identical results."""
+        _lib.check(self.lib.surfd_dec_set_chain(self._h, 1 if on else 0))
+
     def set_sm_budget(self, n_sms):
         """CTAs of the persistent tensor-core GEMM (0 = all SMs); see surfd_dec_set_sm_budget"""
         _lib.check(self.lib.surfd_dec_set_sm_budget(self._h, int(n_sms)))

@@ -123,6 +123,31 @@ def test_persistent_sampler_is_bit_identical_to_graph_replay(case):
         net.set_sampler(0)
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("L,cond", [(32, "no_cond"), (64, "img")], ids=["uncond32", "img64"])
+def test_persistent_sampler_large_batches(L, cond):
+    """More samples per call than one round of units covers (B > 8: a token GEMM has more units than resident CTAs): the
+    persistent engine -- default wide units with the weight stream, and the graph-identical units -- against the graph
+    engine.  (re-added; every wait in the kernel is bounded, a protocol error aborts the run and
+    status() raises.)"""
+    gen = torch.Generator().manual_seed(3)
+    S = U.SpacedSchedule(U.cosine_betas(), U.space_timesteps(1000, [6]))
+    sd = synth.synth_mdm(L, cond)
+    for B in (12, 40):
+        net = U.UNetSampler(sd, L, cond, max_batch=B)
+        noise = torch.randn(7, B, L, generator=gen)
+        ctx = torch.randn(B, 512, generator=gen) if cond == "img" else None
+        net.set_sampler(0)
+        ref = net.sample(S, noise, ctx)
+        for mode, n_sms, tol in ((2, 0, 0.0), (1, 0, 2e-4), (1, 140, 2e-4)):
+            net.set_sampler(mode, n_sms)
+            out = net.sample(S, noise, ctx)
+            torch.cuda.synchronize(); net.status()
+            err = float((out - ref).abs().max())
+            assert torch.isfinite(out).all() and err <= tol, (B, mode, n_sms, err)
+        del net
+
+
 @pytest.mark.parametrize("mode", [0, 2], ids=["fp32-ffma", "tf32-mma"])
 def test_persistent_sampler_precision_modes(mode):
     L = 32

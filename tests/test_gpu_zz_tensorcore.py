@@ -94,3 +94,19 @@ def test_tf32_poly_lattice_and_mesh_match_fp32_topology():
     sel = (g0.abs().sum(-1) > 0) & (g1.abs().sum(-1) > 0)
     d = (g0[sel] - g1[sel]).abs().max(-1).values
     assert float(d.median()) < 1e-3 and float(d.quantile(0.99)) < 5e-2, (float(d.median()), float(d.quantile(0.99)))
+
+
+def test_layer_chain_kernel_is_bit_identical_to_per_layer_launches():
+    """tc_chain_kernel (all ten 512x512 layers of a pass in one cooperative launch, grid barrier between layers, optional
+    path: set_chain) performs the same MMAs and epilogues in the same order as ten tc_gemm_kernel launches."""
+    L = 32
+    sd = synth.synth_ae_rand(L, 4321)["decoder"]
+    gen = torch.Generator().manual_seed(5)
+    lat = torch.randn(L, generator=gen)
+    a = UdfDecoder(sd, L, max_chunk_points=140 * 256); a.set_precision(1); a.set_latent(lat)
+    b = UdfDecoder(sd, L, max_chunk_points=140 * 256); b.set_precision(1); b.set_chain(True); b.set_latent(lat)
+    for m in (1, 129, 5000, 35840, 80001):                 # partial tile, fewer tiles than CTAs, exactly one chunk, 3 chunks
+        pts = torch.rand(m, 3, generator=gen) * 2 - 1
+        ua, ga = a.query(pts, want_grad=True)
+        ub, gb = b.query(pts, want_grad=True)
+        assert torch.equal(ua, ub) and torch.equal(ga, gb), (m, float((ua - ub).abs().max()), float((ga - gb).abs().max()))
