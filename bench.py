@@ -254,13 +254,14 @@ def bench_gpu(args):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    kname = "tc_gemm_kernel (tcgen05 kind::tf32" if args.precision == "tf32" else "sgemm_nt_kernel (fp32 FFMA"
-    roofline_decoder = {"bound": "tensor", "kernel": kname + ", decoder 512x512 layer, fused bias+residual+CBN+ReLU epilogue)",
+    kname = ("tc_chain_kernel (tcgen05 kind::tf32, the ten 512x512 layers of a pass per cooperative launch" if args.precision == "tf32"
+             else "sgemm_nt_kernel (fp32 FFMA")
+    roofline_decoder = {"bound": "tensor", "kernel": kname + ", decoder 512x512 layers, fused bias+residual+CBN+ReLU epilogue)",
                 "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": pk["source"] + " bf16 burst / 2 (TF32-class contraction held to the tensor pipe)",
                 "launches": n_launch, "flops_per_launch": round(flops_total / max(1, n_launch)), "ms_per_launch": round(ms_total / max(1, n_launch), 4),
-                "measured": "event pair around every launch of one batch's lattice + face-filter chains (activations of consecutive layers "
-                            "exceed L2, residual/mask operands come from HBM)",
+                "measured": "event pair around every layer-chain launch of one batch's lattices + face filters (10 layers per launch in TF32 "
+                            "mode; activations of consecutive layers exceed L2, residual/mask operands come from HBM)",
                 "isolated": {"ms_per_launch": round(ms_iso, 4), "points_per_launch": m_iso,
                              "tflops": round(2.0 * m_iso * 512 * 512 / (ms_iso * 1e-3) / 1e12, 1)}}
     # The dominant kernel of the step is the persistent sampler (one launch = the whole 1000-step reverse process of a batch).

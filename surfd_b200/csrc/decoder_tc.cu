@@ -2,13 +2,14 @@
 // C[M][512] = A[M][512] * W[512][512]^T with the same fused epilogue as the FFMA kernel (bias, CBN/ReLU mask,
 // residual, next layer's CBN+ReLU activation), operands in TF32 (kind::tf32, fp32 accumulate in TMEM).
 //
-// Structure (one persistent CTA per SM, 6 warps, no cluster):
+// Structure (one persistent CTA per SM, 10 warps, no cluster):
 //   warp 0  TMA producer : cp.async.bulk.tensor.2d of the A tile (128 x 32 fp32, 128B-swizzled) and the W tile
 //                          (256 x 32) into a 4-stage shared-memory ring, mbarrier complete_tx
 //   warp 1  MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=256, K=8) x4 per
 //                          stage, tcgen05.commit frees the stage; the 128x256 fp32 accumulator lives in TMEM and
 //                          is double-buffered (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 2-5 epilogue   : tcgen05.ld 32x32b (one accumulator row per thread), fused epilogue, vectorised row stores
+//   warps 2-9 epilogue   : tcgen05.ld 32x32b (one accumulator row per thread), fused epilogue, vectorised row stores;
+//                          two warps per TMEM lane quadrant, one half of the tile's columns each
 // Both operands are K-major (activations [points][K], weights [out][K], K contiguous), so A and B tiles use the same
 // canonical SWIZZLE_128B K-major layout that TMA writes and the UMMA shared-memory descriptor reads.
 #include <cuda.h>
@@ -23,10 +24,10 @@ constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4;               // 16 KB
 constexpr int B_BYTES = BN * BK * 4;               // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;     // 48 KB
-constexpr int STG_LD = 36;                         // padded row of the epilogue transpose stage (floats)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * STG_LD * 4 /*epilogue stages*/;
+constexpr int EPI_WARPS = 8;                       // two per TMEM lane quadrant: each takes one half of the tile's 256 columns
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * 32 * 32 * 4 /*epilogue stages*/;
 constexpr int K_TOTAL = 512, KBLOCKS = K_TOTAL / BK;
-constexpr int THREADS = 192;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,6 +109,73 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// One epilogue warp's share of a 128 x 256 accumulator tile: TMEM lane quadrant `quad` (32 rows), columns [half * 128, + 128).
+// ncu (r2, source view): the epilogue, not HBM or the tensor pipe, bounds a tile -- ~5,000 dependent instructions per warp and
+// tile with ONE warp per scheduler (0.2 IPC: 13 us against 4.2 us of MMAs).  Eight epilogue warps (two per scheduler) halve
+// each warp's share and let the schedulers overlap the two.
+// Each thread owns one accumulator row in TMEM, but row-per-lane global accesses are fully divergent, so every 32 x 32 block is
+// transposed through a shared-memory stage (16-byte pieces XOR-swizzled by the row: conflict-free for the row-wise writes
+// and the 8-lanes-per-row reads) and the global side runs with 8 lanes per row: 128 contiguous bytes per row, 4 rows per access.
+__device__ __forceinline__ void epilogue_tile(const Epilogue& e, int M, int m0, int n0, int quad, uint32_t tmem_tile, float* stage, int lane) {
+  const int srow = lane >> 3, scol4 = lane & 7, scol = scol4 * 4;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32 / 2; ++c) {
+    // Residual / mask operands of this 32x32 block first: all 8 (+8) row segments are requested before anything is stored
+    // (R and C are the same buffer for the in-place residual update: loads placed after stores would be serialised).
+    float4 rq[8], mk[8];
+    {
+      const int nn = n0 + c * 32 + scol;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int m = m0 + quad * 32 + it * 4 + srow;
+        const size_t off = (size_t)(m < M ? m : M - 1) * e.ld + nn;
+        if (e.R) rq[it] = *reinterpret_cast<const float4*>(e.R + off);
+        if (e.mask) mk[it] = *reinterpret_cast<const float4*>(e.mask + off);
+      }
+    }
+    uint32_t r[32];
+    tmem_ld32(tmem_tile + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(stage + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+          make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+    __syncwarp();
+    const int n = n0 + c * 32 + scol;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), ms = bias, s2 = bias, t2 = bias;
+    if (e.bias) bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    if (e.mask) ms = __ldg(reinterpret_cast<const float4*>(e.mscale + n));
+    if (e.act) { s2 = __ldg(reinterpret_cast<const float4*>(e.s2 + n)); t2 = __ldg(reinterpret_cast<const float4*>(e.t2 + n)); }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + srow;
+      const int m = m0 + quad * 32 + rr;
+      if (m >= M) continue;
+      float4 v = *reinterpret_cast<const float4*>(stage + rr * 32 + ((scol4 ^ (rr & 7)) << 2));
+      const size_t off = (size_t)m * e.ld + n;
+      v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+      if (e.mask) {
+        const float4 k4 = mk[it];
+        v.x = k4.x > 0.f ? v.x * ms.x : 0.f; v.y = k4.y > 0.f ? v.y * ms.y : 0.f;
+        v.z = k4.z > 0.f ? v.z * ms.z : 0.f; v.w = k4.w > 0.f ? v.w * ms.w : 0.f;
+      }
+      if (e.R) { const float4 q4 = rq[it]; v.x += q4.x; v.y += q4.y; v.z += q4.z; v.w += q4.w; }
+      if (e.C) {
+        float4 o = v;
+        if (e.round_c) { o.x = round_to_tf32(o.x); o.y = round_to_tf32(o.y); o.z = round_to_tf32(o.z); o.w = round_to_tf32(o.w); }
+        *reinterpret_cast<float4*>(e.C + off) = o;
+      }
+      if (e.act) {
+        float4 a;
+        a.x = fmaxf(fmaf(s2.x, v.x, t2.x), 0.f); a.y = fmaxf(fmaf(s2.y, v.y, t2.y), 0.f);
+        a.z = fmaxf(fmaf(s2.z, v.z, t2.z), 0.f); a.w = fmaxf(fmaf(s2.w, v.w, t2.w), 0.f);
+        if (e.round_act) { a.x = round_to_tf32(a.x); a.y = round_to_tf32(a.y); a.z = round_to_tf32(a.z); a.w = round_to_tf32(a.w); }
+        *reinterpret_cast<float4*>(e.act + off) = a;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, Epilogue e, int* err) {
   extern __shared__ uint8_t smem_raw[];
@@ -128,7 +196,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -186,76 +254,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
-    const int quad = warp & 3;
+    // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * 32);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m0 = (tile >> 1) * BM, n0 = (tile & 1) * BN;
+      const int m0 = (tile >> 1) * BM, n0 = (tile & 1) * BN + half * (BN / 2);
       mbar_wait(&tfull[acc], acc_phase, err, 4);
       tc_fence_after();
-      // Each thread owns one accumulator row in TMEM, but row-per-lane global accesses are fully divergent (32 lines per
-      // instruction; ncu: epilogue-bound at 18% tensor-pipe activity).  So every 32x32 block is transposed through a padded
-      // shared-memory stage and the global side runs with 8 lanes per row: 128 contiguous bytes per row, 4 rows per access.
-      float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * STG_LD);
-      const int srow = lane >> 3, scol = (lane & 7) * 4;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        // Residual / mask operands of this 32x32 block first: all 8 (+8) row segments are requested before anything is
-        // stored.  (Inside the store loop the compiler must keep each load behind the previous iteration's stores -- R and C
-        // are the same buffer for the in-place residual update -- which serialises 64 HBM round trips per tile: measured
-        // 181 us per launch in the layer chain against 48 us for the same GEMM without a residual.)
-        float4 rq[8], mk[8];
-        {
-          const int nn = n0 + c * 32 + scol;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int m = m0 + quad * 32 + it * 4 + srow;
-            const size_t off = (size_t)(m < M ? m : M - 1) * e.ld + nn;
-            if (e.R) rq[it] = *reinterpret_cast<const float4*>(e.R + off);
-            if (e.mask) mk[it] = *reinterpret_cast<const float4*>(e.mask + off);
-          }
-        }
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(stage + lane * STG_LD + 4 * q) =
-              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-        __syncwarp();
-        const int n = n0 + c * 32 + scol;
-        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), ms = bias, s2 = bias, t2 = bias;
-        if (e.bias) bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-        if (e.mask) ms = __ldg(reinterpret_cast<const float4*>(e.mscale + n));
-        if (e.act) { s2 = __ldg(reinterpret_cast<const float4*>(e.s2 + n)); t2 = __ldg(reinterpret_cast<const float4*>(e.t2 + n)); }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + srow;
-          const int m = m0 + quad * 32 + rr;
-          if (m >= M) continue;
-          float4 v = *reinterpret_cast<const float4*>(stage + rr * STG_LD + scol);
-          const size_t off = (size_t)m * e.ld + n;
-          v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-          if (e.mask) {
-            const float4 k4 = mk[it];
-            v.x = k4.x > 0.f ? v.x * ms.x : 0.f; v.y = k4.y > 0.f ? v.y * ms.y : 0.f;
-            v.z = k4.z > 0.f ? v.z * ms.z : 0.f; v.w = k4.w > 0.f ? v.w * ms.w : 0.f;
-          }
-          if (e.R) { const float4 q4 = rq[it]; v.x += q4.x; v.y += q4.y; v.z += q4.z; v.w += q4.w; }
-          if (e.C) {
-            float4 o = v;
-            if (e.round_c) { o.x = round_to_tf32(o.x); o.y = round_to_tf32(o.y); o.z = round_to_tf32(o.z); o.w = round_to_tf32(o.w); }
-            *reinterpret_cast<float4*>(e.C + off) = o;
-          }
-          if (e.act) {
-            float4 a;
-            a.x = fmaxf(fmaf(s2.x, v.x, t2.x), 0.f); a.y = fmaxf(fmaf(s2.y, v.y, t2.y), 0.f);
-            a.z = fmaxf(fmaf(s2.z, v.z, t2.z), 0.f); a.w = fmaxf(fmaf(s2.w, v.w, t2.w), 0.f);
-            if (e.round_act) { a.x = round_to_tf32(a.x); a.y = round_to_tf32(a.y); a.z = round_to_tf32(a.z); a.w = round_to_tf32(a.w); }
-            *reinterpret_cast<float4*>(e.act + off) = a;
-          }
-        }
-      }
+      epilogue_tile(e, M, m0, n0, quad, tmem_base + (uint32_t)(acc * BN + half * (BN / 2)), stage, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -308,7 +315,7 @@ tc_chain_kernel(const __grid_constant__ ChainProg prog, int n_layers, int M, uns
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -366,69 +373,14 @@ tc_chain_kernel(const __grid_constant__ ChainProg prog, int n_layers, int M, uns
         }
       }
     } else {
-      // ===== epilogue warps 2..5 (see tc_gemm_kernel) =====
-      const Epilogue& e = L.e;
-      const int quad = warp & 3;
-      float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * STG_LD);
-      const int srow = lane >> 3, scol = (lane & 7) * 4;
+      // ===== epilogue warps 2..9 (see tc_gemm_kernel) =====
+      const int quad = warp & 3, half = (warp - 2) >> 2;
+      float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * 32);
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile >> 1) * BM, n0 = (tile & 1) * BN;
+        const int m0 = (tile >> 1) * BM, n0 = (tile & 1) * BN + half * (BN / 2);
         mbar_wait(&tfull[acc], acc_phase, err, 4);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          float4 rq[8], mk[8];
-          {
-            const int nn = n0 + c * 32 + scol;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int m = m0 + quad * 32 + it * 4 + srow;
-              const size_t off = (size_t)(m < M ? m : M - 1) * e.ld + nn;
-              if (e.R) rq[it] = *reinterpret_cast<const float4*>(e.R + off);
-              if (e.mask) mk[it] = *reinterpret_cast<const float4*>(e.mask + off);
-            }
-          }
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * q) =
-                make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-          __syncwarp();
-          const int n = n0 + c * 32 + scol;
-          float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), ms = bias, s2 = bias, t2 = bias;
-          if (e.bias) bias = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-          if (e.mask) ms = __ldg(reinterpret_cast<const float4*>(e.mscale + n));
-          if (e.act) { s2 = __ldg(reinterpret_cast<const float4*>(e.s2 + n)); t2 = __ldg(reinterpret_cast<const float4*>(e.t2 + n)); }
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + srow;
-            const int m = m0 + quad * 32 + rr;
-            if (m >= M) continue;
-            float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + scol);
-            const size_t off = (size_t)m * e.ld + n;
-            v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-            if (e.mask) {
-              const float4 k4 = mk[it];
-              v.x = k4.x > 0.f ? v.x * ms.x : 0.f; v.y = k4.y > 0.f ? v.y * ms.y : 0.f;
-              v.z = k4.z > 0.f ? v.z * ms.z : 0.f; v.w = k4.w > 0.f ? v.w * ms.w : 0.f;
-            }
-            if (e.R) { const float4 q4 = rq[it]; v.x += q4.x; v.y += q4.y; v.z += q4.z; v.w += q4.w; }
-            if (e.C) {
-              float4 o = v;
-              if (e.round_c) { o.x = round_to_tf32(o.x); o.y = round_to_tf32(o.y); o.z = round_to_tf32(o.z); o.w = round_to_tf32(o.w); }
-              *reinterpret_cast<float4*>(e.C + off) = o;
-            }
-            if (e.act) {
-              float4 a;
-              a.x = fmaxf(fmaf(s2.x, v.x, t2.x), 0.f); a.y = fmaxf(fmaf(s2.y, v.y, t2.y), 0.f);
-              a.z = fmaxf(fmaf(s2.z, v.z, t2.z), 0.f); a.w = fmaxf(fmaf(s2.w, v.w, t2.w), 0.f);
-              if (e.round_act) { a.x = round_to_tf32(a.x); a.y = round_to_tf32(a.y); a.z = round_to_tf32(a.z); a.w = round_to_tf32(a.w); }
-              *reinterpret_cast<float4*>(e.act + off) = a;
-            }
-          }
-        }
+        epilogue_tile(L.e, M, m0, n0, quad, tmem_base + (uint32_t)(acc * BN + half * (BN / 2)), stg, lane);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);

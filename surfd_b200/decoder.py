@@ -103,9 +103,8 @@ class UdfDecoder:
         _lib.check(self.lib.surfd_dec_set_precision(self._h, int(mode)))
 
     def set_chain(self, on):
-        """TF32 mode: True = the ten 512x512 layers of a pass in ONE cooperative launch (tc_chain_kernel: grid barrier between
-        layers, the chunk's activations stay in L2); False (default: measured faster, profiles/README.md) = one launch per
-        layer.  Bit-identical results."""
+        """TF32 mode: True (default) = the ten 512x512 layers of a pass in ONE cooperative launch (tc_chain_kernel: grid barrier
+        between layers, no launch gaps); False = one launch per layer.  Bit-identical results."""
         _lib.check(self.lib.surfd_dec_set_chain(self._h, 1 if on else 0))
 
     def set_sm_budget(self, n_sms):

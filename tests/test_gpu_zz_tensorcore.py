@@ -103,7 +103,7 @@ def test_layer_chain_kernel_is_bit_identical_to_per_layer_launches():
     sd = synth.synth_ae_rand(L, 4321)["decoder"]
     gen = torch.Generator().manual_seed(5)
     lat = torch.randn(L, generator=gen)
-    a = UdfDecoder(sd, L, max_chunk_points=140 * 256); a.set_precision(1); a.set_latent(lat)
+    a = UdfDecoder(sd, L, max_chunk_points=140 * 256); a.set_precision(1); a.set_chain(False); a.set_latent(lat)
     b = UdfDecoder(sd, L, max_chunk_points=140 * 256); b.set_precision(1); b.set_chain(True); b.set_latent(lat)
     for m in (1, 129, 5000, 35840, 80001):                 # partial tile, fewer tiles than CTAs, exactly one chunk, 3 chunks
         pts = torch.rand(m, 3, generator=gen) * 2 - 1

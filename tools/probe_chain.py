@@ -12,7 +12,7 @@ L, N = 32, int(sys.argv[1]) if len(sys.argv) > 1 else 256
 lat = torch.randn(L, generator=torch.Generator().manual_seed(0)).cuda() * 0.7
 sd = synth.synth_ae_poly(L)["decoder"]
 ref = None
-for chain, tiles in ((0, 6), (1, 1), (1, 2), (1, 3), (1, 6), (0, 2)):
+for chain, tiles in ((0, 6), (1, 3), (1, 6), (1, 9), (1, 12), (0, 9)):
     dec = UdfDecoder(sd, L, max_chunk_points=140 * 128 * tiles)
     dec.set_precision(1); dec.set_sm_budget(140); dec.set_chain(bool(chain))
     dec.set_latent(lat)
