@@ -56,7 +56,8 @@ UNET_PARAM_BYTES = 0   # set from the architecture walk: SURVEY.md 8(d) counts t
 def workload_text():
     c = {"no_cond": "uncond", "img": "cond_mode=img with a random CLIP-sized [B,512] context",
          "text": "cond_mode=text with random CLIP-text-sized [B,512] embeds"}[COND]
-    g = f", classifier-free guidance {GUIDANCE:g} replayed as two UNet passes per step (models/cfg_sampler.py)" if GUIDANCE != 1.0 else ""
+    g = (f", classifier-free guidance {GUIDANCE:g}: both UNet forwards of a step (models/cfg_sampler.py) in one batched pass"
+         if GUIDANCE != 1.0 else "")
     return (f"{CONFIG} = BASELINE.json {CONFIGS[CONFIG]['baseline']}: {c}{g}, all-parameter-randomised MDM (latent {LAT}) + closed-form "
             f"'poly' AE checkpoint, {STEPS_DDPM} DDPM steps, --resolution {RES}, batch {BATCH}/GPU, GridFiller lattice (the scripts' default)")
 
@@ -268,7 +269,9 @@ def bench_gpu(args):
     # Its binding roofline is HBM: every DDPM step (and every CFG pass) streams the UNet's fp32 weights once -- algorithmic bytes
     # = SURVEY 8(d)'s 553.3 MB (the 138.3 M parameters counted once; the packed blob also holds a second copy of the 22 emb_layers
     # matrices, which is implementation traffic, not algorithmic).  Timed live with a CUDA event pair around one more launch.
-    n_pass = 2 if GUIDANCE != 1.0 else 1
+    # Classifier-free guidance: the reference runs two forwards per step; the persistent engine runs the pair as one pass over
+    # 2B rows (same FLOPs), so the weights are needed -- and counted -- once per DDPM step.
+    n_pass = 1
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
     e0.record(); pipe.sample_latents(noise_dev, ctx_dev, None, GUIDANCE, n_steps=STEPS_DDPM); e1.record(); torch.cuda.synchronize(dev)

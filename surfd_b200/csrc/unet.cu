@@ -701,6 +701,8 @@ struct PersistArgs {
   const int* wl_start;           // [grid] first entry of the CTA's list
   const int* wl_count;           // [grid] its length
   int use_tma;                // tcgen05 units take their weights from the packed stream through cp.async.bulk (see WJob)
+  int pair_B;                 // classifier-free guidance as ONE pass over 2 * pair_B samples (rows b and pair_B + b are the two
+                              // forwards of sample b; the out-conv combines them); 0: n_pass sequential passes over B samples
 };
 
 // Weight stream of the tcgen05 units.  The weights of a unit are immutable and the op list is static, so they do not have
@@ -2305,6 +2307,41 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
           case P_OUTCONV: {   // last conv (224 -> 1) + the DDPM update of the element it produces
             const int C = o.i0, L = o.i1;
             const int warp = tid >> 5, lane = tid & 31;
+            if (pa.pair_B > 0) {
+              // guidance pair in one batch: x0 = x0b + scale * (x0a - x0b) with x0a / x0b the predictions of rows b / pair_B + b
+              // (models/cfg_sampler.py:19-26); both rows receive the updated sample
+              const int half = pa.pair_B * L;
+              for (int wi = cta * 8 + warp; wi < half; wi += G * 8) {
+                const int l = wi % L, b = wi / L;
+                float acc_a = 0.f, acc_b = 0.f;
+                for (int tap = 0; tap < 3; ++tap) {
+                  const int src = l + tap - 1;
+                  if (src < 0 || src >= L) continue;
+                  const float* ar = o.in0 + ((size_t)b * L + src) * C;
+                  const float* br = ar + (size_t)half * C;
+                  const float* wr = o.w0 + (size_t)tap * C;
+                  for (int c = lane; c < C; c += 32) { acc_a = fmaf(ar[c], wr[c], acc_a); acc_b = fmaf(br[c], wr[c], acc_b); }
+                }
+#pragma unroll
+                for (int of = 16; of > 0; of >>= 1) {
+                  acc_a += __shfl_xor_sync(0xffffffffu, acc_a, of);
+                  acc_b += __shfl_xor_sync(0xffffffffu, acc_b, of);
+                }
+                if (lane == 0) {
+                  const float x0a = acc_a + o.w1[0], x0b = acc_b + o.w1[0];
+                  const float x0 = __fadd_rn(x0b, __fmul_rn(pa.guidance, __fsub_rn(x0a, x0b)));
+                  const int ns = pa.n_steps;
+                  const float c1 = pa.coef[sidx], c2 = pa.coef[ns + sidx], sd = pa.coef[2 * ns + sidx];
+                  const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, pa.x[wi]));
+                  const float mask = sidx != 0 ? 1.0f : 0.0f;
+                  const float nz = pa.noise[(size_t)(1 + iter) * pa.noise_stride + wi];
+                  const float xn = __fadd_rn(mean, __fmul_rn(__fmul_rn(mask, sd), nz));
+                  pa.x[wi] = xn;
+                  pa.x[half + wi] = xn;
+                }
+              }
+              break;
+            }
             for (int wi = cta * 8 + warp; wi < pa.B * L; wi += G * 8) {
               const int l = wi % L, b = wi / L;
               float acc = 0.f;
@@ -2411,7 +2448,7 @@ static_assert(8 * CONV_STAGES * 2 * CT * CTP >= 8 * CT * 33 + CT * CT, "reductio
 struct Lane {
   DevBuf pool, emb_all, temb, e1, emb, t_cur, x0a, x0b, xcur, state;
   // persistent sampler: op descriptors, K-slice scratch, semaphores, barrier word + abort flag
-  DevBuf emb_silu, ctxv, p_ops, p_partials, p_sems, p_sync, p_prof, p_wlist, p_wlidx, p_wstream;
+  DevBuf emb_silu, ctxv, p_ops, p_partials, p_sems, p_sync, p_prof, p_wlist, p_wlidx, p_wstream, ctx2, lab2;
   int p_use_tma = 0;
   int p_B = -1, p_n_emb = 0, p_n_prog = 0, p_smem = 0, p_grid = 0, p_split = -1, p_wide = -1, p_sem_bank = 0, p_use_tc = 0;
   const float* p_ctx = nullptr;
@@ -2437,7 +2474,7 @@ struct Lane {
     pool.release(); emb_all.release(); temb.release(); e1.release(); emb.release(); t_cur.release(); x0a.release(); x0b.release();
     xcur.release(); state.release();
     emb_silu.release(); ctxv.release(); p_ops.release(); p_partials.release(); p_sems.release(); p_sync.release(); p_prof.release();
-    p_wlist.release(); p_wlidx.release(); p_wstream.release();
+    p_wlist.release(); p_wlidx.release(); p_wstream.release(); ctx2.release(); lab2.release();
     p_B = -1;
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
@@ -2519,7 +2556,8 @@ extern "C" int surfd_unet_set_lanes(surfd_unet* u, int n_lanes) {
   SURFD_CUDA(cudaDeviceSynchronize());
   for (auto& ln : u->lanes) ln.release();
   u->lanes.assign((size_t)n_lanes, Lane());
-  const int cap0 = u->max_batch;                                   // lane 0 also serves surfd_unet_forward at full batch
+  const int cap0 = 2 * u->max_batch;                               // lane 0 also serves surfd_unet_forward at full batch and the
+                                                                   // persistent engine's guidance pairs (2 rows per sample)
   const int cap = (u->max_batch + n_lanes - 1) / n_lanes;
   for (int i = 0; i < n_lanes; ++i) SURFD_TRY(lane_init(u, u->lanes[(size_t)i], i == 0 ? cap0 : cap));
   return 0;
@@ -3028,23 +3066,51 @@ static int sample_persistent(surfd_unet* u, int B, int n_steps, const int64_t* t
   const int L = u->L;
   int grid = u->sampler_sms > 0 ? u->sampler_sms : u->num_sms;
   if (grid > u->num_sms) grid = u->num_sms;     // one CTA per SM (234 registers x 256 threads)
-  SURFD_TRY(persist_build(u, ln, B, ctx, lab, grid));
+  int pair_max = 64;   // rows per launch in the verified range of the engine (see surfd_sample)
+  if (const char* e = getenv("SURFD_PERSIST_MAX_BATCH")) pair_max = atoi(e);
+  // Classifier-free guidance (two forwards per step, models/cfg_sampler.py:19-26): the one-round engine runs the pair as ONE
+  // pass over 2B rows -- the same FLOPs, but the 553 MB of weights stream once per step instead of twice and the op chain is
+  // walked once (C5: 2.99 -> 1.5 s per 1000 steps at B = 4).  The graph-identical engine (persist_split 0) keeps two passes.
+  const bool pair = guidance != 1.0f && u->persist_split == 1 && 2 * B <= ln.cap && 2 * B <= pair_max;
+  const int BB = pair ? 2 * B : B;
+  if (pair) {
+    const size_t xb = (size_t)B * L * sizeof(float);
+    SURFD_CUDA(cudaMemcpyAsync(ln.xcur.p, noise_dev, xb, cudaMemcpyDeviceToDevice, st));   // x_T = noise row 0, for both rows of a pair
+    SURFD_CUDA(cudaMemcpyAsync(ln.xcur.as<char>() + xb, noise_dev, xb, cudaMemcpyDeviceToDevice, st));
+    if (ctx) {
+      const size_t cb = (size_t)B * CTX * sizeof(float);
+      SURFD_TRY(ln.ctx2.reserve(2 * cb));
+      SURFD_CUDA(cudaMemcpyAsync(ln.ctx2.p, ctx, cb, cudaMemcpyDeviceToDevice, st));
+      SURFD_CUDA(cudaMemcpyAsync(ln.ctx2.as<char>() + cb, ctx, cb, cudaMemcpyDeviceToDevice, st));
+      ctx = ln.ctx2.as<float>();
+    }
+    if (lab) {
+      const size_t lb = (size_t)B * sizeof(int64_t);
+      SURFD_TRY(ln.lab2.reserve(2 * lb));
+      SURFD_CUDA(cudaMemcpyAsync(ln.lab2.p, lab, lb, cudaMemcpyDeviceToDevice, st));
+      SURFD_CUDA(cudaMemcpyAsync(ln.lab2.as<char>() + lb, lab, lb, cudaMemcpyDeviceToDevice, st));
+      lab = ln.lab2.as<int64_t>();
+    }
+  } else {
+    SURFD_CUDA(cudaMemcpyAsync(ln.xcur.p, noise_dev, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, st));   // x_T = noise row 0
+  }
+  SURFD_TRY(persist_build(u, ln, BB, ctx, lab, grid));
   int max_grid = 0;
   if (u->precision == 0) SURFD_TRY(persist_max_grid<0>(ln.p_smem, u->num_sms, &max_grid));
   else if (u->precision == 1) SURFD_TRY(persist_max_grid<1>(ln.p_smem, u->num_sms, &max_grid));
   else SURFD_TRY(persist_max_grid<2>(ln.p_smem, u->num_sms, &max_grid));
   SURFD_REQUIRE(max_grid >= grid, "persistent sampler kernel: the requested CTAs cannot all be resident");
-  SURFD_CUDA(cudaMemcpyAsync(ln.xcur.p, noise_dev, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, st));   // x_T = noise row 0
   SURFD_CUDA(cudaMemsetAsync(ln.p_sync.p, 0, P_SYNC_WORDS * sizeof(unsigned), st));
   SURFD_CUDA(cudaMemsetAsync(ln.p_sems.p, 0, 3 * (size_t)ln.p_sem_bank * sizeof(unsigned), st));
   if (ctx) {   // projected context: constant over the loop, computed once (the graph path accumulates it every step)
-    const dim3 g1((unsigned)cdiv(EMB, 8), (unsigned)cdiv(B, 8));
+    const dim3 g1((unsigned)cdiv(EMB, 8), (unsigned)cdiv(BB, 8));
     const auto& h = u->hdr;
-    UNET_LAUNCH(false, linear_rows_kernel, dim3(g1), dim3(256), 0, st, 0, ctx, B, CTX, u->w(h[9]), u->w(h[10]), EMB, 0, 0, 0, ln.ctxv.as<float>());
+    UNET_LAUNCH(false, linear_rows_kernel, dim3(g1), dim3(256), 0, st, 0, ctx, BB, CTX, u->w(h[9]), u->w(h[10]), EMB, 0, 0, 0, ln.ctxv.as<float>());
   }
   PersistArgs pa{};
   pa.ops = ln.p_ops.as<POp>(); pa.n_emb = ln.p_n_emb; pa.n_prog = ln.p_n_prog;
-  pa.n_steps = n_steps; pa.B = B; pa.L = L; pa.n_pass = guidance != 1.0f ? 2 : 1;
+  pa.n_steps = n_steps; pa.B = BB; pa.L = L; pa.n_pass = (guidance != 1.0f && !pair) ? 2 : 1;
+  pa.pair_B = pair ? B : 0;
   pa.tmap = tmap_dev; pa.coef = coef_dev; pa.noise = noise_dev; pa.noise_stride = (long long)B * L; pa.guidance = guidance;
   pa.x = ln.xcur.as<float>(); pa.x0a = ln.x0a.as<float>();
   pa.partials = ln.p_partials.as<float>(); pa.sems = ln.p_sems.as<unsigned>(); pa.sem_bank = ln.p_sem_bank; pa.use_tc = ln.p_use_tc; pa.sync = ln.p_sync.as<unsigned>();

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 CS=/usr/local/cuda/bin/compute-sanitizer
 run() {  # tool, stage, extra env
   local tool=$1 stage=$2
-  ( time timeout -s KILL 900 $CS --tool $tool --print-limit 20 python tools/sanitize_target.py $stage ) > gpurun_out/sanitize_${tool}_${stage}.log 2>&1
+  ( time timeout -s KILL 400 $CS --tool $tool --print-limit 20 python tools/sanitize_target.py $stage ) > gpurun_out/sanitize_${tool}_${stage}.log 2>&1
   echo "== $tool $stage: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|ok' gpurun_out/sanitize_${tool}_${stage}.log | tr '\n' ' ')"
 }
 run memcheck mc
