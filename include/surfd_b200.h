@@ -144,15 +144,17 @@ int surfd_unet_set_lanes(surfd_unet* u, int n_lanes);
  * CTAs (0 = one per SM), ops separated by grid barriers; token GEMMs are wide units (32 tokens x 128 outputs x one K slice,
  * every op a single round of the resident CTAs) on tcgen05 tensor cores with fp32-class split products.  mode 0: CUDA-graph
  * replay of the per-step kernel sequence (~170 nodes, one graph launch per DDPM step); also used when the device cannot launch
- * cooperatively and for batches above 8 samples per call (the persistent engine's verified range).  mode 2: the persistent
+ * cooperatively and for batches above 64 samples per call (the persistent engine's verified range).  mode 2: the persistent
  * kernel with the graph path's units and K split -- samples are bit-identical to mode 0 and independent of n_sms.
- * Measured on B200 at batch 8: 1.32 (mode 1) / 2.28 (mode 0) / 1.95 (mode 2) ms per DDPM step.
+ * In mode 1 the token GEMMs' weights arrive as packed 32 KB images through cp.async.bulk (a ring that one thread keeps full
+ * across barriers and ops), and classifier-free guidance runs both forwards of a step as one pass over 2B rows.
+ * Measured on B200 at batch 8: 1.26 (mode 1) / 2.28 (mode 0) / 1.98 (mode 2) ms per DDPM step.
  * All modes compute in the precision selected by surfd_unet_set_precision and agree to fp32 rounding. */
 int surfd_unet_set_sampler(surfd_unet* u, int mode, int n_sms);
 /* Diagnostics: out == NULL switches the persistent kernel's per-op-type cycle counters on/off; out != NULL reads the
  * last run's counters: out[(h * 8 + op) * 3 + {body cycles, barrier cycles, count}], h = 0 first CTA / 1 last CTA,
  * op = 1 emb1, 2 linear, 3 in-conv, 4 group norm, 5 token GEMM, 6 attention, 7 out-conv + DDPM update. */
-int surfd_unet_profile(surfd_unet* u, int on, int64_t* out /* [48] or NULL */);
+int surfd_unet_profile(surfd_unet* u, int on, int64_t* out /* [64] or NULL */);
 /* SURFD_ABORTED if the last persistent run reported a barrier time-out (valid after its stream was synchronised). */
 int surfd_unet_status(surfd_unet* u);
 /* token-GEMM arithmetic: 0 = fp32 FFMA, 1 = fp32-class split products (default: 3xTF32 on mma.sync in the per-op kernels, fp16

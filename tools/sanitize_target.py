@@ -10,7 +10,7 @@ from surfd_b200.decoder import UdfDecoder
 from surfd_b200.meshudf import MarchingCubes, finish_mesh
 
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
-L, N = 32, int(os.environ.get("SAN_N", "48"))
+L, N = 32, int(os.environ.get("SAN_N", "64"))
 if what in ("sampler", "all"):
     B, steps = 2, int(os.environ.get("SAN_STEPS", "3"))
     net = U.UNetSampler(synth.synth_mdm(L), L, max_batch=B)
