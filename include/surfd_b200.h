@@ -23,6 +23,7 @@ extern "C" {
 #define SURFD_QUEUE_OVERFLOW 3  /* internal BFS queue bound exceeded (pathological field) */
 #define SURFD_BAD_ARGUMENT 4    /* reference: ValueError on bad shapes _marching_cubes_lewiner.py:102-105 */
 #define SURFD_ABORTED 5         /* the persistent sampler kernel gave up at a grid barrier (never expected) */
+#define SURFD_RANGE 6           /* persistent sampler, precision mode 1: an activation left the fp16 range of the split products */
 
 int surfd_version(void);
 /* last CUDA / argument error text of the calling thread (static buffer) */
@@ -155,7 +156,8 @@ int surfd_unet_set_sampler(surfd_unet* u, int mode, int n_sms);
  * last run's counters: out[(h * 8 + op) * 3 + {body cycles, barrier cycles, count}], h = 0 first CTA / 1 last CTA,
  * op = 1 emb1, 2 linear, 3 in-conv, 4 group norm, 5 token GEMM, 6 attention, 7 out-conv + DDPM update. */
 int surfd_unet_profile(surfd_unet* u, int on, int64_t* out /* [64] or NULL */);
-/* SURFD_ABORTED if the last persistent run reported a barrier time-out (valid after its stream was synchronised). */
+/* SURFD_ABORTED if the last persistent run reported a barrier time-out, SURFD_RANGE if one of its activations left the fp16
+ * range the split-product token GEMMs need (|x| < 6e4, finite); valid after the run's stream was synchronised. */
 int surfd_unet_status(surfd_unet* u);
 /* token-GEMM arithmetic: 0 = fp32 FFMA, 1 = fp32-class split products (default: 3xTF32 on mma.sync in the per-op kernels, fp16
  * hi + lo/4096 two-term split on tcgen05 in the persistent engine; both 2^-22 relative), 2 = single-pass TF32 */

@@ -646,7 +646,7 @@ __global__ void step_advance_kernel(StepState* st) {
 //   * the DDPM update is the epilogue of the last op (each output element needs only its own x0).
 // Activations are read with plain loads after the barrier's fence (weights are immutable and may use the read-only path).
 // =================================================================================================================
-constexpr int P_SYNC_WORDS = 64;   // [0] barrier counter, [1] abort flag
+constexpr int P_SYNC_WORDS = 64;   // [0] barrier counter, [1] abort flag, [2] an activation left the fp16 range of the split products
 constexpr int P_MAX_KS = 16;   // most K slices per output tile in the persistent kernel
 enum { P_EMB1 = 1, P_LIN = 2, P_INCONV = 3, P_GN = 4, P_CONV = 5, P_ATTN = 6, P_OUTCONV = 7 };
 
@@ -1734,6 +1734,11 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
       const float* src = astg + s * TC_ASTG + (g * CT + rr) * CT + kk0;
       float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
       if (g == 1 && !(f_begin + 2 * p + 1 < f_end)) { x0 = make_float4(0.f, 0.f, 0.f, 0.f); x1 = x0; }   // odd chunk count
+      {   // the fp16 split needs |x| < 65504 (and finite): an outlier activation is reported, not silently turned into inf
+        const float m = fmaxf(fmaxf(fmaxf(fabsf(x0.x), fabsf(x0.y)), fmaxf(fabsf(x0.z), fabsf(x0.w))),
+                              fmaxf(fmaxf(fabsf(x1.x), fabsf(x1.y)), fmaxf(fabsf(x1.z), fabsf(x1.w))));
+        if (!(m < 6.0e4f)) atomicOr(abort_flag + 1, 1u);
+      }
       uint4 hi, lo;
       split_f16x2(make_float2(x0.x, x0.y), hi.x, lo.x);
       split_f16x2(make_float2(x0.z, x0.w), hi.y, lo.y);
@@ -2595,9 +2600,9 @@ extern "C" int surfd_unet_create(const float* packed, size_t n_floats, const int
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) u->num_sms = v;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess) u->coop = v != 0;
-    ce = cudaHostAlloc(&u->h_abort, sizeof(unsigned), cudaHostAllocDefault);
+    ce = cudaHostAlloc(&u->h_abort, 2 * sizeof(unsigned), cudaHostAllocDefault);
     if (ce != cudaSuccess) return fail(set_error(-(int)ce, cudaGetErrorString(ce), __FILE__, __LINE__));
-    *u->h_abort = 0u;
+    u->h_abort[0] = u->h_abort[1] = 0u;
   }
   // measured on B200 (B=8, L=32): 1 lane 2.6 ms/step, 8 concurrent lanes 5.6 ms/step -- many tiny cluster launches from
   // several streams contend in the front end, so the default is a single lane; set_lanes() stays for experiments.
@@ -2739,8 +2744,12 @@ extern "C" int surfd_unet_profile(surfd_unet* u, int on, int64_t* out) {
 
 extern "C" int surfd_unet_status(surfd_unet* u) {
   SURFD_REQUIRE(u != nullptr, "null argument");
-  if (u->h_abort && *u->h_abort != 0u)
+  if (u->h_abort && u->h_abort[0] != 0u)
     return set_error(SURFD_ABORTED, "persistent sampler aborted: a grid barrier timed out", __FILE__, __LINE__);
+  if (u->h_abort && u->h_abort[1] != 0u)
+    return set_error(SURFD_RANGE, "persistent sampler: an activation left the fp16 range of the split-product token GEMMs (|x| >= 6e4 or "
+                                  "not finite); the samples of this call are invalid -- use set_precision(0) or the graph engine (set_sampler(0))",
+                     __FILE__, __LINE__);
   return 0;
 }
 
@@ -3124,7 +3133,7 @@ static int sample_persistent(surfd_unet* u, int B, int n_steps, const int64_t* t
   if (u->precision == 0) SURFD_TRY(persist_launch<0>(pa, grid, ln.p_smem, st));
   else if (u->precision == 1) SURFD_TRY(persist_launch<1>(pa, grid, ln.p_smem, st));
   else SURFD_TRY(persist_launch<2>(pa, grid, ln.p_smem, st));
-  SURFD_CUDA(cudaMemcpyAsync(u->h_abort, ln.p_sync.as<unsigned>() + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  SURFD_CUDA(cudaMemcpyAsync(u->h_abort, ln.p_sync.as<unsigned>() + 1, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));   // abort, range flags
   SURFD_CUDA(cudaMemcpyAsync(out_dev, ln.xcur.p, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }

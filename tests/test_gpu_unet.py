@@ -185,3 +185,22 @@ def test_persistent_sampler_variants_agree(debug, what, monkeypatch):
         assert torch.isfinite(out).all()
         assert float((out - ref).abs().max()) < 2e-4, (what, B, float((out - ref).abs().max()))
 
+
+
+def test_persistent_sampler_reports_fp16_range_violation():
+    """precision mode 1 of the persistent engine splits operands into fp16 hi + lo: an activation outside the fp16 range must be
+    reported by status() (SURFD_RANGE), not silently turned into inf / NaN samples."""
+    from surfd_b200 import _lib
+    L = 32
+    sd = dict(synth.synth_mdm(L))
+    sd["Unet.input_blocks.0.0.weight"] = sd["Unet.input_blocks.0.0.weight"] * 1e7     # the raw residual stream feeds the downsample conv
+    net = U.UNetSampler(sd, L, max_batch=4)
+    S = U.SpacedSchedule(U.cosine_betas(), U.space_timesteps(1000, [2]))
+    noise = torch.randn(3, 4, L, generator=torch.Generator().manual_seed(1))
+    net.sample(S, noise)
+    torch.cuda.synchronize()
+    with pytest.raises(_lib.SurfdError) as ei:
+        net.status()
+    assert ei.value.status == 6
+    ok = U.UNetSampler(synth.synth_mdm(L), L, max_batch=4)                          # a healthy network stays silent
+    ok.sample(S, noise); torch.cuda.synchronize(); ok.status()
