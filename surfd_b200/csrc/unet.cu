@@ -1992,8 +1992,10 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
 }
 
 // ---- GroupNorm unit (128 threads = one half of the CTA), arithmetic of gn_kernel -------------------------------
-__device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, float* red) {
+__device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, float* red, long long* prof = nullptr) {
   const int tid = threadIdx.x & 127;
+  const bool pf = prof != nullptr && threadIdx.x == 0;
+  const long long tg0 = pf ? clock64() : 0;
   const float* in1 = o.in0;
   const float* in2 = o.in1;
   const int C1 = o.i0, C2 = o.i1, T = o.i2, silu = o.i3;
@@ -2043,13 +2045,16 @@ __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, 
 #pragma unroll
   for (int k = 0; k < PGN_CACHE; ++k) if (tid + 128 * k < n) s += xc[k];
   for (int i = tid + 128 * PGN_CACHE; i < n; i += 128) s += load(i);
+  const long long tg1 = pf ? clock64() : 0;
   const float mean = block_sum(s) / (float)n;
+  const long long tg2 = pf ? clock64() : 0;
   float q = 0.f;
 #pragma unroll
   for (int k = 0; k < PGN_CACHE; ++k) if (tid + 128 * k < n) { const float d = xc[k] - mean; q += d * d; }
   for (int i = tid + 128 * PGN_CACHE; i < n; i += 128) { const float d = load(i) - mean; q += d * d; }
   const float var = block_sum(q) / (float)n;
   const float rstd = 1.0f / sqrtf(var + 1e-5f);
+  const long long tg3 = pf ? clock64() : 0;
   auto emit = [&](int t, int c, float x, float gm, float bt) {
     float y = (x - mean) * rstd * gm + bt;
     if (silu) y = y / (1.0f + expf(-y));
@@ -2061,6 +2066,7 @@ __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, 
 #pragma unroll
   for (int k = 0; k < PGN_CACHE; ++k) if (tid + 128 * k < n) emit(tt[k], cc[k], xc[k], gc[k], bc[k]);
   for (int i = tid + 128 * PGN_CACHE; i < n; i += 128) { const int c = g * cg + i % cg; emit(i / cg, c, load(i), gamma[c], beta[c]); }
+  if (pf) { prof[58] += tg1 - tg0; prof[59] += tg2 - tg1; prof[60] += tg3 - tg2; prof[61] += clock64() - tg3; prof[62] += 1; }
 }
 
 // ---- small-M linears: rows [mb, mb+8) staged in shared memory (xs, row stride K), two output columns per warp pass ----
@@ -2279,7 +2285,7 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
           }
           case P_GN: {
             const int n_units = pa.B * 32;
-            for (int u = cta * 2 + half; u < n_units; u += 2 * G) p_gn_unit(o, u >> 5, u & 31, half, gn_red[half]);
+            for (int u = cta * 2 + half; u < n_units; u += 2 * G) p_gn_unit(o, u >> 5, u & 31, half, gn_red[half], cta == 0 ? pa.prof : nullptr);
             break;
           }
           case P_CONV:

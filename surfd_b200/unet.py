@@ -392,6 +392,7 @@ class UNetSampler:
         self.last_gemm_phases = dict(chunk_stream=buf[0], cta_partial=buf[1], publish=buf[2], reduce_epilogue=buf[24], units=buf[25], chunks_warp0=buf[26], wait_cycles=buf[27],
                                      w_full_wait=buf[48], stage_wait=buf[49], done_wait=buf[50], w_late_pairs=buf[51],
                                      split=buf[52], fence=buf[53], sync=buf[54], mma_issue=buf[55], a_issue=buf[56], a_wait=buf[57])
+        self.last_gn_phases = dict(load_sum=buf[58], mean_reduce=buf[59], var_reduce=buf[60], emit=buf[61], units=buf[62])
         names = {1: "emb1", 2: "linear", 3: "inconv", 4: "groupnorm", 5: "token_gemm", 6: "attention", 7: "outconv+update"}
         return {("first_cta", "last_cta")[h]: {names[o]: tuple(buf[(h * 8 + o) * 3 + i] for i in range(3)) for o in names} for h in range(2)}
 

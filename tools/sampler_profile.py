@@ -52,6 +52,9 @@ for prec, B in ((1, 8),):
             print("    first CTA token-GEMM phases (us per unit): " + ", ".join("%s %.2f" % (k, v / ph["units"] / 1965.0) for k, v in ph.items() if k not in ("units", "chunks_warp0", "wait_cycles", "w_late_pairs")),
                   "| units per step %.1f | %.2f chunk pairs per unit, %.2f us until the first pair has landed"
                   % (ph["units"] / 100, ph["chunks_warp0"] / ph["units"], ph["wait_cycles"] / ph["units"] / 1965.0), "| weight images that were late: %d of %d pairs" % (ph["w_late_pairs"], ph["chunks_warp0"]))
+        gp = net.last_gn_phases
+        if gp["units"]:
+            print("    first CTA GroupNorm unit phases (us per unit): " + ", ".join("%s %.2f" % (k, v / gp["units"] / 1965.0) for k, v in gp.items() if k != "units"))
         print("  mode %d profiled %.3f ms/step; per op type (us per op: body / barrier, count per step)" % (mode, t))
         for cta in ("first_cta", "last_cta"):
             row = []
