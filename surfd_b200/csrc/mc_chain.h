@@ -655,18 +655,6 @@ MC_HD void replay_r(Chain& g, ChainCache& cc, const Chain* home) {
           const uint32_t skip = (uint32_t)MC_POPC((ahead & (0u - ahead)) - 1u);
           g.q.head += skip + 1u;
           cur = cc.qw_cur[w + skip];
-          {   // pull the state of the cube that will most likely be visited next (the following open window entry) towards
-              // L1 while this visit computes: a hint only -- the visit itself reads the state after this one's stores
-            const uint32_t rest = ahead >> (skip + 1u);
-            if (rest) {
-              const Rec& nr = cc.wrec[w + skip + 1u + (uint32_t)MC_POPC((rest & (0u - rest)) - 1u)];
-              MC_LANE_LOOP(l) {
-                const int32_t v = nr.vid[l];
-                if (v >= 0) MC_PREFETCH_L1(g.vs + v);
-                if (l < 13) MC_PREFETCH_L1(g.slot + 4 * (int64_t)nr.vid[edge_corner(l)] + edge_j(l));
-              }
-            }
-          }
           visit_r(g, cc.wrec[w + skip], home, cur, visit_neighbours ? 1 : 2, done_set);
           if (done_set) {   // keep the window coherent: other entries naming the same cube are now visited
             uint32_t same = 0;

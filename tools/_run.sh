@@ -1,16 +1,4 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv | tail -1
-( time timeout -s KILL 900 python -m pytest tests -m gpu -q ) > gpurun_out/r2ad_tests.log 2>&1; grep -n "passed\|failed" gpurun_out/r2ad_tests.log
-( time timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/r2ad_smoke.log 2>&1; tail -2 gpurun_out/r2ad_smoke.log
-for c in C3 C2; do
-  ( time timeout -s KILL 900 python bench.py --config $c --steps 5 --warmup 3 ) > gpurun_out/r2ad_bench_$c.json 2> gpurun_out/r2ad_bench_$c.err
-done
-python - <<'PY'
-import json
-for c in ("C3","C2"):
-    try:
-        d=json.loads(open('gpurun_out/r2ad_bench_%s.json'%c).read().strip().splitlines()[-1])
-        print(c, 'value', d['value'], 'ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['value'], d.get('stages_s_per_step'), 'frac', d['roofline']['frac'], d['roofline']['traffic'], 'dec', d['roofline_decoder']['frac'], d['roofline_decoder']['traffic'], 'cls', d['roofline_mc_classify']['frac'], d.get('precision_fp32'), 'cpu', d['cpu_baseline']['value'], 'launches', d['gpu_launches'])
-    except Exception as e:
-        print(c, 'failed', e)
-PY
+( time timeout -s KILL 600 python -m pytest tests/test_gpu_mc.py tests/test_gpu_baseline_sizes.py -m gpu -x -q ) > gpurun_out/r2ae_mc_tests.log 2>&1; tail -3 gpurun_out/r2ae_mc_tests.log
+( timeout -s KILL 300 python tools/mc_profile.py 512 ) > gpurun_out/r2ae_mc512.log 2>&1; tail -1 gpurun_out/r2ae_mc512.log
+( timeout -s KILL 300 python tools/mc_profile.py 256 ) > gpurun_out/r2ae_mc256.log 2>&1; tail -1 gpurun_out/r2ae_mc256.log
