@@ -51,3 +51,14 @@ def analytic_field(kind, N, noise=0.0, seed=0):
 
 MC_CASES = [("sphere", 32, 0.0), ("sphere", 33, 0.3), ("torus", 48, 0.3), ("two", 40, 0.0), ("hemi", 40, 0.0),
             ("hemi", 64, 1.0), ("torus", 64, 1.0)]
+
+
+def noise_field(N, seed, level=0.3):
+    """every cube is a candidate (udf = level * voxel everywhere) and the gradients are random unit vectors: the walk is all
+    seeds, unsure pushes and ambiguous cases -- the stress case for queues, priorities and capacities"""
+    rng = np.random.default_rng(seed)
+    udf = np.full((N, N, N), level * 2.0 / (N - 1), np.float32)
+    udf *= rng.uniform(0.5, 1.5, udf.shape).astype(np.float32)
+    g = rng.standard_normal((N, N, N, 3)).astype(np.float32)
+    g /= np.linalg.norm(g, axis=-1, keepdims=True)
+    return udf, np.ascontiguousarray(g)

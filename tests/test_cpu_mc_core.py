@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT, GOLDEN
-from fields import analytic_field, MC_CASES
+from fields import analytic_field, noise_field, MC_CASES
 
 
 @pytest.fixture(scope="module")
@@ -75,3 +75,14 @@ def test_empty_field_reports_empty_surface(host_mc):
     g = np.zeros((16, 16, 16, 3), np.float32)
     rc, v, f, st = host_mc(udf, g)
     assert rc == 1 and len(v) == 0 and len(f) == 0
+
+
+def test_core_dense_noise_field_matches_live_reference(host_mc, ref_mc):
+    if ref_mc is None:
+        pytest.skip("oracle/_ref not built (reference absent)")
+    for N, seed in [(20, 1), (28, 2)]:
+        udf, grads = noise_field(N, seed)
+        rv, rf = ref_mc(udf, grads)
+        for fn in ("mc_host_run", "mc_host_run_r"):
+            rc, v, f, st = host_mc(udf, grads, fn)
+            assert rc == 0 and np.array_equal(v, rv) and np.array_equal(f, rf), (N, fn, len(v), len(rv), st)

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN
-from fields import analytic_field, MC_CASES
+from fields import analytic_field, noise_field, MC_CASES
 from surfd_b200.meshudf import MarchingCubes, udf_mc_lewiner, get_mesh_from_udf, DecoderUdf
 from surfd_b200 import synth
 from surfd_b200.decoder import UdfDecoder
@@ -49,6 +49,24 @@ def test_device_mc_exact_zero_udf_uses_the_extension_rule(ref_mc):
         rv, rf = ref_mc(udf, grads)
         v, f = mc.run_raw(torch.from_numpy(udf).cuda(), torch.from_numpy(grads).cuda())
         assert np.array_equal(v.cpu().numpy(), rv) and np.array_equal(f.cpu().numpy().reshape(-1), rf), (kind, N)
+
+
+def test_dense_noise_field_grows_capacities_and_stays_bit_exact(ref_mc):
+    """every cube a candidate, random gradients: far more candidates / vertices / queue traffic than the O(N^2) start
+    capacities -- the handle reports SURFD_CAPACITY, grows and reruns (transparently in run_raw), bit-exact again"""
+    if ref_mc is None:
+        pytest.skip("oracle/_ref not present on this machine")
+    mc = MarchingCubes()
+    for N, seed in [(28, 2), (40, 3)]:
+        udf, grads = noise_field(N, seed)
+        rv, rf = ref_mc(udf, grads)
+        v, f = mc.run_raw(torch.from_numpy(udf).cuda(), torch.from_numpy(grads).cuda())
+        assert np.array_equal(v.cpu().numpy(), rv) and np.array_equal(f.cpu().numpy().reshape(-1), rf), (N, v.shape, rv.shape)
+    # the same handle still serves a regular field afterwards
+    udf, grads = analytic_field("sphere", 64, 0.3, seed=5)
+    rv, rf = ref_mc(udf, grads)
+    v, f = mc.run_raw(torch.from_numpy(udf).cuda(), torch.from_numpy(grads).cuda())
+    assert np.array_equal(v.cpu().numpy(), rv) and np.array_equal(f.cpu().numpy().reshape(-1), rf)
 
 
 def test_launch_finish_on_side_streams_matches_blocking_call():
