@@ -658,6 +658,8 @@ struct PartSrc {
   const float* emb;           // [B][emb_ld] or null
   const float* res;           // [B*T][N] or null
   int ks, tiles_n, emb_ld, N;
+  const unsigned* p2p;        // non-null: the producing GEMM is NOT followed by a grid barrier -- its units count their arrivals per
+                              // output tile here (monotonic over the run) and the consumer waits for exactly the tiles it reads
 };
 
 struct POp {
@@ -677,6 +679,7 @@ struct POp {
   float inv_ks, inv_tn, inv_T; // P_CONV: 1 / ks, 1 / tiles_n, 1 / T_out (unit decoding without integer divisions, see div_small)
   int wide;                   // P_CONV: 1 = wide unit (32 x 128 tile, distributed slice reduction), 0 = narrow unit
   int defer;                  // P_CONV (wide, ks > 1): leave the K-slice partial tiles to the next op (no exchange inside this op)
+  unsigned* p2p;              // P_CONV (deferred, weight-stream flow): per-tile arrival counters; no grid barrier behind this op
   PartSrc ps;                 // P_GN / P_ATTN: the first input is a deferred token-GEMM output
 };
 
@@ -1946,6 +1949,7 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();   // the accumulators have been read: the next unit may overwrite them
+    if (o.p2p != nullptr && tid == 0) red_release_add(o.p2p + tile, 1u);   // this slice's partial tile is published
     if (ks > 1 && !o.defer) {
       if (tid == 0) {
         red_release_add(sems + tile, 1u);
@@ -1992,7 +1996,24 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
 }
 
 // ---- GroupNorm unit (128 threads = one half of the CTA), arithmetic of gn_kernel -------------------------------
-__device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, float* red, long long* prof = nullptr) {
+// at least `want` arrivals (wrap-safe); false: aborted
+__device__ __forceinline__ bool spin_at_least(const unsigned* p, unsigned want, unsigned* abort_flag) {
+  const long long t0 = clock64();
+  unsigned spins = 0;
+  while ((int)(ld_acquire(p) - want) < 0) {
+    if ((++spins & 1023u) == 0u) {
+      if (*(volatile unsigned*)abort_flag != 0u || clock64() - t0 > 2000000000LL) {
+        atomicExch(abort_flag, 1u);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+// exec: how many times this op has run in this launch, this time included (p2p hand-off: arrivals per tile = ks * exec)
+__device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, float* red, long long* prof = nullptr, unsigned exec = 0u,
+                                          unsigned* abort_flag = nullptr) {
   const int tid = threadIdx.x & 127;
   const bool pf = prof != nullptr && threadIdx.x == 0;
   const long long tg0 = pf ? clock64() : 0;
@@ -2008,6 +2029,19 @@ __device__ __forceinline__ void p_gn_unit(const POp& o, int b, int g, int half, 
   const int n = T * cg;
   const PartSrc ps = o.ps;   // into registers: the descriptor lives in shared memory and the barriers below carry memory clobbers
   const bool deferred = ps.ks > 0;
+  if (deferred && ps.p2p != nullptr) {
+    // No grid barrier separates this op from the GEMM that produced its first input: wait for the K slices of exactly the
+    // output tiles this (sample, group) unit reads -- the sample's token rows x the group's channels, at most 2 x 2 tiles.
+    if (tid == 0) {
+      const int c_lo = g * cg, c_hi = min((g + 1) * cg, C1) - 1;
+      if (c_lo <= c_hi) {
+        const unsigned want = (unsigned)ps.ks * exec;
+        for (int tm = (b * T) >> 5; tm <= (b * T + T - 1) >> 5; ++tm)
+          for (int tn = c_lo >> 7; tn <= c_hi >> 7; ++tn) spin_at_least(ps.p2p + tm * ps.tiles_n + tn, want, abort_flag);
+      }
+    }
+    named_bar(1 + half, 128);
+  }
   float* fin = const_cast<float*>(o.in0);   // a deferred first input is finalised in place for its later consumers
   auto load = [&](int idx) -> float {
     const int t = idx / cg, c = g * cg + idx % cg;
@@ -2285,7 +2319,8 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
           }
           case P_GN: {
             const int n_units = pa.B * 32;
-            for (int u = cta * 2 + half; u < n_units; u += 2 * G) p_gn_unit(o, u >> 5, u & 31, half, gn_red[half], cta == 0 ? pa.prof : nullptr);
+            for (int u = cta * 2 + half; u < n_units; u += 2 * G) p_gn_unit(o, u >> 5, u & 31, half, gn_red[half], cta == 0 ? pa.prof : nullptr,
+                                                                              (unsigned)(iter * pa.n_pass + pass + 1), pa.sync + 1);
             break;
           }
           case P_CONV:
@@ -2397,15 +2432,22 @@ __global__ void __launch_bounds__(256, 1) unet_persistent_kernel(PersistArgs pa)
         __syncthreads();   // the op is complete in this CTA, the next descriptor is in place
         long long t_op1 = 0;
         if (profiled) t_op1 = clock64();
-        grid_arrive(pa.sync);
+        // A deferred token GEMM with per-tile arrival counters hands its partial tiles to the GroupNorm behind it point to
+        // point: no grid barrier here, the GroupNorm units wait for the tiles they read (p_gn_unit).
+        const bool no_barrier = MODE == 1 && sop[slot].type == P_CONV && sop[slot].p2p != nullptr;
         pre_issued = false;
-        if (tid == 0) pump();
-        if (MODE != 0 && !use_tma && has_next && sop[slot ^ 1].type == P_CONV && sop[slot ^ 1].wide) {
-          if (sop[slot ^ 1].wide == 2) tc_preissue(sop[slot ^ 1], smem, cta);
-          else wide_preissue<WTP, W_STAGE, W_STAGES>(sop[slot ^ 1], smem, cta);
-          pre_issued = true;
+        if (!no_barrier) {
+          grid_arrive(pa.sync);
+          if (tid == 0) pump();
+          if (MODE != 0 && !use_tma && has_next && sop[slot ^ 1].type == P_CONV && sop[slot ^ 1].wide) {
+            if (sop[slot ^ 1].wide == 2) tc_preissue(sop[slot ^ 1], smem, cta);
+            else wide_preissue<WTP, W_STAGE, W_STAGES>(sop[slot ^ 1], smem, cta);
+            pre_issued = true;
+          }
+          if (!grid_wait(pa.sync, target, (unsigned)G, &s_ok, pump)) return;
+        } else if (tid == 0) {
+          pump();
         }
-        if (!grid_wait(pa.sync, target, (unsigned)G, &s_ok, pump)) return;
         if (profiled) {
           long long* pr = pa.prof + ((cta == 0 ? 0 : 8) + sop[slot].type) * 3;
           pr[0] += t_op1 - t_op0;
@@ -2459,7 +2501,8 @@ static_assert(8 * CONV_STAGES * 2 * CT * CTP >= 8 * CT * 33 + CT * CT, "reductio
 struct Lane {
   DevBuf pool, emb_all, temb, e1, emb, t_cur, x0a, x0b, xcur, state;
   // persistent sampler: op descriptors, K-slice scratch, semaphores, barrier word + abort flag
-  DevBuf emb_silu, ctxv, p_ops, p_partials, p_sems, p_sync, p_prof, p_wlist, p_wlidx, p_wstream, ctx2, lab2;
+  DevBuf emb_silu, ctxv, p_ops, p_partials, p_sems, p_sync, p_prof, p_wlist, p_wlidx, p_wstream, ctx2, lab2, p_p2p;
+  size_t p_p2p_words = 0;
   int p_use_tma = 0;
   int p_B = -1, p_n_emb = 0, p_n_prog = 0, p_smem = 0, p_grid = 0, p_split = -1, p_wide = -1, p_sem_bank = 0, p_use_tc = 0;
   const float* p_ctx = nullptr;
@@ -2485,7 +2528,7 @@ struct Lane {
     pool.release(); emb_all.release(); temb.release(); e1.release(); emb.release(); t_cur.release(); x0a.release(); x0b.release();
     xcur.release(); state.release();
     emb_silu.release(); ctxv.release(); p_ops.release(); p_partials.release(); p_sems.release(); p_sync.release(); p_prof.release();
-    p_wlist.release(); p_wlidx.release(); p_wstream.release(); ctx2.release(); lab2.release();
+    p_wlist.release(); p_wlidx.release(); p_wstream.release(); ctx2.release(); lab2.release(); p_p2p.release();
     p_B = -1;
     if (stream) cudaStreamDestroy(stream);
     if (done) cudaEventDestroy(done);
@@ -3056,6 +3099,24 @@ static int persist_build(surfd_unet* u, Lane& ln, int B, const float* ctx, const
       ln.p_use_tma = 1;
     }
   }
+  // point-to-point hand-off GEMM -> GroupNorm (weight-stream flow): per-tile arrival counters, one array per deferred GEMM
+  // (monotonic over a launch: a tile has received ks * executions arrivals), zeroed before every launch
+  ln.p_p2p_words = 0;
+  if (ln.p_use_tma && !(dbg & 256)) {
+    size_t words = 0;
+    for (size_t i = 0; i + 1 < ops.size(); ++i)
+      if (ops[i].type == P_CONV && ops[i].defer && ops[i].wide == 2 && ops[i + 1].type == P_GN) words += (size_t)ops[i].tiles_n * ops[i].tiles_m;
+    SURFD_TRY(ln.p_p2p.reserve((words ? words : 1) * sizeof(unsigned)));
+    size_t off = 0;
+    for (size_t i = 0; i + 1 < ops.size(); ++i) {
+      if (ops[i].type == P_CONV && ops[i].defer && ops[i].wide == 2 && ops[i + 1].type == P_GN) {
+        ops[i].p2p = ln.p_p2p.as<unsigned>() + off;
+        ops[i + 1].ps.p2p = ops[i].p2p;
+        off += (size_t)ops[i].tiles_n * ops[i].tiles_m;
+      }
+    }
+    ln.p_p2p_words = words;
+  }
   if (dbg & 4) for (auto& o : ops) o.type = 0;
   SURFD_TRY(ln.p_partials.reserve((max_partial_tiles ? max_partial_tiles : 1) * CT * CT * sizeof(float)));
   for (auto& o : ops) if (o.ps.ks > 0) o.ps.part = ln.p_partials.as<float>();
@@ -3117,6 +3178,7 @@ static int sample_persistent(surfd_unet* u, int B, int n_steps, const int64_t* t
   SURFD_REQUIRE(max_grid >= grid, "persistent sampler kernel: the requested CTAs cannot all be resident");
   SURFD_CUDA(cudaMemsetAsync(ln.p_sync.p, 0, P_SYNC_WORDS * sizeof(unsigned), st));
   SURFD_CUDA(cudaMemsetAsync(ln.p_sems.p, 0, 3 * (size_t)ln.p_sem_bank * sizeof(unsigned), st));
+  if (ln.p_p2p_words) SURFD_CUDA(cudaMemsetAsync(ln.p_p2p.p, 0, ln.p_p2p_words * sizeof(unsigned), st));
   if (ctx) {   // projected context: constant over the loop, computed once (the graph path accumulates it every step)
     const dim3 g1((unsigned)cdiv(EMB, 8), (unsigned)cdiv(BB, 8));
     const auto& h = u->hdr;

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-( time timeout -s KILL 600 python -m pytest tests/test_gpu_mc.py -m gpu -x -q ) > gpurun_out/r2af_mc_tests.log 2>&1; tail -12 gpurun_out/r2af_mc_tests.log | cut -c1-300
-( time timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/r2af_smoke.log 2>&1; tail -4 gpurun_out/r2af_smoke.log
+( time timeout -s KILL 300 python tools/sampler_profile.py ) > gpurun_out/r2ag_sampler_profile.log 2>&1; head -2 gpurun_out/r2ag_sampler_profile.log | cut -c1-300; tail -5 gpurun_out/r2ag_sampler_profile.log | cut -c1-500
+( SURFD_UNET_DEBUG=256 timeout -s KILL 300 python tools/sampler_profile.py ) > gpurun_out/r2ag_sampler_profile_nop2p.log 2>&1; head -2 gpurun_out/r2ag_sampler_profile_nop2p.log | cut -c1-300
+( time timeout -s KILL 900 python -m pytest tests/test_gpu_unet.py tests/test_gpu_baseline_sizes.py -m gpu -x -q -s ) > gpurun_out/r2ag_unet_tests.log 2>&1; grep -n "1000-step\|passed\|failed\|Error" gpurun_out/r2ag_unet_tests.log | head
