@@ -413,11 +413,22 @@ conv_gemm_kernel(ConvArgs a) {
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline int attn_smem_floats(int T, int ch) { return 2 * T * (ch + 1) + T * ch + T * (T + 1); }
 
+// (i / d, i % d) for small non-negative i without an integer division: a lone warp pays ~35 dependent instructions per
+// division by a run-time value, and the unit below did one per element
+__device__ __forceinline__ int attn_div(int x, int d, float inv) {
+  int q = (int)((float)x * inv);
+  const int r = x - q * d;
+  if (r < 0) --q;
+  else if (r >= d) ++q;
+  return q;
+}
+
 template <typename Sync, typename Load>
 __device__ __forceinline__ void attn_unit(const float* qkv, int C, int T, int heads, float scale, float* out, int b, int h, float* sm,
                                           int tid, int nthr, Sync sync, Load load) {
   const int ch = C / heads;
   const int chp = ch + 1;
+  const float inv_ch = 1.0f / (float)ch, inv_T = 1.0f / (float)T;
   float* q = sm;               // [T][chp] (scaled)
   float* k = q + T * chp;      // [T][chp] (scaled)
   float* v = k + T * chp;      // [T][ch]
@@ -425,12 +436,15 @@ __device__ __forceinline__ void attn_unit(const float* qkv, int C, int T, int he
   const float* base = qkv + (size_t)b * T * 3 * C + (size_t)h * 3 * ch;
   for (int i0 = tid; i0 < T * ch; i0 += 4 * nthr) {   // four (q, k, v) triples in flight per thread
     float qv[4], kv[4], vv[4];
+    int tt[4], cc[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * nthr;
       qv[u] = kv[u] = vv[u] = 0.f;
+      tt[u] = cc[u] = 0;
       if (i < T * ch) {
-        const int t = i / ch, c = i % ch;
+        const int t = attn_div(i, ch, inv_ch), c = i - t * ch;
+        tt[u] = t; cc[u] = c;
         const float* p = base + (size_t)t * 3 * C + c;
         qv[u] = load(p, b * T + t, h * 3 * ch + c); kv[u] = load(p + ch, b * T + t, h * 3 * ch + ch + c);
         vv[u] = load(p + 2 * ch, b * T + t, h * 3 * ch + 2 * ch + c);
@@ -440,19 +454,27 @@ __device__ __forceinline__ void attn_unit(const float* qkv, int C, int T, int he
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * nthr;
       if (i < T * ch) {
-        const int t = i / ch, c = i % ch;
-        q[t * chp + c] = qv[u] * scale;
-        k[t * chp + c] = kv[u] * scale;
+        q[tt[u] * chp + cc[u]] = qv[u] * scale;
+        k[tt[u] * chp + cc[u]] = kv[u] * scale;
         v[i] = vv[u];
       }
     }
   }
   sync();
+  // scores: one (query, key) pair per thread; four independent partial sums over the channels (a single accumulator is a
+  // chain of ch dependent FMAs: 112 x 4 cycles at the 4-token levels, where only 16 threads have work)
   for (int i = tid; i < T * T; i += nthr) {
-    const int t = i / T, s = i % T;
-    float acc = 0.f;
-    for (int c = 0; c < ch; ++c) acc = fmaf(q[t * chp + c], k[s * chp + c], acc);
-    w[t * (T + 1) + s] = acc;
+    const int t = attn_div(i, T, inv_T), s_ = i - t * T;
+    const float* qr = q + t * chp;
+    const float* kr = k + s_ * chp;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= ch; c += 4) {
+      a0 = fmaf(qr[c], kr[c], a0); a1 = fmaf(qr[c + 1], kr[c + 1], a1);
+      a2 = fmaf(qr[c + 2], kr[c + 2], a2); a3 = fmaf(qr[c + 3], kr[c + 3], a3);
+    }
+    for (; c < ch; ++c) a0 = fmaf(qr[c], kr[c], a0);
+    w[t * (T + 1) + s_] = (a0 + a1) + (a2 + a3);
   }
   sync();
   // softmax: one warp per row, lanes over the keys
@@ -472,10 +494,16 @@ __device__ __forceinline__ void attn_unit(const float* qkv, int C, int T, int he
   }
   sync();
   for (int i = tid; i < T * ch; i += nthr) {
-    const int t = i / ch, c = i % ch;
-    float acc = 0.f;
-    for (int s = 0; s < T; ++s) acc = fmaf(w[t * (T + 1) + s], v[s * ch + c], acc);
-    out[((size_t)b * T + t) * C + h * ch + c] = acc;
+    const int t = attn_div(i, ch, inv_ch), c = i - t * ch;
+    const float* wr = w + t * (T + 1);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int s = 0;
+    for (; s + 4 <= T; s += 4) {
+      a0 = fmaf(wr[s], v[s * ch + c], a0); a1 = fmaf(wr[s + 1], v[(s + 1) * ch + c], a1);
+      a2 = fmaf(wr[s + 2], v[(s + 2) * ch + c], a2); a3 = fmaf(wr[s + 3], v[(s + 3) * ch + c], a3);
+    }
+    for (; s < T; ++s) a0 = fmaf(wr[s], v[s * ch + c], a0);
+    out[((size_t)b * T + t) * C + h * ch + c] = (a0 + a1) + (a2 + a3);
   }
   sync();   // the buffers may be reused for the next unit
 }
