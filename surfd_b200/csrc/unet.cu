@@ -746,7 +746,6 @@ struct WJob {
   const uint8_t* base;        // [tiles_n * ks][pairs_max][32 KB]
   int tiles_n, tiles_m, ks, n_chunks, pairs_max, pad;
 };
-constexpr int WJOB_MAX = 96;
 
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -1492,6 +1491,15 @@ __device__ __forceinline__ void tcw_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// What the token-row copies of one K chunk need, computed ONCE per chunk (by one thread) instead of by all 256: the chunk ->
+// (segment, channel block, tap) decoding is the same for every row of the tile.
+struct ChunkDesc {
+  const float* base;   // source tensor (first or second concat source), already offset to the chunk's channels
+  int ld;              // its row stride in floats
+  int shift;           // tap - taps / 2: token offset of this tap
+  int stride, up, T_in;
+  int valid;           // 0: the pair's second chunk does not exist (odd chunk count)
+};
 // per-CTA state of the tcgen05 path (static shared memory of the persistent kernel)
 struct TcState {
   uint64_t stage_free[TC_STAGES];   // the MMAs that read operand stage s have completed
@@ -1499,6 +1507,7 @@ struct TcState {
   uint64_t done;                    // all MMAs of the unit have completed
   uint32_t tmem_base;
   uint32_t pad;
+  ChunkDesc cd[2 * 4];              // token-row descriptors of the current batch of chunk pairs (2 per pair)
 };
 // thread-local, uniform: commits issued so far per barrier (a wait targets the phase of the latest commit; waiting twice for
 // the same phase is harmless, so no wait is ever "owed")
@@ -1655,6 +1664,48 @@ __device__ __forceinline__ void tc_issue(const ConvArgs& a, int n_chunks0, int f
 // carries a memory clobber: interleaved with the copies, each field was re-read from shared memory behind a dependent
 // address computation -- measured 1.3 us per unit for issuing 0.17 us worth of loads), the row -> (sample, token) division
 // is done once per unit by the caller, and the chunk -> (channel block, tap) division is by a constant.
+__device__ __forceinline__ ChunkDesc make_chunk_desc(const ConvArgs& a, int n_chunks0, int f_begin, int f_end, int pair, int g) {
+  ChunkDesc d;
+  const int f = f_begin + 2 * pair + g;
+  d.valid = f < f_end ? 1 : 0;
+  const Seg& sg = a.seg[(d.valid && f >= n_chunks0) ? 1 : 0];
+  const int q = d.valid ? (f >= n_chunks0 ? f - n_chunks0 : f) : 0;
+  const int taps = sg.taps;
+  const int cb = taps == 3 ? q / 3 : (taps == 1 ? q : q / taps);
+  const int tap = q - cb * taps;
+  const bool second = cb * CT >= sg.C1;
+  d.base = (second ? sg.A2 : sg.A) + (second ? cb * CT - sg.C1 : cb * CT);
+  d.ld = second ? sg.Cin - sg.C1 : sg.C1;
+  d.shift = tap - (taps >> 1);
+  d.stride = sg.stride; d.up = sg.up; d.T_in = sg.T_in;
+  return d;
+}
+// token rows of one chunk pair from its two descriptors (shared memory)
+__device__ __forceinline__ void tc_issue_rows_d(const ChunkDesc* cd, float* astg, int rb, int rl, bool rok) {
+  const int tid = (int)threadIdx.x;
+  const int lp = tid & 7, cr = tid >> 3;
+  const ChunkDesc c0 = cd[0], c1 = cd[1];
+  const float* src[2];
+  int bytes[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const ChunkDesc& c = g ? c1 : c0;
+    const int T_eff = c.up ? 2 * c.T_in : c.T_in;
+    const int sr = rl * c.stride + c.shift;
+    const bool ok = c.valid && rok && sr >= 0 && sr < T_eff;
+    const int st = c.up ? (sr >> 1) : sr;
+    src[g] = c.base + (ok ? ((size_t)rb * c.T_in + st) * c.ld : (size_t)0) + 4 * lp;
+    bytes[g] = ok ? 16 : 0;
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    if (g == 0 ? c0.valid : c1.valid) {
+      const uint32_t da = tcw_smem_u32(astg + (g * CT + cr) * CT + 4 * lp);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(src[g]), "r"(bytes[g]) : "memory");
+    }
+  }
+}
+
 struct SegRows { const float* A; const float* A2; int Cin, taps, stride, up, T_in, C1; };   // what the token-row copies need of a Seg
 __device__ __forceinline__ SegRows seg_rows(const Seg& g) { return SegRows{g.A, g.A2, g.Cin, g.taps, g.stride, g.up, g.T_in, g.C1}; }
 __device__ __forceinline__ void tc_issue_rows(const SegRows& s0, const SegRows& s1, int n_chunks0, int f_begin, int f_end, int pair, float* astg,
@@ -1750,7 +1801,6 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
     const int m_row = m0 + (tid >> 3);   // this thread's token row of the tile -> (sample, token)
     const bool row_ok = m_row < M;
     const int row_b = div_small(m_row, a.T_out, o.inv_T), row_l = m_row - row_b * a.T_out;
-    const SegRows sr0 = seg_rows(a.seg[0]), sr1 = seg_rows(a.seg[1]);   // into registers once per unit (see tc_issue_rows)
     auto stage_of = [&](int pair) { return (int)((gp0 + (uint32_t)pair) & (TC_STAGES - 1)); };
     auto issue_pair = [&](int pair, int what) {
       const int s = stage_of(pair);
@@ -1853,7 +1903,9 @@ __device__ __forceinline__ bool p_conv_tc(const POp& o, float* smem, float* part
           if (pf) prof[49] += clock64() - ts0;
           if (tid == 128) wstream_pump(wc, ts, ops);   // the previous batch's stages are free: request this batch's images now
         }
-        for (int i = 0; i < nb; ++i) tc_issue_rows(sr0, sr1, n_chunks0, f_begin, f_end, b0 + i, astg + stage_of(b0 + i) * TC_ASTG, row_b, row_l, row_ok);
+        if (tid < 2 * nb) ts->cd[tid] = make_chunk_desc(a, n_chunks0, f_begin, f_end, b0 + (tid >> 1), tid & 1);
+        __syncthreads();
+        for (int i = 0; i < nb; ++i) tc_issue_rows_d(ts->cd + 2 * i, astg + stage_of(b0 + i) * TC_ASTG, row_b, row_l, row_ok);
         asm volatile("cp.async.commit_group;" ::: "memory");
         const long long ti1 = pf ? clock64() : 0;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
