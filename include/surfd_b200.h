@@ -83,7 +83,8 @@ int surfd_dec_logits(surfd_decoder* d, const float* pts_dev, int64_t M, float* l
 /* Whole lattice of one shape.  mode 0: dense get_udf_and_grads (meshudf.py:254-304);
  * mode 1: coarse-to-fine GridFiller.fill_grid (meshudf.py:36-206).  udf_dev [N^3], grad_dev [N^3][3]
  * (zero where not evaluated), both also clamped like meshudf.py:342.  counts (host, may be NULL):
- * [0] udf evaluations, [1] gradient evaluations.  Synchronises `stream` (level sizes are read back). */
+ * [0] udf evaluations, [1] gradient evaluations.  Synchronises `stream` (level sizes are read back).
+ * grad_dev NULL: udf only -- utils.GridFiller.fill_grid (utils/utils.py:252-339), the filler of the --watertight branch. */
 int surfd_udf_lattice(surfd_decoder* d, int N, int mode, double max_dist, float* udf_dev, float* grad_dev,
                       int64_t* counts_host, void* stream);
 

@@ -8,7 +8,11 @@ reference's mesh clean-up (meshudf.py:379-434, surfd_b200/meshclean.py) and outp
 components under 2500 faces, .obj; generate_uncond.py:113-122, surfd_b200/output.py) on the device -- both restated from the
 documented behaviour of trimesh / pymeshlab, which are absent here (parity unpinned).  The CLIP encoders are outside this
 path, so conditional modes take pre-computed 512-d embeddings through --context_path (or use an installed `clip` package).
-`--watertight` (third-party `mcubes` at iso 0.01, generate_text.py:132-158) is not built and raises.
+`--watertight` (generate_image.py / generate_text.py:132-158: udf lattice -> `mcubes.marching_cubes(udf, 0.01)` -> components
+under 5000 faces removed) runs on the device through surfd_b200/watertight.py for the two scripts that have the flag
+(parity unpinned: PyMCubes absent); the other three scripts parse and ignore it, like the reference.
+File names follow the scripts: {k}.obj, <category name>/{k}.obj, sketch_<sketch file stem>.obj, <image file stem>.obj,
+<prompt with dashes>_{k}.obj (the sketch / image scripts produce ONE shape; with --num_samples > 1 a _{k} suffix is added).
 Extra flags: --context_path, --dense_grid (use_fast_grid_filler=False), --precision {fp32,tf32}, --raw_mesh (stop at the
 meshudf.py:379 boundary).
 Multi-GPU: launch with torchrun; samples are sharded contiguously over ranks; rank 0 alone reads the two checkpoints and
@@ -82,6 +86,25 @@ def write_obj(path, verts, faces):
             fh.write("f %d %d %d\n" % (a[0], a[1], a[2]))
 
 
+CAT2NAME = {0: "long_sleeve_upper", 1: "short_sleeve_upper", 2: "no_sleeve_upper", 3: "long_sleeve_dress", 4: "short_sleeve_dress",
+            5: "no_sleeve_dress", 6: "long_pants", 7: "short_pants", 8: "dress"}      # generate_cat.py:21-29
+
+
+def mesh_path_for(args, kind, k, B):
+    """output file of sample k, named like the reference's scripts (generate_uncond.py:114, generate_cat.py:121,
+    generate_sketch.py:124,145, generate_image.py:92-94,147, generate_text.py:130)"""
+    many = f"_{k}" if B > 1 else ""
+    if kind == "cat":
+        return os.path.join(args.output_dir, CAT2NAME.get(args.category, str(args.category)), f"{k}.obj")
+    if kind == "sketch" and args.sketch_path:
+        return os.path.join(args.output_dir, f"sketch_{args.sketch_path.split('/')[-1][:-4]}{many}.obj")
+    if kind == "image" and args.image_path:
+        return os.path.join(args.output_dir, f"{args.image_path.split('/')[-1].split('.')[0]}{many}.obj")
+    if kind == "text" and args.prompt:
+        return os.path.join(args.output_dir, args.prompt.replace(" ", "-").replace(".", "")[:100] + f"_{k}.obj")
+    return os.path.join(args.output_dir, f"{k}.obj")
+
+
 def _context(args, kind, B, device):
     if args.context_path:
         ctx = torch.load(args.context_path, map_location="cpu")
@@ -123,9 +146,7 @@ def main(kind, argv=None):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if args.watertight:
-        raise NotImplementedError("--watertight (utils.GridFiller + third-party mcubes at iso 0.01, generate_text.py:132-158) is "
-                                  "not part of this build (SURVEY.md 8(f)-4)")
+    watertight = args.watertight and kind in ("image", "text")      # the other three scripts never read the flag
     if not args.sigma_small:
         raise NotImplementedError("--sigma_small False (FIXED_LARGE variance) is never used by the reference's checkpoints")
     latent = 64 if kind in ("image", "text") else 32      # generate_image.py:76, generate_text.py:80 vs generate_uncond.py:55
@@ -168,13 +189,20 @@ def main(kind, argv=None):
     t0 = time.time()
     if hi > lo:
         from .meshclean import clean_mesh
-        from .output import finish_and_save
-        lat, meshes, stats = pipe.generate(noise.to(dev), args.resolution, ctx, lab, guidance=float(args.guidance_param),
-                                           n_steps=1000, use_fast_grid_filler=not args.dense_grid, noise_schedule=args.noise_schedule)
+        from .output import finish_and_save, write_obj_meshlab
+        if watertight:
+            lat = pipe.sample_latents(noise.to(dev), ctx, lab, float(args.guidance_param), 1000, args.noise_schedule)
+            meshes = pipe.watertight(lat, args.resolution, iso=0.01, mincomponentsize=5000)
+        else:
+            lat, meshes, stats = pipe.generate(noise.to(dev), args.resolution, ctx, lab, guidance=float(args.guidance_param),
+                                               n_steps=1000, use_fast_grid_filler=not args.dense_grid, noise_schedule=args.noise_schedule)
         torch.cuda.synchronize()
         for k, (v, f) in enumerate(meshes):
-            mesh_path = os.path.join(args.output_dir, f"{lo + k}.obj")
-            if args.raw_mesh:
+            mesh_path = mesh_path_for(args, kind, lo + k, B)
+            os.makedirs(os.path.dirname(mesh_path) or ".", exist_ok=True)
+            if watertight:
+                write_obj_meshlab(mesh_path, v, f)
+            elif args.raw_mesh:
                 write_obj(mesh_path, v, f)
             else:
                 v, f = clean_mesh(v, f, smooth_borders=True)

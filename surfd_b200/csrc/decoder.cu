@@ -816,18 +816,18 @@ static int lattice_grads(surfd_decoder* d, int N, float thr, float* udf_dev, flo
 extern "C" int surfd_udf_lattice(surfd_decoder* d, int N, int mode, double max_dist, float* udf_dev, float* grad_dev,
                                  int64_t* counts_host, void* stream) {
   SURFD_REQUIRE(d && d->latent_set, "decoder latent not set");
-  SURFD_REQUIRE(udf_dev && grad_dev, "null argument");
+  SURFD_REQUIRE(udf_dev, "null argument");   // grad_dev NULL: udf only (utils/utils.py:252-339, the --watertight filler)
   SURFD_REQUIRE(N >= 2 && N <= 1024, "N out of range");
   SURFD_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (dense) or 1 (GridFiller)");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n3 = (int64_t)N * N * N;
   int64_t n_udf = 0, n_grad = 0;
-  SURFD_CUDA(cudaMemsetAsync(grad_dev, 0, (size_t)n3 * 3 * sizeof(float), st));
+  if (grad_dev) SURFD_CUDA(cudaMemsetAsync(grad_dev, 0, (size_t)n3 * 3 * sizeof(float), st));
   if (mode == 0) {
     SURFD_TRY(lattice_eval(d, nullptr, 0, n3, N, 1, N, false, udf_dev, grad_dev, st));
     n_udf = n3;
     const float thr = (float)(max_dist - 1e-3);  // meshudf.py:295, compared in fp32
-    SURFD_TRY(lattice_grads(d, N, thr, udf_dev, grad_dev, &n_grad, st));
+    if (grad_dev) SURFD_TRY(lattice_grads(d, N, thr, udf_dev, grad_dev, &n_grad, st));
   } else {
     // levels 32, 64, ..., N   (meshudf.py:44: [32 * 2**i for i in range(int(log2(N) - 4))])
     int n_lv = 0, NLs[8];
@@ -879,7 +879,7 @@ extern "C" int surfd_udf_lattice(surfd_decoder* d, int N, int mode, double max_d
       SURFD_CHECK_LAUNCH();
     }
     const float thr = (float)(2.5 * 2.0 / N);  // meshudf.py:199
-    SURFD_TRY(lattice_grads(d, N, thr, udf_dev, grad_dev, &n_grad, st));
+    if (grad_dev) SURFD_TRY(lattice_grads(d, N, thr, udf_dev, grad_dev, &n_grad, st));
   }
   if (counts_host) { counts_host[0] = n_udf; counts_host[1] = n_grad; }
   return 0;

@@ -138,13 +138,14 @@ class UdfDecoder:
         _lib.check(self.lib.surfd_dec_logits(self._h, _lib.ptr(pts), M, _lib.ptr(out), _lib.stream_ptr()))
         return out
 
-    def lattice(self, N, use_fast_grid_filler=True, max_dist=0.1):
-        """(udf [N,N,N], grads [N,N,N,3], counts) -- GridFiller.fill_grid or get_udf_and_grads."""
+    def lattice(self, N, use_fast_grid_filler=True, max_dist=0.1, grads=True):
+        """(udf [N,N,N], grads [N,N,N,3], counts) -- GridFiller.fill_grid or get_udf_and_grads.  grads=False: udf only
+        (utils.GridFiller.fill_grid, utils/utils.py:252-339), the second item is None."""
         udf = torch.empty(N, N, N, device=self.device, dtype=torch.float32)
-        grad = torch.empty(N, N, N, 3, device=self.device, dtype=torch.float32)
+        grad = torch.empty(N, N, N, 3, device=self.device, dtype=torch.float32) if grads else None
         counts = (ctypes.c_int64 * 2)()
         _lib.check(self.lib.surfd_udf_lattice(self._h, int(N), 1 if use_fast_grid_filler else 0, float(max_dist),
-                                              _lib.ptr(udf), _lib.ptr(grad), counts, _lib.stream_ptr()))
+                                              _lib.ptr(udf), _lib.ptr(grad) if grads else None, counts, _lib.stream_ptr()))
         return udf, grad, (int(counts[0]), int(counts[1]))
 
     def time_layer(self, iters=20, points=None):

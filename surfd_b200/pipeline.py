@@ -138,6 +138,21 @@ class SurfDPipeline:
         self._account(marks, timings)
         return meshes, stats
 
+    def watertight(self, latents, N, iso=0.01, mincomponentsize=5000):
+        """the `--watertight` branch (generate_text.py:132-158): per shape, coarse-to-fine udf lattice -> classic marching
+        cubes at `iso` -> components under `mincomponentsize` faces removed.  Returns [(verts [V,3] in lattice-index units,
+        faces [F,3])]; the lattice stays on the device (surfd_b200/watertight.py)."""
+        from .watertight import watertight_mesh
+        out = []
+        for k in range(latents.shape[0]):
+            with _nvtx("surfd.lattice"):
+                self.decoder.set_latent(latents[k])
+                udf, _, _ = self.decoder.lattice(N, use_fast_grid_filler=True, grads=False)
+            with _nvtx("surfd.watertight"):
+                out.append(watertight_mesh(udf, iso, mincomponentsize))
+            del udf
+        return out
+
     def generate_many(self, noises, N, contexts=None, labels=None, guidance=1.0, n_steps=1000, use_fast_grid_filler=True,
                       noise_schedule="cosine", timings=None, to_host=False, io=None):
         """Several independent batches, software-pipelined on one GPU: while batch i's marching-cubes replays (one warp

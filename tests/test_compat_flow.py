@@ -178,26 +178,39 @@ def test_generate_uncond_flow_with_swapped_imports(tmp_path):
 
 @pytest.mark.gpu
 def test_cli_entry_points_end_to_end(tmp_path):
-    """`python -m sample.generate_uncond` / `generate_text` (surfd_b200.cli.main) with the reference's flags on synthetic
-    checkpoints in the reference's on-disk layouts: full 1000-step sampler, 64^3 extraction, clean-up + output stage, .obj files.
-    The text run uses pre-computed [B,512] embeddings and guidance 2.0 (both forwards of a step in one batched pass)."""
+    """`python -m sample.generate_uncond` / `generate_text` / `generate_image --watertight` (surfd_b200.cli.main) with the
+    reference's flags on synthetic checkpoints in the reference's on-disk layouts: full 1000-step sampler, extraction, clean-up +
+    output stage, .obj files named like the scripts name them.  The text run uses pre-computed [B,512] embeddings and guidance
+    2.0 (both forwards of a step in one batched pass); the image run takes the --watertight branch (udf-only lattice at 256^3,
+    classic marching cubes at 0.01, components under 5000 faces removed) and must produce a closed surface."""
     from surfd_b200 import cli, synth
-    for kind, L, cond, extra in (("uncond", 32, "no_cond", []),
-                                 ("text", 64, "text", ["--guidance_param", "2.0", "--prompt", "a chair"])):
+    for kind, L, cond, extra, names in (
+            ("uncond", 32, "no_cond", [], ["0.obj", "1.obj"]),
+            ("text", 64, "text", ["--guidance_param", "2.0", "--prompt", "a chair."], ["a-chair_0.obj", "a-chair_1.obj"]),
+            ("image", 64, "img", ["--image_path", "somewhere/img12.png", "--watertight"], ["img12.obj"])):
         model_path, ae_dir, out = str(tmp_path / f"model_{kind}.pt"), str(tmp_path / f"ae_{kind}.pt"), str(tmp_path / f"out_{kind}")
         torch.save(synth.synth_mdm(L, cond), model_path)
         torch.save(synth.synth_ae_poly(L), ae_dir)
-        argv = ["--model_path", model_path, "--ae_dir", ae_dir, "--output_dir", out, "--cond_mode", cond, "--num_samples", "2",
-                "--resolution", "64", "--precision", "tf32"] + extra
-        if kind == "text":
+        n = len(names)
+        argv = ["--model_path", model_path, "--ae_dir", ae_dir, "--output_dir", out, "--cond_mode", cond, "--num_samples", str(n),
+                "--resolution", "256" if kind == "image" else "64", "--precision", "tf32"] + extra
+        if kind != "uncond":
             ctx_path = str(tmp_path / "ctx.pt")
-            torch.save(0.5 * torch.randn(2, 512, generator=torch.Generator().manual_seed(3)), ctx_path)
+            torch.save(0.5 * torch.randn(n, 512, generator=torch.Generator().manual_seed(3)), ctx_path)
             argv += ["--context_path", ctx_path]
         cli.main(kind, argv)
-        for k in range(2):
-            p = os.path.join(out, f"{k}.obj")
+        for name in names:
+            p = os.path.join(out, name)
             assert os.path.exists(p), p
             lines = open(p).read().splitlines()
             nv = sum(1 for ln in lines if ln.startswith("v "))
             nf = sum(1 for ln in lines if ln.startswith("f "))
-            assert nv > 500 and nf > 1000, (kind, k, nv, nf)
+            assert nv > 500 and nf > 1000, (kind, name, nv, nf)
+            if kind == "image":
+                from surfd_b200.output import read_obj
+                v, f = read_obj(p)
+                assert nf >= 5000 and float(v.max()) > 2.0          # lattice-index units, like the reference's export
+                e = torch.cat([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+                _, c = torch.unique(e.min(1).values * v.shape[0] + e.max(1).values, return_counts=True)
+                inside = (v.min() > 0) and (v.max() < 255)
+                assert not inside or (int(c.min()) == 2 and int(c.max()) == 2), "open edges in the watertight shell"
