@@ -255,7 +255,7 @@ def bench_gpu(args):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    kname = ("tc_chain_kernel (tcgen05 kind::tf32, the ten 512x512 layers of a pass per cooperative launch" if args.precision == "tf32"
+    kname = ("tc_chain_kernel (tcgen05 kind::tf32, the ten 512x512 layers of a pass per launch, every CTA running all layers on its own 128-row panels" if args.precision == "tf32"
              else "sgemm_nt_kernel (fp32 FFMA")
     roofline_decoder = {"bound": "tensor", "kernel": kname + ", decoder 512x512 layers, fused bias+residual+CBN+ReLU epilogue)",
                 "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),

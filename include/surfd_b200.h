@@ -54,7 +54,7 @@ int surfd_dec_set_precision(surfd_decoder* d, int mode);
 /* grid size of the persistent tcgen05 GEMM (0 = every SM): leave SMs to concurrently running marching-cubes replays */
 int surfd_dec_set_sm_budget(surfd_decoder* d, int n_sms);
 int surfd_dec_num_sms(surfd_decoder* d);
-/* TF32 mode: 1 (default) = all 512x512 layers of a pass in one cooperative launch (grid barrier between layers), 0 = one launch
+/* TF32 mode: 1 (default) = all 512x512 layers of a pass in one launch (each CTA runs every layer on its own 128-row panels), 0 = one launch
  * per layer; bit-identical results */
 int surfd_dec_set_chain(surfd_decoder* d, int on);
 

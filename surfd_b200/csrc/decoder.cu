@@ -425,7 +425,7 @@ struct surfd_decoder {
   DevBuf wR;         // TF32-rounded (rna) copies for the tensor-core path: 5x{W0, W1}, then 5x{W0T, W1T}
   DevBuf err;        // int error flag written by the tcgen05 kernel's bounded waits
   DevBuf gsync;      // grid-barrier word of the layer-chain kernel
-  int chain = 1;     // TF32 mode: 1 (default) = all 512x512 layers of a pass in one cooperative launch (tc_chain_kernel: no launch gaps,
+  int chain = 1;     // TF32 mode: 1 (default) = all 512x512 layers of a pass in one launch (tc_chain_kernel, CTA-owned row panels: no launch gaps,
                      // no pipeline refill per layer; 9 % faster at 107,520-point chunks), 0 = one launch per layer
   DevBuf vflag;      // face filter: per-vertex "udf > 1/N" flags
   bool profiling = false;             // surfd_dec_profile: event pair around every 512x512 layer GEMM
@@ -633,7 +633,7 @@ extern "C" int surfd_dec_set_sm_budget(surfd_decoder* d, int n_sms) {
 }
 extern "C" int surfd_dec_num_sms(surfd_decoder* d) { return d ? d->num_sms : 0; }
 
-// TF32 mode: 1 (default) = the ten 512x512 layers of a pass run in one cooperative launch (tc_chain_kernel, grid barrier between
+// TF32 mode: 1 (default) = the ten 512x512 layers of a pass run in one launch (tc_chain_kernel: each CTA runs all layers on its own row panels, no barrier between
 // layers); 0 = one launch per layer (tc_gemm_kernel).  Same arithmetic, bit-identical results.
 extern "C" int surfd_dec_set_chain(surfd_decoder* d, int on) {
   SURFD_REQUIRE(d != nullptr, "null decoder");
@@ -651,7 +651,7 @@ extern "C" int surfd_dec_set_latent(surfd_decoder* d, const float* lat_dev, void
   return 0;
 }
 
-// n consecutive 512x512 layers over the same M rows: one cooperative launch in TF32 mode (tc_chain_kernel), else one GEMM
+// n consecutive 512x512 layers over the same M rows: one launch in TF32 mode (tc_chain_kernel), else one GEMM
 // launch per layer.
 static int layer_chain(surfd_decoder* d, const float* const* A, const float* const* W, const float* const* Wr, const Epilogue* e, int n,
                        int M, cudaStream_t st) {

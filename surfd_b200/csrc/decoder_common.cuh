@@ -33,8 +33,8 @@ __device__ __forceinline__ float round_to_tf32(float x) {
 // decoder_tc.cu: A [M][512], W [512][512] (both K contiguous), persistent tcgen05 kernel
 int launch_gemm_tc(const float* A, const float* W, int M, const Epilogue& e, int* err_flag, int num_sms, cudaStream_t st);
 
-// decoder_tc.cu: n consecutive layers over the same rows in ONE cooperative launch (grid barrier between layers; the chunk's
-// activations stay in L2).  gsync: one device word, zeroed by the call.
+// decoder_tc.cu: n consecutive ROW-LOCAL layers over the same rows in ONE launch (each CTA runs all layers on its own 128-row panels, so no CTA
+// depends on another one).  gsync: unused (kept for the signature).
 int launch_chain_tc(const float* const* A, const float* const* W, const Epilogue* e, int n, int M, unsigned* gsync, int* err_flag,
                     int num_sms, cudaStream_t st);
 

@@ -103,8 +103,8 @@ class UdfDecoder:
         _lib.check(self.lib.surfd_dec_set_precision(self._h, int(mode)))
 
     def set_chain(self, on):
-        """TF32 mode: True (default) = the ten 512x512 layers of a pass in ONE cooperative launch (tc_chain_kernel: grid barrier
-        between layers, no launch gaps); False = one launch per layer.  Bit-identical results."""
+        """TF32 mode: True (default) = the ten 512x512 layers of a pass in ONE launch (tc_chain_kernel: every CTA walks its own
+        128-row panels through all layers -- no launch gaps, no grid barrier); False = one launch per layer.  Bit-identical results."""
         _lib.check(self.lib.surfd_dec_set_chain(self._h, 1 if on else 0))
 
     def set_sm_budget(self, n_sms):

@@ -33,10 +33,11 @@ class SurfDPipeline:
         self.sampler = U.UNetSampler(mdm_state, latent_dim, cond_mode, num_actions, device=device, max_batch=max_batch,
                                      packed=packed_unet)
         # leave one SM per concurrent marching-cubes replay to the persistent decoder GEMM's budget and size the point chunk
-        # to whole tiles per CTA: (148 - 8) CTAs x 9 x 128 rows (layer-chain kernel: 24.9-25.0 ms per 256^3 lattice at 161k-215k points, 25.8 at 107k)
+        # to an EVEN number of 128-row panels per CTA (the layer-chain kernel interleaves two panels): (148 - 8) CTAs x 10 x 128 rows
+        # (profiles/r2_probe_panels.log: 512^3 lattice 88.4 ms at 9 panels per CTA, 87.6 at 10, 86.9 at 16)
         n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         budget = max(1, n_sms - mc_parallel)
-        self.decoder = UdfDecoder(ae_state, latent_dim, device=device, packed=packed_decoder, max_chunk_points=budget * 1152)
+        self.decoder = UdfDecoder(ae_state, latent_dim, device=device, packed=packed_decoder, max_chunk_points=budget * 1280)
         self.decoder.set_sm_budget(budget)
         # the persistent sampler kernel (one CTA per SM, cooperative launch) leaves the same SMs free: the marching-cubes
         # replays of the previous batch keep running next to it instead of delaying its launch

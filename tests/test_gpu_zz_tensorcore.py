@@ -97,7 +97,7 @@ def test_tf32_poly_lattice_and_mesh_match_fp32_topology():
 
 
 def test_layer_chain_kernel_is_bit_identical_to_per_layer_launches():
-    """tc_chain_kernel (all ten 512x512 layers of a pass in one cooperative launch, grid barrier between layers, optional
+    """tc_chain_kernel (all ten 512x512 layers of a pass in one launch, each CTA walking its own 128-row panels through every layer, optional
     path: set_chain) performs the same MMAs and epilogues in the same order as ten tc_gemm_kernel launches."""
     L = 32
     sd = synth.synth_ae_rand(L, 4321)["decoder"]
