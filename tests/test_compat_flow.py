@@ -176,6 +176,30 @@ def test_generate_uncond_flow_with_swapped_imports(tmp_path):
         get_mesh_from_udf(wrong, N=64, differentiable=False)
 
 
+def test_cli_flags_and_output_names_follow_the_scripts():
+    """generate_args() takes the reference's flags (utils/parser_util.py:40-170, incl. the parse_and_load_from_model rule
+    `cond_mask_prob == 0 -> guidance_param = 1`), and every script's output file is named like the reference names it
+    (generate_uncond.py:114, generate_cat.py:21-29,121, generate_sketch.py:124,145, generate_image.py:92-94,147, generate_text.py:130)."""
+    from surfd_b200 import cli
+    base = ["--model_path", "m.pt", "--ae_dir", "ae.pt", "--output_dir", "out"]
+    a = cli.generate_args(base + ["--cond_mode", "no_cond", "--guidance_param", "3.0"])
+    assert a.guidance_param == 1 and a.resolution == 512 and a.num_samples == 1 and not a.watertight
+    assert cli.mesh_path_for(a, "uncond", 3, 8) == os.path.join("out", "3.obj")
+    a = cli.generate_args(base + ["--cond_mode", "category", "--category", "6"])
+    assert cli.mesh_path_for(a, "cat", 0, 1) == os.path.join("out", "long_pants", "0.obj")
+    a = cli.generate_args(base + ["--cond_mode", "sketch", "--sketch_path", "data/sketches/dress_07.png"])
+    assert cli.mesh_path_for(a, "sketch", 0, 1) == os.path.join("out", "sketch_dress_07.obj")
+    a = cli.generate_args(base + ["--cond_mode", "img", "--image_path", "imgs/chair.v2.jpg", "--watertight", "--cond_mask_prob", "0.1",
+                                  "--guidance_param", "2.5"])
+    assert a.watertight and a.guidance_param == 2.5
+    assert cli.mesh_path_for(a, "image", 0, 1) == os.path.join("out", "chair.obj")           # img_name.split('.')[0]
+    assert cli.mesh_path_for(a, "image", 1, 2) == os.path.join("out", "chair_1.obj")
+    a = cli.generate_args(base + ["--cond_mode", "text", "--prompt", "a round table. with four legs"])
+    assert cli.mesh_path_for(a, "text", 2, 4) == os.path.join("out", "a-round-table-with-four-legs_2.obj")
+    with pytest.raises(SystemExit):
+        cli.generate_args(base)                                                                # --cond_mode is required
+
+
 @pytest.mark.gpu
 def test_cli_entry_points_end_to_end(tmp_path):
     """`python -m sample.generate_uncond` / `generate_text` / `generate_image --watertight` (surfd_b200.cli.main) with the
