@@ -6,14 +6,15 @@ reference's flags (utils/parser_util.py:40-170: --model_path --output_dir --cond
 What runs here: reverse diffusion -> UDF lattice -> MeshUDF marching cubes -> UDF face filter (the hot path), then the
 reference's mesh clean-up (meshudf.py:379-434, surfd_b200/meshclean.py) and output stage (Laplacian smoothing, removal of
 components under 2500 faces, .obj; generate_uncond.py:113-122, surfd_b200/output.py) on the device -- both restated from the
-documented behaviour of trimesh / pymeshlab, which are absent here (parity unpinned).  The CLIP encoders are outside this
-path, so conditional modes take pre-computed 512-d embeddings through --context_path (or use an installed `clip` package).
+documented behaviour of trimesh / pymeshlab, which are absent here (parity unpinned).  The CLIP ViT-B/32 conditioning step of the text / image /
+sketch scripts runs on the device through surfd_b200/clip_encoder.py (--clip_path: the weights are not shipped; --clip_vocab: the
+BPE merges file for text), once per generation; --context_path takes pre-computed 512-d embeddings instead.
 `--watertight` (generate_image.py / generate_text.py:132-158: udf lattice -> `mcubes.marching_cubes(udf, 0.01)` -> components
 under 5000 faces removed) runs on the device through surfd_b200/watertight.py for the two scripts that have the flag
 (parity unpinned: PyMCubes absent); the other three scripts parse and ignore it, like the reference.
 File names follow the scripts: {k}.obj, <category name>/{k}.obj, sketch_<sketch file stem>.obj, <image file stem>.obj,
 <prompt with dashes>_{k}.obj (the sketch / image scripts produce ONE shape; with --num_samples > 1 a _{k} suffix is added).
-Extra flags: --context_path, --dense_grid (use_fast_grid_filler=False), --precision {fp32,tf32}, --raw_mesh (stop at the
+Extra flags: --context_path, --clip_path, --clip_vocab, --dense_grid (use_fast_grid_filler=False), --precision {fp32,tf32}, --raw_mesh (stop at the
 meshudf.py:379 boundary).
 Multi-GPU: launch with torchrun; samples are sharded contiguously over ranks; rank 0 alone reads the two checkpoints and
 packs them, the flat blobs reach the other ranks through ONE NCCL broadcast each (surfd_b200.dist.broadcast_packed).
@@ -65,6 +66,8 @@ def generate_args(argv=None):
     g.add_argument("--sigma_small", default=True, type=bool)
     g = p.add_argument_group("surfd_b200 extensions")
     g.add_argument("--context_path", default=None, type=str, help="torch file with pre-computed [B,512] CLIP embeddings")
+    g.add_argument("--clip_path", default=None, type=str, help="OpenAI CLIP ViT-B/32 checkpoint (ViT-B-32.pt); default: $SURFD_CLIP_PATH, ~/.cache/clip/ViT-B-32.pt")
+    g.add_argument("--clip_vocab", default=None, type=str, help="bpe_simple_vocab_16e6.txt.gz of a CLIP install (text mode)")
     g.add_argument("--dense_grid", action="store_true", help="use_fast_grid_filler=False (dense lattice)")
     g.add_argument("--precision", default="fp32", choices=["fp32", "tf32"], help="decoder GEMM precision")
     g.add_argument("--raw_mesh", action="store_true", help="write the mesh at the meshudf.py:379 boundary (no clean-up / smoothing)")
@@ -105,7 +108,17 @@ def mesh_path_for(args, kind, k, B):
     return os.path.join(args.output_dir, f"{k}.obj")
 
 
+def _clip_checkpoint(args):
+    for c in (args.clip_path, os.environ.get("SURFD_CLIP_PATH"), os.path.expanduser("~/.cache/clip/ViT-B-32.pt")):
+        if c and os.path.exists(c):
+            return c
+    return None
+
+
 def _context(args, kind, B, device):
+    """[B, 512] conditioning: pre-computed embeddings (--context_path), or the scripts' own CLIP ViT-B/32 step on the device
+    (surfd_b200/clip_encoder.py: generate_text.py:97 + mdm.py:86-97, generate_image.py:92-115, generate_sketch.py:74-82) -- once per
+    generation, not once per denoiser call"""
     if args.context_path:
         ctx = torch.load(args.context_path, map_location="cpu")
         ctx = torch.as_tensor(ctx, dtype=torch.float32).reshape(-1, 512)
@@ -114,17 +127,24 @@ def _context(args, kind, B, device):
         if ctx.shape[0] < B:
             raise SystemExit(f"--context_path holds {ctx.shape[0]} embeddings but {B} samples were requested")
         return ctx[:B].contiguous()
-    try:
-        import clip  # noqa: F401  (not shipped here)
-    except Exception:
-        raise SystemExit(f"cond_mode={kind}: the CLIP encoders are outside this path; pass --context_path with [B,512] embeddings")
-    model, preprocess = clip.load("ViT-B/32", device="cpu", jit=False)
-    with torch.no_grad():
-        if kind == "text":
-            return model.encode_text(clip.tokenize([args.prompt] * B, truncate=True)).float()
-        from PIL import Image
-        img = preprocess(Image.open(args.image_path or args.sketch_path)).unsqueeze(0)
-        return model.encode_image(img).float().repeat(B, 1)
+    ckpt = _clip_checkpoint(args)
+    if ckpt is None:
+        raise SystemExit(f"cond_mode={kind}: no CLIP ViT-B/32 checkpoint (weights are not shipped): pass --clip_path / set SURFD_CLIP_PATH, "
+                         "or pass --context_path with pre-computed [B,512] embeddings")
+    from . import clip_encoder as CE
+    enc = CE.ClipEncoder.from_file(ckpt, device)
+    if kind == "text":
+        if not args.prompt:
+            raise SystemExit("--prompt is required for generate_text")
+        tok = CE.Tokenizer(CE.find_vocab(args.clip_vocab or ckpt))
+        return enc.encode_text(tok.tokenize([args.prompt] * B, truncate=True)).float()
+    if kind == "image":
+        if not (args.image_path and args.mask_path):
+            raise SystemExit("--image_path and --mask_path are required for generate_image")
+        return enc.encode_image(CE.image_condition(args.image_path, args.mask_path)).float().repeat(B, 1)
+    if not args.sketch_path:
+        raise SystemExit("--sketch_path is required for generate_sketch")
+    return enc.encode_image(CE.sketch_condition(args.sketch_path)).float().repeat(B, 1)
 
 
 def main(kind, argv=None):
@@ -181,7 +201,11 @@ def main(kind, argv=None):
     noise = torch.randn(1001, B, latent, generator=gen)[:, lo:hi].contiguous()
     ctx = lab = None
     if kind in ("sketch", "image", "text"):
-        ctx = _context(args, kind, B, dev)[lo:hi]
+        # rank 0 encodes (one CLIP pass per generation), the [B,512] result reaches the other ranks by one broadcast
+        ctx = _context(args, kind, B, dev).to(dev) if rank == 0 else torch.empty(B, 512, device=dev)
+        if world > 1:
+            dist.broadcast(ctx, src=0)
+        ctx = ctx[lo:hi]
     if kind == "cat":
         if not 0 <= args.category < args.num_actions:
             raise IndexError(f"--category {args.category} outside [0, {args.num_actions})")

@@ -1,0 +1,12 @@
+"""`import mcubes` of the `--watertight` branch (sample/generate_text.py:138-139): marching_cubes(volume, isovalue) ->
+(vertices float64 [V,3] in index units, triangles [F,3]) as numpy arrays, computed on the device by surfd_b200.watertight
+(classic marching cubes; vertex / face ORDER is not PyMCubes' scan order -- parity unpinned, the package is absent here)."""
+import numpy as np
+import torch
+
+
+def marching_cubes(volume, isovalue):
+    from ...watertight import marching_cubes as _mc
+    dev = volume.device if torch.is_tensor(volume) and volume.is_cuda else ("cuda" if torch.cuda.is_available() else "cpu")
+    v, f = _mc(torch.as_tensor(np.asarray(volume.detach().cpu()) if torch.is_tensor(volume) and not volume.is_cuda else volume).to(dev), isovalue)
+    return v.cpu().numpy(), f.cpu().numpy().astype(np.uint64)

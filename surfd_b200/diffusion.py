@@ -43,7 +43,7 @@ class MDM:
         self.cond_mode = kargs.get("cond_mode", "no_cond")
         self.cond_mask_prob = kargs.get("cond_mask_prob", 0.0)
         self.clip_version = clip_version
-        self.clip_model = None      # the CLIP encoders are outside this path: conditioning arrives as y['context']
+        self.clip_model = None      # loaded on the first encode_text (surfd_b200.compat.clip); img / sketch conditioning arrives as y['context']
         self._state = None
         self._device = None
         self._samplers = {}         # latent length -> UNetSampler
@@ -111,8 +111,23 @@ class MDM:
         return s
 
     def encode_text(self, raw_text):
-        raise RuntimeError("cond_mode='text': the CLIP text encoder is outside this path (SURVEY.md 8(f)); pass the 512-d "
-                           "embeddings as y['context'] (they are constant over the 1000 steps, mdm.py:96-97)")
+        """mdm.py:86-89: clip_model.encode_text(clip.tokenize(raw_text, truncate=True)).float() -- which the reference re-runs
+        inside every one of the 1000 denoiser calls (mdm.py:96-97); here the embedding of a prompt list is computed once and
+        kept.  The weights are not shipped: surfd_b200.compat.clip.load finds them through $SURFD_CLIP_PATH."""
+        key = tuple(raw_text) if not isinstance(raw_text, str) else (raw_text,)
+        hit = self._text_cache.get(key) if hasattr(self, "_text_cache") else None
+        if hit is not None:
+            return hit
+        from .compat import clip
+        if self.clip_model is None:
+            try:
+                self.clip_model, _ = clip.load(self.clip_version or "ViT-B/32", device=self._device or "cuda", jit=False)
+            except RuntimeError as e:
+                raise RuntimeError("cond_mode='text': %s; or pass the 512-d embeddings as y['context'] (they are constant over the "
+                                   "1000 steps)" % e)
+        emb = self.clip_model.encode_text(clip.tokenize(list(key), truncate=True)).float()
+        self._text_cache = {key: emb}
+        return emb
 
     def conditioning(self, y, batch):
         """(context [B,512] or None, labels [B] or None) from the reference's model_kwargs['y'] dict (mdm.py:91-110)"""

@@ -202,3 +202,51 @@ def synth_mdm(L=32, cond_mode="no_cond", seed=1234, num_actions=9):
         else:
             sd[k] = _fill(shp, gen, "bias")
     return sd
+
+
+def synth_clip(seed=77, vision=(768, 12, 32, 7), text=(512, 12), embed_dim=512, context_length=77, vocab_size=49408):
+    """All-parameter-randomised CLIP checkpoint in the OpenAI state-dict layout (CLIP/clip/model.py:399-436 reads the
+    configuration off these shapes).  Defaults = ViT-B/32: vision (width 768, 12 layers, patch 32, 7 x 7 grid = 224 px),
+    text (width 512, 12 layers), 512-d embedding, 77 tokens, 49,408-entry vocabulary.  Matrices ~ N(0,1)/sqrt(fan_in),
+    biases ~ 0.02 N(0,1), LayerNorm weights 1 + 0.1 N(0,1) and biases 0.05 N(0,1), so that every parameter matters.
+    Every value is fp16-representable, like the published checkpoints (stored in half precision; build_model casts the
+    matrices to fp16 on load and `clip.load(device='cpu')` widens them again)."""
+    gen = torch.Generator().manual_seed(seed)
+    rn = lambda *shape: torch.randn(*shape, generator=gen)
+    vw, vl, patch, grid = vision
+    tw, tl = text
+    sd = {}
+
+    def blocks(prefix, width, layers):
+        for i in range(layers):
+            p = f"{prefix}.resblocks.{i}."
+            sd[p + "attn.in_proj_weight"] = rn(3 * width, width) / width ** 0.5
+            sd[p + "attn.in_proj_bias"] = 0.02 * rn(3 * width)
+            sd[p + "attn.out_proj.weight"] = rn(width, width) / width ** 0.5
+            sd[p + "attn.out_proj.bias"] = 0.02 * rn(width)
+            sd[p + "ln_1.weight"] = 1 + 0.1 * rn(width)
+            sd[p + "ln_1.bias"] = 0.05 * rn(width)
+            sd[p + "mlp.c_fc.weight"] = rn(4 * width, width) / width ** 0.5
+            sd[p + "mlp.c_fc.bias"] = 0.02 * rn(4 * width)
+            sd[p + "mlp.c_proj.weight"] = rn(width, 4 * width) / (4 * width) ** 0.5
+            sd[p + "mlp.c_proj.bias"] = 0.02 * rn(width)
+            sd[p + "ln_2.weight"] = 1 + 0.1 * rn(width)
+            sd[p + "ln_2.bias"] = 0.05 * rn(width)
+
+    sd["visual.class_embedding"] = rn(vw) / vw ** 0.5
+    sd["visual.positional_embedding"] = rn(grid * grid + 1, vw) / vw ** 0.5
+    sd["visual.proj"] = rn(vw, embed_dim) / vw ** 0.5
+    sd["visual.conv1.weight"] = rn(vw, 3, patch, patch) / (3 * patch * patch) ** 0.5
+    sd["visual.ln_pre.weight"] = 1 + 0.1 * rn(vw)
+    sd["visual.ln_pre.bias"] = 0.05 * rn(vw)
+    blocks("visual.transformer", vw, vl)
+    sd["visual.ln_post.weight"] = 1 + 0.1 * rn(vw)
+    sd["visual.ln_post.bias"] = 0.05 * rn(vw)
+    sd["token_embedding.weight"] = 0.5 * rn(vocab_size, tw)
+    sd["positional_embedding"] = 0.1 * rn(context_length, tw)
+    blocks("transformer", tw, tl)
+    sd["ln_final.weight"] = 1 + 0.1 * rn(tw)
+    sd["ln_final.bias"] = 0.05 * rn(tw)
+    sd["text_projection"] = rn(tw, embed_dim) / tw ** 0.5
+    sd["logit_scale"] = torch.tensor(2.6593)
+    return {k: v.half().float() for k, v in sd.items()}
