@@ -7,6 +7,11 @@ import torch
 
 def marching_cubes(volume, isovalue):
     from ...watertight import marching_cubes as _mc
-    dev = volume.device if torch.is_tensor(volume) and volume.is_cuda else ("cuda" if torch.cuda.is_available() else "cpu")
-    v, f = _mc(torch.as_tensor(np.asarray(volume.detach().cpu()) if torch.is_tensor(volume) and not volume.is_cuda else volume).to(dev), isovalue)
+    if torch.is_tensor(volume) and volume.is_cuda:
+        vol = volume
+    else:
+        if not torch.cuda.is_available():
+            raise RuntimeError("surfd_b200 has no CPU path: mcubes.marching_cubes runs on the CUDA device")
+        vol = torch.as_tensor(volume).to("cuda")
+    v, f = _mc(vol, isovalue)
     return v.cpu().numpy(), f.cpu().numpy().astype(np.uint64)
