@@ -182,3 +182,51 @@ def test_mdm_encode_text_runs_once_per_prompt_list(tmp_path, monkeypatch):
     m2._device = "cpu"
     with pytest.raises(RuntimeError, match="weights are not shipped"):
         m2.encode_text(["a chair"])
+
+
+REF = "/root/reference"
+
+
+def _ref_module(name, rel):
+    import importlib.util, sys, types
+    sys.modules.setdefault("ftfy", types.SimpleNamespace(fix_text=lambda s: s))      # absent here; identity on the strings below
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "CLIP", "clip")), reason="reference tree not present (GPU box)")
+def test_tokenizer_against_the_live_reference_tokenizer():
+    """the reference's own SimpleTokenizer, imported where it lies, on strings that exercise every branch of the pre-tokeniser:
+    contractions, digits (one token each), punctuation runs, non-ASCII letters, HTML entities (unescaped twice), whitespace runs,
+    the special tokens, upper case"""
+    ref = _ref_module("ref_clip_tok_live", "CLIP/clip/simple_tokenizer.py").SimpleTokenizer()
+    tok = Tokenizer(os.path.join(REF, "CLIP", "clip", "bpe_simple_vocab_16e6.txt.gz"))
+    texts = ["a chair", "A CHAIR!!!", "it's they're we've I'm you'll he'd isn't", "table no. 42 costs 1999.99$", "  many   spaces\t\nand lines ",
+             "caf\u00e9 na\u00efve \u00fcber stra\u00dfe", "&amp;lt;b&amp;gt; bold &lt;i&gt;", "<|startoftext|> a lamp <|endoftext|>", "...---???", "x",
+             "\u65e5\u672c\u8a9e \u306e \u6905\u5b50", "emoji \U0001F600 chair", "supercalifragilisticexpialidocious antidisestablishmentarianism",
+             "a sofa with 3 seats, 2 arm-rests & a foot_stool (dark-grey)"]
+    for t in texts:
+        assert tok.encode(t) == ref.encode(t), t
+    assert tok.encoder == ref.encoder
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "CLIP", "clip")), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("seed", [1, 2])
+def test_encoders_against_the_live_reference_model(seed):
+    """the reference's own build_model / CLIP on a small seeded configuration (2 + 2 layers), random images and token rows with
+    the end-of-text token at different positions"""
+    model_py = _ref_module("ref_clip_model_live", "CLIP/clip/model.py")
+    sd = synth.synth_clip(seed, vision=(128, 2, 32, 3), text=(128, 2), embed_dim=64)
+    ref = model_py.build_model({k: v.clone() for k, v in sd.items()}).float()
+    enc = ClipEncoder(sd, device="cpu")
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(3, 3, 96, 96, generator=g)
+    tokens = torch.randint(1, 49000, (4, 77), generator=g)
+    for i, pos in enumerate((3, 20, 76, 40)):
+        tokens[i, pos] = 49407
+        tokens[i, pos + 1:] = 0
+    with torch.no_grad():
+        assert float((ref.encode_image(images) - enc.encode_image(images)).abs().max()) < 2e-5
+        assert float((ref.encode_text(tokens) - enc.encode_text(tokens)).abs().max()) < 2e-5

@@ -83,3 +83,25 @@ def test_small_components_are_removed_and_negative_values_clamped():
     c, consistent = _edge_counts(f, v.shape[0])
     assert int(c.min()) == 2 and int(c.max()) == 2 and consistent
     assert v.dtype == torch.float32 and f.dtype == torch.int64 and int(f.max()) == v.shape[0] - 1
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_fields_give_closed_oriented_surfaces_away_from_the_lattice_boundary(seed):
+    """the 256-entry table is consistent on ambiguous faces: whatever the field, every interior edge of the extracted surface is
+    shared by exactly two faces running in opposite directions (edges on the lattice boundary may be open)"""
+    g = torch.Generator().manual_seed(100 + seed)
+    vol = torch.nn.functional.interpolate(torch.rand(1, 1, 7, 7, 7, generator=g), size=(24, 24, 24), mode="trilinear", align_corners=True)[0, 0]
+    vol = vol + 0.15 * torch.rand(24, 24, 24, generator=g)                 # noise: many ambiguous cubes
+    v, f = marching_cubes(vol, 0.55)
+    assert f.shape[0] > 500
+    e = torch.cat([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    nv = v.shape[0]
+    on_boundary = ((v <= 0) | (v >= 23)).any(1)
+    und = e.min(1).values * nv + e.max(1).values
+    uniq, inv, cnt = torch.unique(und, return_inverse=True, return_counts=True)
+    interior = ~(on_boundary[e[:, 0]] & on_boundary[e[:, 1]])
+    assert bool((cnt[inv][interior] == 2).all())
+    directed = e[:, 0] * nv + e[:, 1]
+    assert torch.unique(directed).numel() == directed.numel()
+    ov, of = marching_cubes_loop(vol.numpy(), 0.55)
+    assert canonical_faces(v.numpy(), f.numpy()) == canonical_faces(ov, of)
