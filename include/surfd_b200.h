@@ -181,6 +181,18 @@ int surfd_sample(surfd_unet* u, int B, int n_steps, const int64_t* tmap_dev, con
 /* kernel-launch counter (all kernels launched by this library since load / last reset) */
 int64_t surfd_launch_count(int reset);
 
+/* ---- output stage, host side (no device work): the Wavefront .obj text conversion of o3d.io.write_triangle_mesh
+ * (utils/utils.py:79-121, sample/generate_uncond.py:113-116) and of pymeshlab's load_new_mesh / save_current_mesh
+ * (generate_uncond.py:117-122).  The layouts are the callers' (surfd_b200/output.py). */
+/* header + nv lines "v x y z" + mid + nf lines "f a b c" (indices written 1-based) + footer.  number_format 0 = "%f"
+ * (MeshLab exporter), 1 = "%g" (C++ ostream default: open3d).  verts: HOST double [nv][3]; faces: HOST int64 [nf][3], 0-based.
+ * header / mid / footer may be NULL. */
+int surfd_obj_write(const char* path, const char* header, const double* verts, int64_t nv, int number_format,
+                    const char* mid, const int64_t* faces, int64_t nf, const char* footer);
+/* `v x y z` and `f a[/..] b[/..] c[/..]` records (1-based), everything else skipped.  Call with verts = faces = NULL for the
+ * counts (*nv, *nf), then with HOST buffers of those sizes (double [nv][3], int64 [nf][3], 0-based on return). */
+int surfd_obj_read(const char* path, int64_t* nv, int64_t* nf, double* verts, int64_t* faces);
+
 #ifdef __cplusplus
 }
 #endif

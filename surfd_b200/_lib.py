@@ -55,6 +55,8 @@ PROTOTYPES = {
     "surfd_unet_packed_floats": (ctypes.c_size_t, []),
     "surfd_unet_forward": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "surfd_sample": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_float, c_vp, c_vp]),
+    "surfd_obj_write": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, c_vp, c_i64, ctypes.c_int, ctypes.c_char_p, c_vp, c_i64, ctypes.c_char_p]),
+    "surfd_obj_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_vp, c_vp]),
 }
 
 SURFD_OK, SURFD_EMPTY_SURFACE, SURFD_CAPACITY, SURFD_QUEUE_OVERFLOW, SURFD_BAD_ARGUMENT = 0, 1, 2, 3, 4

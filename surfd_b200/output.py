@@ -48,9 +48,30 @@ def _fmt_g(arr):
     return np.char.mod("%g", arr)
 
 
+def _native_write(path, header, v64, number_format, mid, f64, footer):
+    """the text conversion runs in the C library (csrc/objio.cu: surfd_obj_write); v64 float64 [V,3], f64 int64 [F,3] 0-based, host"""
+    import ctypes
+    import numpy as np
+    from . import _lib
+    v64 = np.ascontiguousarray(v64, dtype=np.float64).reshape(-1, 3)
+    f64 = np.ascontiguousarray(f64, dtype=np.int64).reshape(-1, 3)
+    _lib.check(_lib.load().surfd_obj_write(os.fsencode(path), header.encode(), ctypes.c_void_p(v64.ctypes.data), v64.shape[0], int(number_format),
+                                           mid.encode(), ctypes.c_void_p(f64.ctypes.data), f64.shape[0], footer.encode()))
+
+
 def write_obj_o3d(path, vertices, triangles):
     """open3d 0.18.0 WriteTriangleMeshToOBJ layout (cpp/open3d/io/file_format/FileOBJ.cpp) for a mesh without normals,
-    colours or uvs: 4 comment lines, `v x y z` with default ostream precision, `f a b c` 1-based"""
+    colours or uvs: 4 comment lines, `v x y z` with default ostream precision (%g), `f a b c` 1-based"""
+    v = vertices.detach().to(torch.float64).cpu().numpy()
+    f = triangles.detach().cpu().numpy()
+    name = os.path.splitext(os.path.basename(path))[0]
+    header = "# Created by Open3D \n# object name: %s\n# number of points: %d\n# number of triangles: %d\n" % (name, len(v), len(f))
+    _native_write(path, header, v, 1, "", f, "")
+    return True
+
+
+def _write_obj_o3d_py(path, vertices, triangles):
+    """the same layout formatted by numpy / Python: the specification the native writer is tested against (tests only)"""
     import numpy as np
     v = vertices.detach().to(torch.float64).cpu().numpy()
     f = triangles.detach().cpu().numpy().astype(np.int64) + 1
@@ -76,7 +97,21 @@ class io:   # noqa: N801  (open3d.io)
 
 
 def read_obj(path, device="cpu"):
-    """minimal Wavefront reader (v / f records, 1-based, `a/b/c` tolerated)"""
+    """minimal Wavefront reader (v / f records, 1-based, `a/b/c` tolerated); parsed by the C library (csrc/objio.cu)"""
+    import ctypes
+    import numpy as np
+    from . import _lib
+    lib = _lib.load()
+    nv, nf = ctypes.c_int64(0), ctypes.c_int64(0)
+    _lib.check(lib.surfd_obj_read(os.fsencode(path), ctypes.byref(nv), ctypes.byref(nf), None, None))
+    v = np.empty((nv.value, 3), dtype=np.float64)
+    f = np.empty((nf.value, 3), dtype=np.int64)
+    _lib.check(lib.surfd_obj_read(os.fsencode(path), ctypes.byref(nv), ctypes.byref(nf), ctypes.c_void_p(v.ctypes.data), ctypes.c_void_p(f.ctypes.data)))
+    return torch.from_numpy(v).to(device), torch.from_numpy(f).to(device)
+
+
+def _read_obj_py(path, device="cpu"):
+    """the same reader in Python: the specification the native reader is tested against (tests only)"""
     import numpy as np
     vs, fs = [], []
     with open(path) as fh:
@@ -191,6 +226,15 @@ def remove_small_components(vertices, faces, mincomponentsize=2500, removeunref=
 
 def write_obj_meshlab(path, vertices, faces):
     """MeshLab 2023.12 OBJ exporter layout (vcglib wrap/io_trimesh/export_obj.h) without normals / colours / texture"""
+    import numpy as np
+    v = vertices.detach().to(torch.float32).cpu().numpy().astype(np.float64)
+    f = faces.detach().cpu().numpy()
+    header = "####\n#\n# OBJ File Generated by Meshlab\n#\n####\n# Object %s\n#\n# Vertices: %d\n# Faces: %d\n#\n####\n" % (os.path.basename(path), len(v), len(f))
+    _native_write(path, header, v, 0, "# %d vertices, 0 vertices normals\n\n" % len(v), f, "# %d faces, 0 coords texture\n\n# End of File\n" % len(f))
+
+
+def _write_obj_meshlab_py(path, vertices, faces):
+    """the same layout formatted by numpy / Python: the specification the native writer is tested against (tests only)"""
     import numpy as np
     v = vertices.detach().to(torch.float32).cpu().numpy()
     f = faces.detach().cpu().numpy().astype(np.int64) + 1
