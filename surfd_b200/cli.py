@@ -78,15 +78,9 @@ def generate_args(argv=None):
 
 
 def write_obj(path, verts, faces):
-    """minimal Wavefront writer (the reference goes through open3d, utils/utils.py:79-121)"""
-    v = verts.detach().cpu().numpy()
-    f = faces.detach().cpu().numpy() + 1
-    with open(path, "w") as fh:
-        fh.write("# surfd_b200\n")
-        for a in v:
-            fh.write("v %.6f %.6f %.6f\n" % (a[0], a[1], a[2]))
-        for a in f:
-            fh.write("f %d %d %d\n" % (a[0], a[1], a[2]))
+    """minimal Wavefront writer for --raw_mesh (`v %.6f %.6f %.6f`, `f a b c`); text conversion in the C library"""
+    from .output import _native_write
+    _native_write(path, "# surfd_b200\n", verts.detach().to(torch.float64).cpu().numpy(), 0, "", faces.detach().cpu().numpy(), "")
 
 
 CAT2NAME = {0: "long_sleeve_upper", 1: "short_sleeve_upper", 2: "no_sleeve_upper", 3: "long_sleeve_dress", 4: "short_sleeve_dress",
