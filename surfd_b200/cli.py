@@ -195,13 +195,8 @@ def main(kind, argv=None):
     noise = torch.randn(1001, B, latent, generator=gen)[:, lo:hi].contiguous()
     ctx = lab = None
     if kind in ("sketch", "image", "text"):
-        if world == 1:
-            ctx = _context(args, kind, B, dev)[lo:hi]
-        else:
-            # rank 0 encodes (one CLIP pass per generation), the [B,512] result reaches the other ranks by one broadcast
-            ctx = _context(args, kind, B, dev).to(dev) if rank == 0 else torch.empty(B, 512, device=dev)
-            dist.broadcast(ctx, src=0)
-            ctx = ctx[lo:hi]
+        from .dist import conditioning_from_rank0
+        ctx = conditioning_from_rank0(lambda: _context(args, kind, B, dev), B, 512, dev, rank, world)[lo:hi]
     if kind == "cat":
         if not 0 <= args.category < args.num_actions:
             raise IndexError(f"--category {args.category} outside [0, {args.num_actions})")

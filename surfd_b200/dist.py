@@ -26,3 +26,23 @@ def broadcast_packed(tensors, src=0):
     for t in tensors:
         dist.broadcast(t, src)
     return tensors
+
+
+def conditioning_from_rank0(make, batch, width, device, rank=None, world=None):
+    """the [batch, width] conditioning tensor (CLIP embeddings): rank 0 alone runs `make()` -- one encoder pass per generation,
+    one copy of the encoder weights per node -- and the result reaches the other ranks through one broadcast; a single
+    process just calls `make()`."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if world > 1 else 0
+    if world == 1:
+        return make()
+    if rank == 0:
+        ctx = make().to(device, torch.float32).contiguous()
+        if tuple(ctx.shape) != (batch, width):
+            raise ValueError(f"conditioning must have shape ({batch}, {width}), got {tuple(ctx.shape)}")
+    else:
+        ctx = torch.empty(batch, width, device=device, dtype=torch.float32)
+    dist.broadcast(ctx, src=0)
+    return ctx

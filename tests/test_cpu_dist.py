@@ -8,7 +8,7 @@ import torch.multiprocessing as mp
 
 from surfd_b200 import synth, unet as U
 from surfd_b200.decoder import pack_decoder
-from surfd_b200.dist import broadcast_packed, shard_range, sliced_noise
+from surfd_b200.dist import broadcast_packed, conditioning_from_rank0, shard_range, sliced_noise
 
 
 def _free_port():
@@ -31,7 +31,14 @@ def _worker(rank, world, port, out):
     broadcast_packed([blob_u, prog, blob_d], 0)
     lo, hi = shard_range(13, world, rank)
     noise = sliced_noise(10, 5, 13, L, lo, hi)
-    torch.save({"sum_u": float(blob_u.double().sum()), "sum_d": float(blob_d.double().sum()), "prog": int(prog.sum()),
+    calls = []
+
+    def make():                     # stands for the CLIP pass: must run on rank 0 only
+        calls.append(rank)
+        return torch.arange(13 * 512, dtype=torch.float32).reshape(13, 512) * 0.5
+
+    ctx = conditioning_from_rank0(make, 13, 512, "cpu")[lo:hi]
+    torch.save({"ctx": ctx, "calls": calls, "sum_u": float(blob_u.double().sum()), "sum_d": float(blob_d.double().sum()), "prog": int(prog.sum()),
                 "lo": lo, "hi": hi, "noise": noise}, out + f".{rank}")
     dist.barrier()
     dist.destroy_process_group()
@@ -46,6 +53,13 @@ def test_two_rank_broadcast_and_sharding(tmp_path):
     assert (r0["lo"], r0["hi"], r1["lo"], r1["hi"]) == (0, 7, 7, 13)                                  # contiguous shards cover the batch
     full = sliced_noise(10, 5, 13, 32, 0, 13)
     assert torch.equal(torch.cat([r0["noise"], r1["noise"]], 1), full)                                # same noise as a single-GPU run
+    assert r0["calls"] == [0] and r1["calls"] == []                                                    # the encoder ran on rank 0 only
+    assert torch.equal(torch.cat([r0["ctx"], r1["ctx"]], 0), torch.arange(13 * 512, dtype=torch.float32).reshape(13, 512) * 0.5)
+
+
+def test_single_process_conditioning_is_a_plain_call():
+    t = torch.ones(3, 512)
+    assert conditioning_from_rank0(lambda: t, 3, 512, "cpu") is t
 
 
 def test_shard_range_edges():
